@@ -1,0 +1,149 @@
+"""ctypes binding of libkta_gpu.so (include/kta.h) + the in-tree nvcc build recipe.
+
+The library is the product; this module only loads it.  There is no Python/CPU implementation of
+the scan anywhere in this package: if the shared object is missing or CUDA is unusable, calls fail
+loudly (KtaError / OSError) instead of falling back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libkta_gpu.so")
+INCLUDE = os.path.normpath(os.path.join(_HERE, "..", "include"))
+
+KTA_KEY_TILE = 1024
+KTA_HIST_BUCKETS = 32
+INT64_MIN = -(1 << 63)
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--cudart", "static",
+]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "kta.h")]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libkta_gpu.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(p) for p in _sources())
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "kta_lib.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+class KtaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kta error {code}: {msg}")
+        self.code = code
+
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_PARTITION, ERR_DIV_BY_ZERO, ERR_NOT_ENABLED, ERR_NOT_FINALIZED = range(8)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("num_partitions", C.c_int32),
+        ("count_alive_keys", C.c_int32), ("hll_precision", C.c_int32), ("reserved0", C.c_int32),
+        ("ring_records", C.c_int64), ("ring_key_bytes", C.c_int64), ("now_s", C.c_int64),
+        ("now_ns", C.c_int32), ("reserved1", C.c_int32),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("seq_base", C.c_uint64), ("partition", C.c_void_p), ("offset", C.c_void_p),
+        ("ts_ms", C.c_void_p), ("key_len", C.c_void_p), ("value_len", C.c_void_p), ("key_bytes", C.c_void_p),
+        ("key_bytes_len", C.c_int64), ("key_tile_base", C.c_void_p), ("seq", C.c_void_p),
+    ]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("n_total", C.c_int64), ("num_partitions", C.c_int32), ("run_len", C.c_int32),
+        ("distinct_keys", C.c_uint64), ("key_mode", C.c_int32), ("value_mean", C.c_int32),
+        ("null_key_per_10k", C.c_int32), ("tombstone_per_10k", C.c_int32), ("ts_missing_per_10k", C.c_int32),
+        ("empty_value_per_10k", C.c_int32),
+    ]
+
+
+# every symbol include/kta.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "kta_last_error": (C.c_char_p, []),
+    "kta_abi_version": (C.c_int, []),
+    "kta_device_count": (C.c_int, []),
+    "kta_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
+    "kta_destroy": (C.c_int, [_P]),
+    "kta_reset": (C.c_int, [_P]),
+    "kta_push": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int32, C.c_int32]),
+    "kta_push_batch_host": (C.c_int, [_P, C.POINTER(Batch)]),
+    "kta_scan_batch_device": (C.c_int, [_P, C.POINTER(Batch)]),
+    "kta_sync": (C.c_int, [_P]),
+    "kta_finalize": (C.c_int, [_P]),
+    "kta_counter": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(C.c_uint64)]),
+    "kta_avg": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(C.c_uint64)]),
+    "kta_dirty_ratio": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float)]),
+    "kta_global": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
+    "kta_timestamps": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "kta_alive_keys": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "kta_hist": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(C.c_uint64)]),
+    "kta_alive_keys_hll": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "kta_hll_registers": (C.c_int, [_P, _P, C.c_size_t]),
+    "kta_fnv32_host": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P]),
+    "kta_merge_words": (C.c_int64, [_P, C.c_int32]),
+    "kta_merge_export_device": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "kta_merge_import_device": (C.c_int, [_P, C.c_int32, _P]),
+    "kta_alive_export_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "kta_alive_export_device": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "kta_alive_import_device": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "kta_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "kta_set_timing": (C.c_int, [_P, C.c_int]),
+    "kta_scan_time_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "kta_stream": (_P, [_P]),
+    "kta_set_stream": (C.c_int, [_P, _P]),
+    "kta_synth_shard_records": (C.c_int64, [C.POINTER(SynthSpec), C.c_int32, C.c_int32]),
+    "kta_synth_fill_host": (C.c_int, [C.POINTER(SynthSpec), C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                      _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "kta_synth_fill_device": (C.c_int, [C.POINTER(SynthSpec), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                        _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    # test hook, not part of kta.h's stable surface
+    "kta_set_hash_capture": (C.c_int, [_P, _P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libkta_gpu.so (building it first if the sources are newer / it is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(_lib, name)  # AttributeError if the export is missing: loud by design
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise KtaError(rc, (lib().kta_last_error() or b"").decode("utf-8", "replace"))

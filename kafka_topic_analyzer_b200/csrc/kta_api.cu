@@ -1,0 +1,969 @@
+// kta_api.cu — host side of libkta_gpu.so: the C ABI of include/kta.h over the sm_100a kernels.
+//
+// Mirrors, for this one path, what the reference's host does around the handlers:
+//   MessageMetrics::new / LogCompactionInMemoryMetrics::new      src/metric.rs:30-46, 267-271
+//   one handle_message per polled record                         src/kafka.rs:107-109
+//   getters + derived values read by the report                  src/metric.rs:104-203, src/main.rs:130-170
+// There is deliberately no CPU implementation of the scan in this file: if CUDA is unusable every
+// compute entry point fails with KTA_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kta_kernels.cuh"
+#include "kta_synth.h"
+
+using namespace kta;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? KTA_ERR_NOMEM : KTA_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
+    } while (0)
+
+extern "C" const char *kta_last_error(void) { return g_err; }
+extern "C" int kta_abi_version(void) { return KTA_ABI_VERSION; }
+extern "C" int kta_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+static constexpr int NCHUNK = 3;
+static constexpr int64_t DEFAULT_RING_RECORDS = 1 << 22;  // 4 Mi records per chunk
+static constexpr int SMEM_FIXED = 2 * 8 + 2 * 8 + WARPS * 8 + WARPS * 4 * 8 + 4 * 4;
+
+struct Chunk {
+    // device staging (shared by kta_push and kta_push_batch_host)
+    int32_t *d_partition = nullptr, *d_klen = nullptr, *d_vlen = nullptr;
+    int64_t *d_ts = nullptr;
+    uint64_t *d_seq = nullptr;
+    uint8_t *d_keys = nullptr;
+    uint64_t *d_tile_base = nullptr;
+    cudaEvent_t free_ev = nullptr;  // recorded after the scan that reads this chunk
+    // pinned landing area for kta_push
+    int32_t *h_partition = nullptr, *h_klen = nullptr, *h_vlen = nullptr;
+    int64_t *h_ts = nullptr;
+    uint8_t *h_keys = nullptr;
+    uint64_t *h_tile_base = nullptr;
+};
+
+struct kta_handle {
+    kta_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    bool need_hash = false;
+    // device state
+    unsigned long long *d_sums = nullptr;
+    long long *d_minmax = nullptr;
+    uint32_t *d_hll = nullptr;
+    unsigned long long *d_alive_table = nullptr;
+    uint8_t *d_alive_dirty = nullptr;
+    unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export counter
+    uint32_t *d_hash_out = nullptr;          // test hook
+    uint64_t *d_tb_scratch = nullptr;        // key_tile_base scratch for device batches
+    int64_t tb_scratch_tiles = 0;
+    size_t nsums = 0, nhll = 0;
+    // landing ring
+    Chunk chunks[NCHUNK];
+    bool ring_dev_ready = false, ring_host_ready = false;
+    int64_t ring_records = 0, ring_key_bytes = 0;
+    int cur = 0;          // chunk being filled by kta_push
+    int64_t cur_n = 0;    // records in it
+    int64_t cur_kb = 0;   // key bytes in it
+    uint64_t next_seq = 0;
+    // host mirror (valid after finalize)
+    bool finalized = false;
+    std::vector<uint64_t> h_sums;
+    long long h_minmax[4] = {0, 0, 0, 0};
+    std::vector<uint32_t> h_hll;
+    uint64_t h_alive = 0;
+    // occupancy-derived grids
+    int grid_scan[2][2] = {{0, 0}, {0, 0}};  // [HASH][SMEM]
+    size_t smem_scan[2][2] = {{0, 0}, {0, 0}};
+    // stats / timing
+    uint64_t launches = 0, records = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    double scan_ms = 0;
+    uint64_t scan_launches_timed = 0;
+};
+
+static int set_device(const kta_handle *h) {
+    CU(cudaSetDevice(h->device));
+    return KTA_OK;
+}
+
+static size_t scan_smem_bytes(bool hash, bool smem, int P) {
+    return (hash ? 2 * (size_t)KEYBUF : 0) + SMEM_FIXED + (smem ? smem_counter_words(P) * 4 : 0);
+}
+
+template <bool HASH, bool SMEM>
+static int prepare_variant(kta_handle *h) {
+    const size_t smem = scan_smem_bytes(HASH, SMEM, h->cfg.num_partitions);
+    CU(cudaFuncSetAttribute(scan_kernel<HASH, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<HASH, SMEM>, THREADS, smem));
+    if (occ < 1) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", smem);
+    h->grid_scan[HASH][SMEM] = occ * h->sm_count;
+    h->smem_scan[HASH][SMEM] = smem;
+    return KTA_OK;
+}
+
+static int state_reset_device(kta_handle *h) {
+    state_init_kernel<<<64, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (h->d_alive_table) {
+        const uint32_t npages = 1u << (32 - DIRTY_SHIFT);
+        alive_clear_kernel<<<h->sm_count * 8, THREADS, 0, h->stream>>>(h->d_alive_table, h->d_alive_dirty, npages);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    return KTA_OK;
+}
+
+static void free_chunk(Chunk &c) {
+    cudaFree(c.d_partition); cudaFree(c.d_klen); cudaFree(c.d_vlen); cudaFree(c.d_ts); cudaFree(c.d_seq);
+    cudaFree(c.d_keys); cudaFree(c.d_tile_base);
+    if (c.free_ev) cudaEventDestroy(c.free_ev);
+    cudaFreeHost(c.h_partition); cudaFreeHost(c.h_klen); cudaFreeHost(c.h_vlen); cudaFreeHost(c.h_ts);
+    cudaFreeHost(c.h_keys); cudaFreeHost(c.h_tile_base);
+    c = Chunk{};
+}
+
+extern "C" int kta_destroy(kta_handle *h) {
+    if (!h) return KTA_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &c : h->chunks) free_chunk(c);
+    cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
+    cudaFree(h->d_alive_dirty); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
+    for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return KTA_OK;
+}
+
+static int create_impl(const kta_config *cfg, kta_handle *h) {
+    h->cfg = *cfg;
+    if (cfg->num_partitions < 1 || cfg->num_partitions > (1 << 20))
+        return fail(KTA_ERR_INVALID, "num_partitions %d out of range [1, 2^20]", cfg->num_partitions);
+    if (cfg->hll_precision != 0 && (cfg->hll_precision < 4 || cfg->hll_precision > 18))
+        return fail(KTA_ERR_INVALID, "hll_precision %d not 0 or 4..18", cfg->hll_precision);
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(KTA_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    if (cfg->device >= 0) h->device = cfg->device;
+    else CU(cudaGetDevice(&h->device));
+    if (h->device >= ndev) return fail(KTA_ERR_INVALID, "device %d >= device count %d", h->device, ndev);
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) return fail(KTA_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only",
+                                     prop.name, prop.major, prop.minor);
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->need_hash = cfg->count_alive_keys == 1 || cfg->hll_precision != 0;
+    if (cfg->now_s == INT64_MIN) {
+        const auto now = std::chrono::system_clock::now().time_since_epoch();
+        const int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(now).count();
+        h->cfg.now_s = ns / 1000000000ll;
+        h->cfg.now_ns = (int32_t)(ns % 1000000000ll);
+    }
+    h->ring_records = cfg->ring_records > 0 ? cfg->ring_records : DEFAULT_RING_RECORDS;
+    h->ring_records = (h->ring_records + TILE - 1) / TILE * TILE;
+    h->ring_key_bytes = cfg->ring_key_bytes > 0 ? cfg->ring_key_bytes : h->ring_records * 24;
+
+    const int P = cfg->num_partitions;
+    h->nsums = sums_words(P);
+    h->nhll = cfg->hll_precision ? ((size_t)1 << cfg->hll_precision) : 0;
+    CU(cudaMalloc(&h->d_sums, h->nsums * 8));
+    CU(cudaMalloc(&h->d_minmax, 4 * 8));
+    CU(cudaMalloc(&h->d_scalar, 2 * 8));
+    if (h->nhll) CU(cudaMalloc(&h->d_hll, h->nhll * 4));
+    if (cfg->count_alive_keys == 1) {
+        // direct-mapped last-writer table over the whole 32-bit hash space: 2^32 × 8 B = 32 GiB
+        CU(cudaMalloc(&h->d_alive_table, ((size_t)1 << 32) * 8));
+        CU(cudaMalloc(&h->d_alive_dirty, (size_t)1 << (32 - DIRTY_SHIFT)));
+        CU(cudaMemsetAsync(h->d_alive_table, 0, ((size_t)1 << 32) * 8, h->stream));
+        CU(cudaMemsetAsync(h->d_alive_dirty, 0, (size_t)1 << (32 - DIRTY_SHIFT), h->stream));
+    }
+    const bool smem = P <= PMAX_SMEM;
+    int rc;
+    if (smem) {
+        if ((rc = prepare_variant<false, true>(h))) return rc;
+        if ((rc = prepare_variant<true, true>(h))) return rc;
+    } else {
+        if ((rc = prepare_variant<false, false>(h))) return rc;
+        if ((rc = prepare_variant<true, false>(h))) return rc;
+    }
+    if ((rc = state_reset_device(h))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return KTA_OK;
+}
+
+extern "C" int kta_create(const kta_config *cfg, kta_handle **out) {
+    if (!cfg || !out) return fail(KTA_ERR_INVALID, "null argument");
+    if (cfg->struct_size != (int32_t)sizeof(kta_config))
+        return fail(KTA_ERR_INVALID, "kta_config.struct_size %d != %zu", cfg->struct_size, sizeof(kta_config));
+    kta_handle *h = new (std::nothrow) kta_handle();
+    if (!h) return fail(KTA_ERR_NOMEM, "out of host memory");
+    const int rc = create_impl(cfg, h);
+    if (rc) {
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        kta_destroy(h);
+        memcpy(g_err, keep, sizeof(keep));
+        *out = nullptr;
+        return rc;
+    }
+    *out = h;
+    return KTA_OK;
+}
+
+extern "C" void *kta_stream(kta_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" int kta_set_stream(kta_handle *h, void *stream) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) CU(cudaStreamDestroy(h->stream));
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+    return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan launch
+// ------------------------------------------------------------------------------------------------
+static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
+    if (prm.n <= 0) return KTA_OK;
+    const int P = h->cfg.num_partitions;
+    const bool exact = h->cfg.count_alive_keys == 1;
+    const bool hash = h->need_hash || h->d_hash_out;
+    prm.ntiles = (prm.n + TILE - 1) / TILE;
+    prm.P = P;
+    prm.exact = exact ? 1 : 0;
+    prm.hll_p = exact ? 0 : h->cfg.hll_precision;  // with -c the sketch is built from the resolved set
+    prm.sums = h->d_sums;
+    prm.minmax = h->d_minmax;
+    prm.hll = h->d_hll;
+    prm.alive_table = h->d_alive_table;
+    prm.alive_dirty = h->d_alive_dirty;
+    prm.hash_out = h->d_hash_out;
+    if (hash) {
+        if (!prm.key_tile_base) return fail(KTA_ERR_INVALID, "internal: key_tile_base missing");
+        if (!prm.key_bytes && key_readable > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL but keys are required");
+        prm.stage_ok = (((uintptr_t)prm.key_bytes & 15u) == 0) ? 1 : 0;
+        prm.key_readable = (uint64_t)key_readable;
+    }
+    const bool smem = P <= PMAX_SMEM;
+    const int grid = (int)std::min<int64_t>(prm.ntiles, h->grid_scan[hash][smem]);
+    const size_t sm = h->smem_scan[hash][smem];
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->timing) {
+        if (h->ev_used == h->ev_pool.size()) {
+            cudaEvent_t a, b;
+            CU(cudaEventCreate(&a));
+            CU(cudaEventCreate(&b));
+            h->ev_pool.emplace_back(a, b);
+        }
+        e0 = h->ev_pool[h->ev_used].first;
+        e1 = h->ev_pool[h->ev_used].second;
+        h->ev_used++;
+        CU(cudaEventRecord(e0, h->stream));
+    }
+    if (hash) {
+        if (smem) scan_kernel<true, true><<<grid, THREADS, sm, h->stream>>>(prm);
+        else scan_kernel<true, false><<<grid, THREADS, sm, h->stream>>>(prm);
+    } else {
+        if (smem) scan_kernel<false, true><<<grid, THREADS, sm, h->stream>>>(prm);
+        else scan_kernel<false, false><<<grid, THREADS, sm, h->stream>>>(prm);
+    }
+    CU(cudaGetLastError());
+    if (h->timing) CU(cudaEventRecord(e1, h->stream));
+    h->launches++;
+    h->records += (uint64_t)prm.n;
+    h->finalized = false;
+    return KTA_OK;
+}
+
+static int collect_timing(kta_handle *h) {
+    for (size_t i = 0; i < h->ev_used; i++) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev_pool[i].first, h->ev_pool[i].second));
+        h->scan_ms += ms;
+        h->scan_launches_timed++;
+    }
+    h->ev_used = 0;
+    return KTA_OK;
+}
+
+static int derive_tile_base(kta_handle *h, const int32_t *d_klen, int64_t n, uint64_t *d_tile_base) {
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 8);
+    tile_key_bytes_kernel<<<grid, THREADS, 0, h->stream>>>(d_klen, n, ntiles, d_tile_base);
+    CU(cudaGetLastError());
+    tile_base_scan_kernel<<<1, 1024, 0, h->stream>>>(d_tile_base, ntiles);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    return KTA_OK;
+}
+
+extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
+    if (!h || !b) return fail(KTA_ERR_INVALID, "null argument");
+    if (b->n < 0) return fail(KTA_ERR_INVALID, "negative n");
+    if (b->n == 0) return KTA_OK;
+    if (!b->partition || !b->ts_ms || !b->key_len || !b->value_len)
+        return fail(KTA_ERR_INVALID, "partition/ts_ms/key_len/value_len columns are required");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    ScanParams prm{};
+    prm.n = b->n;
+    prm.seq_base = b->seq_base;
+    prm.partition = b->partition;
+    prm.ts_ms = b->ts_ms;
+    prm.key_len = b->key_len;
+    prm.value_len = b->value_len;
+    prm.key_bytes = b->key_bytes;
+    prm.seq = b->seq;
+    prm.key_tile_base = b->key_tile_base;
+    if ((h->need_hash || h->d_hash_out) && !prm.key_tile_base) {
+        const int64_t ntiles = (b->n + TILE - 1) / TILE;
+        if (ntiles + 1 > h->tb_scratch_tiles) {
+            // stream-ordered: earlier scans that still read the old scratch finish first
+            CU(cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_tb_scratch);
+            h->d_tb_scratch = nullptr;
+            h->tb_scratch_tiles = 0;
+            CU(cudaMalloc(&h->d_tb_scratch, (size_t)(ntiles + 1) * 8));
+            h->tb_scratch_tiles = ntiles + 1;
+        }
+        if ((rc = derive_tile_base(h, b->key_len, b->n, h->d_tb_scratch))) return rc;
+        prm.key_tile_base = h->d_tb_scratch;
+    }
+    if ((rc = launch_scan(h, prm, b->key_bytes_len))) return rc;
+    h->next_seq = std::max<uint64_t>(h->next_seq, b->seq_base + (uint64_t)b->n);
+    return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// landing ring: host records → pinned chunk → cudaMemcpyAsync → HBM chunk → scan
+// ------------------------------------------------------------------------------------------------
+static int ring_dev_init(kta_handle *h) {
+    if (h->ring_dev_ready) return KTA_OK;
+    const int64_t R = h->ring_records, KB = h->ring_key_bytes;
+    for (auto &c : h->chunks) {
+        CU(cudaMalloc(&c.d_partition, R * 4));
+        CU(cudaMalloc(&c.d_klen, R * 4));
+        CU(cudaMalloc(&c.d_vlen, R * 4));
+        CU(cudaMalloc(&c.d_ts, R * 8));
+        CU(cudaMalloc(&c.d_seq, R * 8));
+        CU(cudaMalloc(&c.d_keys, KB + 64));
+        CU(cudaMalloc(&c.d_tile_base, (R / TILE + 2) * 8));
+        CU(cudaEventCreateWithFlags(&c.free_ev, cudaEventDisableTiming));
+    }
+    h->ring_dev_ready = true;
+    return KTA_OK;
+}
+
+static int ring_host_init(kta_handle *h) {
+    if (h->ring_host_ready) return KTA_OK;
+    int rc;
+    if ((rc = ring_dev_init(h))) return rc;
+    const int64_t R = h->ring_records, KB = h->ring_key_bytes;
+    for (auto &c : h->chunks) {
+        CU(cudaHostAlloc(&c.h_partition, R * 4, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c.h_klen, R * 4, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c.h_vlen, R * 4, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c.h_ts, R * 8, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c.h_keys, KB + 64, cudaHostAllocDefault));
+        CU(cudaHostAlloc(&c.h_tile_base, (R / TILE + 2) * 8, cudaHostAllocDefault));
+    }
+    h->ring_host_ready = true;
+    return KTA_OK;
+}
+
+// stage one pinned chunk and scan it
+static int ring_flush(kta_handle *h) {
+    if (h->cur_n == 0) return KTA_OK;
+    Chunk &c = h->chunks[h->cur];
+    const int64_t n = h->cur_n, kb = h->cur_kb;
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    c.h_tile_base[ntiles] = (uint64_t)kb;
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(c.d_partition, c.h_partition, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c.d_ts, c.h_ts, n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c.d_klen, c.h_klen, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c.d_vlen, c.h_vlen, n * 4, cudaMemcpyHostToDevice, s));
+    if (h->need_hash || h->d_hash_out) {
+        if (kb) CU(cudaMemcpyAsync(c.d_keys, c.h_keys, kb, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(c.d_tile_base, c.h_tile_base, (ntiles + 1) * 8, cudaMemcpyHostToDevice, s));
+    }
+    ScanParams prm{};
+    prm.n = n;
+    prm.seq_base = h->next_seq - (uint64_t)n;
+    prm.partition = c.d_partition;
+    prm.ts_ms = c.d_ts;
+    prm.key_len = c.d_klen;
+    prm.value_len = c.d_vlen;
+    prm.key_bytes = c.d_keys;
+    prm.key_tile_base = c.d_tile_base;
+    int rc;
+    if ((rc = launch_scan(h, prm, (kb + 15) & ~(int64_t)15))) return rc;
+    CU(cudaEventRecord(c.free_ev, s));
+    h->cur = (h->cur + 1) % NCHUNK;
+    h->cur_n = 0;
+    h->cur_kb = 0;
+    // the next chunk may still be in flight from NCHUNK flushes ago
+    CU(cudaEventSynchronize(h->chunks[h->cur].free_ev));
+    return KTA_OK;
+}
+
+extern "C" int kta_push(kta_handle *h, int32_t partition, int64_t offset, int64_t ts_ms, const uint8_t *key,
+                        int32_t key_len, int32_t value_len) {
+    (void)offset;  // never read by a metric; termination logic stays with the caller
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if (!h->ring_host_ready) {
+        if ((rc = set_device(h))) return rc;
+        if ((rc = ring_host_init(h))) return rc;
+    }
+    const bool hash = h->need_hash || h->d_hash_out;
+    const int64_t kl = (hash && key_len > 0) ? key_len : 0;  // key bytes only travel when they are hashed
+    if (kl > h->ring_key_bytes) return fail(KTA_ERR_INVALID, "key of %lld bytes exceeds ring_key_bytes", (long long)kl);
+    if (h->cur_n == h->ring_records || h->cur_kb + kl > h->ring_key_bytes) {
+        if ((rc = set_device(h))) return rc;
+        if ((rc = ring_flush(h))) return rc;
+    }
+    Chunk &c = h->chunks[h->cur];
+    const int64_t i = h->cur_n;
+    if ((i & (TILE - 1)) == 0) c.h_tile_base[i / TILE] = (uint64_t)h->cur_kb;
+    c.h_partition[i] = partition;
+    c.h_ts[i] = ts_ms;
+    c.h_klen[i] = key_len < 0 ? -1 : key_len;
+    c.h_vlen[i] = value_len < 0 ? -1 : value_len;
+    if (kl) {
+        if (!key) return fail(KTA_ERR_INVALID, "key is NULL with key_len %d", key_len);
+        memcpy(c.h_keys + h->cur_kb, key, (size_t)kl);
+        h->cur_kb += kl;
+    }
+    h->cur_n = i + 1;
+    h->next_seq++;
+    h->finalized = false;
+    return KTA_OK;
+}
+
+extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
+    if (!h || !b) return fail(KTA_ERR_INVALID, "null argument");
+    if (b->n < 0) return fail(KTA_ERR_INVALID, "negative n");
+    if (b->n == 0) return KTA_OK;
+    if (!b->partition || !b->ts_ms || !b->key_len || !b->value_len)
+        return fail(KTA_ERR_INVALID, "partition/ts_ms/key_len/value_len columns are required");
+    const bool hash = h->need_hash || h->d_hash_out;
+    if (hash && !b->key_bytes && b->key_bytes_len > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;  // keep seq order with earlier kta_push records
+    if ((rc = ring_dev_init(h))) return rc;
+    cudaStream_t s = h->stream;
+    std::vector<uint64_t> tb_host;  // only when the caller gave no tile bases
+    uint64_t koff = 0;              // absolute key byte offset of the next chunk's first key
+    int64_t r0 = 0;
+    while (r0 < b->n) {
+        int64_t cn = std::min<int64_t>(h->ring_records, b->n - r0);
+        const int ci = h->cur;
+        Chunk &c = h->chunks[ci];
+        CU(cudaEventSynchronize(c.free_ev));
+        uint64_t k0 = 0, k1 = 0;
+        const uint64_t *tb_src = nullptr;
+        if (hash) {
+            if (b->key_tile_base) {
+                // shrink the chunk until its keys fit the staging buffer
+                for (;;) {
+                    k0 = b->key_tile_base[r0 / TILE];
+                    k1 = b->key_tile_base[(r0 + cn + TILE - 1) / TILE];
+                    if ((int64_t)(k1 - k0) <= h->ring_key_bytes || cn <= TILE) break;
+                    cn = std::max<int64_t>(TILE, (cn / 2 + TILE - 1) / TILE * TILE);
+                }
+                tb_src = b->key_tile_base + r0 / TILE;
+            } else {
+                tb_host.resize((size_t)(cn / TILE + 2));
+                uint64_t acc = koff;
+                int64_t i = 0;
+                for (; i < cn; i++) {
+                    if ((i & (TILE - 1)) == 0) {
+                        if ((int64_t)(acc - koff) > h->ring_key_bytes - (int64_t)TILE * 64 && i > 0) break;
+                        tb_host[(size_t)(i / TILE)] = acc;
+                    }
+                    const int32_t v = b->key_len[r0 + i];
+                    acc += v > 0 ? (uint64_t)v : 0;
+                }
+                if (i < cn) {  // stopped early at a tile boundary: recompute the end of the last tile
+                    cn = i;
+                }
+                tb_host[(size_t)((cn + TILE - 1) / TILE)] = acc;
+                k0 = koff;
+                k1 = acc;
+                tb_src = tb_host.data();
+            }
+            if ((int64_t)(k1 - k0) > h->ring_key_bytes)
+                return fail(KTA_ERR_INVALID, "keys of one %d-record tile span %llu bytes > ring_key_bytes %lld", TILE,
+                            (unsigned long long)(k1 - k0), (long long)h->ring_key_bytes);
+        }
+        const int64_t ntiles = (cn + TILE - 1) / TILE;
+        CU(cudaMemcpyAsync(c.d_partition, b->partition + r0, cn * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(c.d_ts, b->ts_ms + r0, cn * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(c.d_klen, b->key_len + r0, cn * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(c.d_vlen, b->value_len + r0, cn * 4, cudaMemcpyHostToDevice, s));
+        if (b->seq && h->cfg.count_alive_keys == 1)
+            CU(cudaMemcpyAsync(c.d_seq, b->seq + r0, cn * 8, cudaMemcpyHostToDevice, s));
+        ScanParams prm{};
+        if (hash) {
+            // keep absolute offsets: place the keys so that (virtual base + k0) is where they land and the
+            // virtual base stays 16-byte aligned
+            const uint64_t shift = k0 & 15ull;
+            if (k1 > k0) CU(cudaMemcpyAsync(c.d_keys + shift, b->key_bytes + k0, k1 - k0, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(c.d_tile_base, tb_src, (ntiles + 1) * 8, cudaMemcpyHostToDevice, s));
+            prm.key_bytes = c.d_keys + shift - k0;
+            prm.key_tile_base = c.d_tile_base;
+        }
+        prm.n = cn;
+        prm.seq_base = b->seq_base + (uint64_t)r0;
+        prm.partition = c.d_partition;
+        prm.ts_ms = c.d_ts;
+        prm.key_len = c.d_klen;
+        prm.value_len = c.d_vlen;
+        prm.seq = (b->seq && h->cfg.count_alive_keys == 1) ? c.d_seq : nullptr;
+        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull)))) return rc;
+        CU(cudaEventRecord(c.free_ev, s));
+        h->cur = (h->cur + 1) % NCHUNK;
+        koff = k1;
+        r0 += cn;
+    }
+    // the caller may reuse its buffers when we return: all host→device copies must have been consumed
+    CU(cudaStreamSynchronize(s));
+    int rc2;
+    if ((rc2 = collect_timing(h))) return rc2;
+    h->next_seq = std::max<uint64_t>(h->next_seq, b->seq_base + (uint64_t)b->n);
+    return KTA_OK;
+}
+
+extern "C" int kta_sync(kta_handle *h) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return collect_timing(h);
+}
+
+extern "C" int kta_reset(kta_handle *h) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    h->cur_n = 0;
+    h->cur_kb = 0;
+    h->next_seq = 0;
+    h->finalized = false;
+    h->launches = 0;
+    h->records = 0;
+    return state_reset_device(h);
+}
+
+extern "C" int kta_finalize(kta_handle *h) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;
+    cudaStream_t s = h->stream;
+    if (h->d_alive_table) {
+        CU(cudaMemsetAsync(h->d_scalar, 0, 8, s));
+        if (h->nhll) CU(cudaMemsetAsync(h->d_hll, 0, h->nhll * 4, s));
+        alive_resolve_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, h->d_alive_dirty,
+                                                                 1u << (32 - DIRTY_SHIFT), h->d_scalar, h->d_hll,
+                                                                 h->cfg.hll_precision);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    h->h_sums.resize(h->nsums);
+    h->h_hll.resize(h->nhll);
+    CU(cudaMemcpyAsync(h->h_sums.data(), h->d_sums, h->nsums * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h->h_minmax, h->d_minmax, 32, cudaMemcpyDeviceToHost, s));
+    if (h->nhll) CU(cudaMemcpyAsync(h->h_hll.data(), h->d_hll, h->nhll * 4, cudaMemcpyDeviceToHost, s));
+    unsigned long long alive = 0;
+    if (h->d_alive_table) CU(cudaMemcpyAsync(&alive, h->d_scalar, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if ((rc = collect_timing(h))) return rc;
+    h->h_alive = alive;
+    h->finalized = true;
+    const uint64_t bad = h->h_sums[h->nsums - 1];
+    if (bad)
+        return fail(KTA_ERR_PARTITION, "%llu record(s) had a partition outside [0, %d)", (unsigned long long)bad,
+                    h->cfg.num_partitions);
+    return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// getters (host arithmetic on the finalized state)
+// ------------------------------------------------------------------------------------------------
+static int check_read(const kta_handle *h, int32_t p, bool per_partition) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    if (!h->finalized) return fail(KTA_ERR_NOT_FINALIZED, "call kta_finalize first");
+    if (per_partition && (p < 0 || p >= h->cfg.num_partitions)) return -1;  // unseen partition: reads as 0
+    return KTA_OK;
+}
+
+static uint64_t raw_counter(const kta_handle *h, int which, int32_t p) {
+    const int P = h->cfg.num_partitions;
+    const uint64_t *s = h->h_sums.data();
+    uint64_t knn = 0, alive = 0;
+    for (int b = 0; b < NB; b++) {
+        knn += s[(size_t)p * NB + b];
+        alive += s[(size_t)(P + p) * NB + b];
+    }
+    const uint64_t knull = s[(size_t)P * (2 * NB + 2) + p];
+    const uint64_t total = knn + knull;
+    switch (which) {
+        case KTA_TOTAL: return total;
+        case KTA_TOMBSTONES: return total - alive;
+        case KTA_ALIVE: return alive;
+        case KTA_KEY_NULL: return knull;
+        case KTA_KEY_NON_NULL: return knn;
+        case KTA_KEY_SIZE_SUM: return s[(size_t)P * (2 * NB) + p];
+        case KTA_VALUE_SIZE_SUM: return s[(size_t)P * (2 * NB + 1) + p];
+    }
+    return 0;
+}
+
+extern "C" int kta_counter(const kta_handle *h, int which, int32_t partition, uint64_t *out) {
+    if (!out || which < 0 || which > KTA_VALUE_SIZE_SUM) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, partition, true);
+    if (rc > 0) return rc;
+    *out = rc < 0 ? 0 : raw_counter(h, which, partition);  // src/metric.rs:198-203: None => 0
+    return KTA_OK;
+}
+
+extern "C" int kta_avg(const kta_handle *h, int which, int32_t partition, uint64_t *out) {
+    if (!out || which < 0 || which > KTA_MESSAGE_SIZE_AVG) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, partition, true);
+    if (rc > 0) return rc;
+    if (rc < 0) { *out = 0; return KTA_OK; }
+    const uint64_t ks = raw_counter(h, KTA_KEY_SIZE_SUM, partition), vs = raw_counter(h, KTA_VALUE_SIZE_SUM, partition);
+    const uint64_t alive = raw_counter(h, KTA_ALIVE, partition);
+    // src/metric.rs:132-157: every average divides by alive(p), guarded only by `sum > 0`
+    const uint64_t sum = which == KTA_KEY_SIZE_AVG ? ks : which == KTA_VALUE_SIZE_AVG ? vs : ks + vs;
+    if (sum > 0) {
+        if (alive == 0)
+            return fail(KTA_ERR_DIV_BY_ZERO, "partition %d: sum %llu > 0 with alive == 0 (the reference panics here)",
+                        partition, (unsigned long long)sum);
+        *out = sum / alive;
+    } else {
+        *out = 0;
+    }
+    return KTA_OK;
+}
+
+extern "C" int kta_dirty_ratio(const kta_handle *h, int32_t partition, float *out) {
+    if (!out) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, partition, true);
+    if (rc > 0) return rc;
+    *out = 0.0f;
+    if (rc < 0) return KTA_OK;
+    const uint64_t total = raw_counter(h, KTA_TOTAL, partition), tomb = raw_counter(h, KTA_TOMBSTONES, partition);
+    if (total > 0 && tomb > 0) {  // src/metric.rs:159-167, f32 throughout, same operation order
+        const volatile float t = (float)tomb;
+        const volatile float d = (float)total / 100.0f;
+        *out = t / d;
+    }
+    return KTA_OK;
+}
+
+extern "C" int kta_global(const kta_handle *h, int which, uint64_t *out) {
+    if (!out) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, 0, false);
+    if (rc) return rc;
+    const int P = h->cfg.num_partitions;
+    const unsigned long long *mm = reinterpret_cast<const unsigned long long *>(h->h_minmax);
+    switch (which) {
+        case KTA_SMALLEST_MESSAGE: *out = mm[2] == ~0ull ? 0 : mm[2]; return KTA_OK;  // metric.rs:177-183
+        case KTA_LARGEST_MESSAGE: *out = mm[3]; return KTA_OK;
+        case KTA_OVERALL_SIZE: {
+            uint64_t s = 0;
+            for (int p = 0; p < P; p++) s += raw_counter(h, KTA_KEY_SIZE_SUM, p) + raw_counter(h, KTA_VALUE_SIZE_SUM, p);
+            *out = s;  // metric.rs:224,238
+            return KTA_OK;
+        }
+        case KTA_OVERALL_COUNT: {
+            uint64_t s = 0;
+            for (int p = 0; p < P; p++) s += raw_counter(h, KTA_TOTAL, p);
+            *out = s;  // metric.rs:215
+            return KTA_OK;
+        }
+    }
+    return fail(KTA_ERR_INVALID, "bad global id %d", which);
+}
+
+extern "C" int kta_timestamps(const kta_handle *h, int64_t *earliest_s, int32_t *earliest_ns, int64_t *latest_s) {
+    const int rc = check_read(h, 0, false);
+    if (rc) return rc;
+    // src/metric.rs:39-40,65-72,209-211: seconds = ms / 1000 truncating; earliest starts at Utc::now(),
+    // latest at the epoch.  Truncating division is monotone, so min/max commute with it.
+    int64_t es = h->cfg.now_s, ls = 0;
+    int32_t ens = h->cfg.now_ns;
+    if (h->h_minmax[0] != INT64_MAX) {
+        const int64_t mn = h->h_minmax[0] / 1000, mx = h->h_minmax[1] / 1000;
+        if (es > mn || (es == mn && ens > 0)) { es = mn; ens = 0; }
+        if (ls < mx) ls = mx;
+    }
+    if (earliest_s) *earliest_s = es;
+    if (earliest_ns) *earliest_ns = ens;
+    if (latest_s) *latest_s = ls;
+    return KTA_OK;
+}
+
+extern "C" int kta_alive_keys(const kta_handle *h, uint64_t *out) {
+    if (!out) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, 0, false);
+    if (rc) return rc;
+    if (h->cfg.count_alive_keys != 1) return fail(KTA_ERR_NOT_ENABLED, "count_alive_keys was not enabled");
+    *out = h->h_alive;
+    return KTA_OK;
+}
+
+extern "C" int kta_hist(const kta_handle *h, int which, int32_t partition, uint64_t out[KTA_HIST_BUCKETS]) {
+    if (!out || which < 0 || which > 1) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, partition, true);
+    if (rc > 0) return rc;
+    const int P = h->cfg.num_partitions;
+    for (int b = 0; b < NB; b++)
+        out[b] = rc < 0 ? 0 : h->h_sums[(size_t)((which ? P : 0) + partition) * NB + b];
+    return KTA_OK;
+}
+
+// Ertl 2017, "New cardinality estimation algorithms for HyperLogLog sketches": improved raw estimator
+static double hll_sigma(double x) {
+    if (x == 1.0) return INFINITY;
+    double y = 1.0, z = x, zo;
+    do { x *= x; zo = z; z += x * y; y += y; } while (zo != z);
+    return z;
+}
+static double hll_tau(double x) {
+    if (x == 0.0 || x == 1.0) return 0.0;
+    double y = 1.0, z = 1.0 - x, zo;
+    do { x = std::sqrt(x); zo = z; y *= 0.5; z -= (1.0 - x) * (1.0 - x) * y; } while (zo != z);
+    return z / 3.0;
+}
+
+extern "C" int kta_alive_keys_hll(const kta_handle *h, double *out) {
+    if (!out) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, 0, false);
+    if (rc) return rc;
+    if (!h->nhll) return fail(KTA_ERR_NOT_ENABLED, "hll_precision was 0");
+    const int p = h->cfg.hll_precision, q = 64 - p;
+    const double m = (double)h->nhll;
+    std::vector<double> C((size_t)q + 2, 0.0);
+    for (uint32_t r : h->h_hll) C[std::min<uint32_t>(r, (uint32_t)q + 1)] += 1.0;
+    double z = m * hll_tau(1.0 - C[(size_t)q + 1] / m);
+    for (int k = q; k >= 1; k--) z = 0.5 * (z + C[(size_t)k]);
+    z += m * hll_sigma(C[0] / m);
+    *out = 0.72134752044448170368 * m * m / z;
+    return KTA_OK;
+}
+
+extern "C" int kta_hll_registers(const kta_handle *h, uint8_t *out, size_t cap) {
+    if (!out) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, 0, false);
+    if (rc) return rc;
+    if (!h->nhll) return fail(KTA_ERR_NOT_ENABLED, "hll_precision was 0");
+    if (cap < h->nhll) return fail(KTA_ERR_INVALID, "buffer too small: %zu < %zu", cap, h->nhll);
+    for (size_t i = 0; i < h->nhll; i++) out[i] = (uint8_t)h->h_hll[i];
+    return KTA_OK;
+}
+
+extern "C" int kta_fnv32_host(kta_handle *h, int64_t n, const int32_t *key_len, const uint8_t *key_bytes,
+                              int64_t key_bytes_len, uint32_t *out) {
+    if (!h || n < 0 || (n && (!key_len || !out))) return fail(KTA_ERR_INVALID, "bad argument");
+    if (n == 0) return KTA_OK;
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    std::vector<uint64_t> off((size_t)n);
+    uint64_t acc = 0;
+    for (int64_t i = 0; i < n; i++) {
+        off[(size_t)i] = acc;
+        acc += key_len[i] > 0 ? (uint64_t)key_len[i] : 0;
+    }
+    if ((int64_t)acc > key_bytes_len) return fail(KTA_ERR_INVALID, "key_bytes_len %lld < sum of key_len %llu",
+                                                  (long long)key_bytes_len, (unsigned long long)acc);
+    int32_t *d_len = nullptr;
+    uint64_t *d_off = nullptr;
+    uint8_t *d_keys = nullptr;
+    uint32_t *d_out = nullptr;
+    cudaStream_t s = h->stream;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaMalloc(&d_len, n * 4))) break;
+        if ((e = cudaMalloc(&d_off, n * 8))) break;
+        if ((e = cudaMalloc(&d_keys, acc + 16))) break;
+        if ((e = cudaMalloc(&d_out, n * 4))) break;
+        if ((e = cudaMemcpyAsync(d_len, key_len, n * 4, cudaMemcpyHostToDevice, s))) break;
+        if ((e = cudaMemcpyAsync(d_off, off.data(), n * 8, cudaMemcpyHostToDevice, s))) break;
+        if (acc && (e = cudaMemcpyAsync(d_keys, key_bytes, acc, cudaMemcpyHostToDevice, s))) break;
+        fnv32_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, s>>>(n, d_len, d_off, d_keys, d_out);
+        h->launches++;
+        if ((e = cudaGetLastError())) break;
+        if ((e = cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, s))) break;
+        e = cudaStreamSynchronize(s);
+    } while (0);
+    cudaFree(d_len); cudaFree(d_off); cudaFree(d_keys); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(KTA_ERR_CUDA, "kta_fnv32_host: %s", cudaGetErrorString(e));
+    return KTA_OK;
+}
+
+// test hook: capture the per-record hash computed inside the fused scan (device buffer of n u32, or NULL)
+extern "C" int kta_set_hash_capture(kta_handle *h, uint32_t *dev_out) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    h->d_hash_out = dev_out;
+    return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU merge
+// ------------------------------------------------------------------------------------------------
+extern "C" int64_t kta_merge_words(const kta_handle *h, int32_t world) {
+    if (!h || world < 1) return -1;
+    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * h->nhll);
+}
+
+extern "C" int kta_merge_export_device(kta_handle *h, int32_t rank, int32_t world, uint64_t *dev_buf) {
+    if (!h || !dev_buf || world < 1 || rank < 0 || rank >= world) return fail(KTA_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;
+    merge_export_kernel<<<h->sm_count, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll, rank,
+                                                           world, reinterpret_cast<unsigned long long *>(dev_buf));
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));  // the collective runs on the caller's stream
+    return collect_timing(h);
+}
+
+extern "C" int kta_merge_import_device(kta_handle *h, int32_t world, const uint64_t *dev_buf) {
+    if (!h || !dev_buf || world < 1) return fail(KTA_ERR_INVALID, "bad argument");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    merge_import_kernel<<<h->sm_count, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll, world,
+                                                           reinterpret_cast<const unsigned long long *>(dev_buf));
+    h->launches++;
+    CU(cudaGetLastError());
+    h->finalized = false;
+    CU(cudaStreamSynchronize(h->stream));
+    return KTA_OK;
+}
+
+static int alive_export(kta_handle *h, int mode, uint32_t *dh, uint64_t *ds, int64_t cap, int64_t *count) {
+    if (!h || !count) return fail(KTA_ERR_INVALID, "bad argument");
+    if (!h->d_alive_table) return fail(KTA_ERR_NOT_ENABLED, "count_alive_keys was not enabled");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;
+    CU(cudaMemsetAsync(h->d_scalar + 1, 0, 8, h->stream));
+    alive_export_kernel<<<h->sm_count * 8, THREADS, 0, h->stream>>>(
+        h->d_alive_table, h->d_alive_dirty, 1u << (32 - DIRTY_SHIFT), mode, h->d_scalar + 1, dh,
+        reinterpret_cast<unsigned long long *>(ds), (unsigned long long)cap);
+    h->launches++;
+    CU(cudaGetLastError());
+    unsigned long long c = 0;
+    CU(cudaMemcpyAsync(&c, h->d_scalar + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *count = (int64_t)c;
+    if (mode == 1 && (int64_t)c > cap) return fail(KTA_ERR_INVALID, "export buffer too small: %llu > %lld", c, (long long)cap);
+    return KTA_OK;
+}
+
+extern "C" int kta_alive_export_count(kta_handle *h, int64_t *count) { return alive_export(h, 0, nullptr, nullptr, 0, count); }
+
+extern "C" int kta_alive_export_device(kta_handle *h, uint32_t *dev_hash, uint64_t *dev_stamp, int64_t cap, int64_t *count) {
+    if (!dev_hash || !dev_stamp) return fail(KTA_ERR_INVALID, "bad argument");
+    return alive_export(h, 1, dev_hash, dev_stamp, cap, count);
+}
+
+extern "C" int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, const uint64_t *dev_stamp, int64_t count) {
+    if (!h || count < 0 || (count && (!dev_hash || !dev_stamp))) return fail(KTA_ERR_INVALID, "bad argument");
+    if (!h->d_alive_table) return fail(KTA_ERR_NOT_ENABLED, "count_alive_keys was not enabled");
+    if (count == 0) return KTA_OK;
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    alive_import_kernel<<<(int)std::min<int64_t>((count + THREADS - 1) / THREADS, (int64_t)h->sm_count * 8), THREADS, 0,
+                          h->stream>>>(h->d_alive_table, h->d_alive_dirty, dev_hash,
+                                       reinterpret_cast<const unsigned long long *>(dev_stamp), count);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->finalized = false;
+    CU(cudaStreamSynchronize(h->stream));
+    return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+extern "C" int kta_stats(const kta_handle *h, uint64_t *kernel_launches, uint64_t *records_scanned) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (records_scanned) *records_scanned = h->records;
+    return KTA_OK;
+}
+
+extern "C" int kta_set_timing(kta_handle *h, int enabled) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    h->timing = enabled != 0;
+    h->scan_ms = 0;
+    h->scan_launches_timed = 0;
+    return KTA_OK;
+}
+
+extern "C" int kta_scan_time_ms(kta_handle *h, double *total_ms, uint64_t *launches) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if ((rc = collect_timing(h))) return rc;
+    if (total_ms) *total_ms = h->scan_ms;
+    if (launches) *launches = h->scan_launches_timed;
+    return KTA_OK;
+}

@@ -1,0 +1,717 @@
+// kta_kernels.cuh — sm_100a device code for the message-scan metric path.
+//
+// What the kernels compute is exactly what the reference computes once per polled message
+// (src/kafka.rs:107-109) in MessageMetrics::handle_message (src/metric.rs:206-253) and
+// LogCompactionInMemoryMetrics::handle_message (src/metric.rs:288-305, hash src/fnv32.rs:92-101),
+// restructured for a B200: records arrive as SoA columns resident in HBM, one CTA walks 1024-record
+// tiles, per-partition counters live in shared memory (u32 + carry word, native ATOMS), the tile's
+// packed key bytes are staged global→shared with one bulk async copy (cp.async.bulk / UBLKCP, mbarrier
+// completion, double buffered), keys are hashed from shared memory, and the alive-key state is a
+// direct-mapped 2^32-entry table of 64-bit last-writer stamps in HBM (32 GiB of the 180 GB).
+// No tensor cores: there is no dense contraction anywhere on this path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kta.h"
+
+namespace kta {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int TILE = KTA_KEY_TILE;        // records per tile
+constexpr int ROWS = TILE / THREADS;      // records per thread per tile
+constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
+constexpr int KEYBUF_COPY = 20480;        // max staged bytes per tile (20 B/record average)
+constexpr int KEYBUF = KEYBUF_COPY + 128; // + slack for the (harmless) over-read of the last words
+constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
+constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
+constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
+constexpr int PMAX_SMEM = 512;            // partitions whose counters fit in shared memory
+
+// words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
+__host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
+// words of the u32 shared-memory mirror: khist | vhist | ksum_lo | ksum_hi | vsum_lo | vsum_hi | knull
+__host__ __device__ inline size_t smem_counter_words(int P) { return (size_t)P * (2 * NB + 5); }
+
+struct ScanParams {
+    int64_t n;
+    uint64_t seq_base;
+    const int32_t *partition;
+    const int64_t *ts_ms;
+    const int32_t *key_len;
+    const int32_t *value_len;
+    const uint8_t *key_bytes;        // may be an offset pointer; only [tile_base..] is dereferenced
+    const uint64_t *key_tile_base;   // [ntiles+1] absolute byte offsets relative to key_bytes
+    const uint64_t *seq;             // optional explicit seq column
+    int64_t ntiles;
+    int32_t P;
+    int32_t hll_p;                   // 0 = off
+    int32_t exact;                   // 1 = update alive table
+    int32_t stage_ok;                // key_bytes is 16-byte aligned → bulk-copy staging allowed
+    uint64_t key_readable;           // bytes that may be read starting at key_bytes (bulk copies round up to 16)
+    unsigned long long *sums;        // [sums_words(P)]
+    long long *minmax;               // [0] min ts_ms, [1] max ts_ms, [2] min size, [3] max size (as u64)
+    uint32_t *hll;                   // [1 << hll_p] registers (u32 each, device side)
+    unsigned long long *alive_table; // [2^32]
+    uint8_t *alive_dirty;            // [2^32 >> DIRTY_SHIFT]
+    uint32_t *hash_out;              // optional per-record hash capture (test hook), 0 for null keys
+};
+
+// ------------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KTA_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KTA_DONE_%=;\n\t"
+        "bra KTA_WAIT_%=;\n\t"
+        "KTA_DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global → shared (TMA engine, no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// streaming loads: read once, do not allocate in L1
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_stream_s64(const int64_t *p) {
+    int64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the reference hash, src/fnv32.rs:92-101: for each byte { hash ^= byte; hash *= 0x811c9dc5 }
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fnv_step(uint32_t h, uint32_t byte) { return (h ^ byte) * FNV_MULT; }
+
+__device__ __forceinline__ uint32_t fnv_word(uint32_t h, uint32_t w) {
+    h = fnv_step(h, w & 0xffu);
+    h = fnv_step(h, (w >> 8) & 0xffu);
+    h = fnv_step(h, (w >> 16) & 0xffu);
+    h = fnv_step(h, w >> 24);
+    return h;
+}
+
+// key at byte offset `a` of a 4-byte-aligned shared-memory buffer (aligned word loads + funnel shift)
+__device__ __forceinline__ uint32_t fnv_smem(const uint32_t *buf32, uint32_t a, int len) {
+    uint32_t h = FNV_BASIS;
+    const uint32_t *wp = buf32 + (a >> 2);
+    const uint32_t sh = (a & 3u) * 8u;
+    if (sh == 0 && len == 16 && (a & 15u) == 0) {  // the common fixed 16-byte aligned key: one LDS.128
+        const uint4 q = *reinterpret_cast<const uint4 *>(wp);
+        h = fnv_word(h, q.x);
+        h = fnv_word(h, q.y);
+        h = fnv_word(h, q.z);
+        h = fnv_word(h, q.w);
+        return h;
+    }
+    uint32_t lo = wp[0];
+    int j = 0;
+    for (; j + 4 <= len; j += 4) {
+        const uint32_t hi = wp[(j >> 2) + 1];
+        h = fnv_word(h, __funnelshift_r(lo, hi, sh));
+        lo = hi;
+    }
+    const int rem = len - j;
+    if (rem > 0) {
+        const uint32_t hi = wp[(j >> 2) + 1];
+        uint32_t w = __funnelshift_r(lo, hi, sh);
+        for (int r = 0; r < rem; r++) {
+            h = fnv_step(h, w & 0xffu);
+            w >>= 8;
+        }
+    }
+    return h;
+}
+
+// key read straight from global memory (tiles whose key span does not fit the staging buffer,
+// misaligned key buffers, and the kta_fnv32 test hook)
+__device__ __forceinline__ uint32_t fnv_global(const uint8_t *key, int len) {
+    uint32_t h = FNV_BASIS;
+    for (int j = 0; j < len; j++) h = fnv_step(h, (uint32_t)__ldg(key + j));
+    return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EXTENSION (not in the reference): HyperLogLog over the 32-bit reference hash
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t hll_mix(uint32_t hash) {
+    uint64_t x = (uint64_t)hash + 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ void hll_update(uint32_t *regs, int p, uint32_t hash) {
+    const uint64_t x = hll_mix(hash);
+    const uint32_t idx = (uint32_t)(x >> (64 - p));
+    const uint64_t rest = x << p;
+    const uint32_t rho = rest ? (uint32_t)__clzll((long long)rest) + 1u : (uint32_t)(64 - p + 1);
+    // registers only grow, so a (possibly stale) cached read is a safe filter: most records stop here
+    if (__ldca(regs + idx) < rho) atomicMax(regs + idx, rho);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-partition counters.  SMEM = true: CTA-private u32 words in shared memory (64-bit sums kept as
+// lo word + carry word, exact); SMEM = false: straight 64-bit global atomics (P > PMAX_SMEM).
+// src/metric.rs:74-100 (inc_*), derived at read-back:  key_non_null = Σ khist, alive = Σ vhist,
+// total = key_non_null + key_null, tombstones = total − alive.
+// ------------------------------------------------------------------------------------------------
+template <bool SMEM>
+struct Counters {
+    uint32_t *s;
+    unsigned long long *g;
+    int P;
+    __device__ __forceinline__ void khist(int p, int b, uint32_t c) const {
+        if (SMEM) atomicAdd(&s[p * NB + ((b + p) & (NB - 1))], c);
+        else atomicAdd(&g[(size_t)p * NB + b], (unsigned long long)c);
+    }
+    __device__ __forceinline__ void vhist(int p, int b, uint32_t c) const {
+        if (SMEM) atomicAdd(&s[(P + p) * NB + ((b + p) & (NB - 1))], c);
+        else atomicAdd(&g[(size_t)(P + p) * NB + b], (unsigned long long)c);
+    }
+    __device__ __forceinline__ void ksum(int p, uint32_t v) const {
+        if (SMEM) {
+            const uint32_t old = atomicAdd(&s[P * (2 * NB) + p], v);
+            if (old + v < old) atomicAdd(&s[P * (2 * NB + 1) + p], 1u);
+        } else atomicAdd(&g[(size_t)P * (2 * NB) + p], (unsigned long long)v);
+    }
+    __device__ __forceinline__ void vsum(int p, uint32_t v) const {
+        if (SMEM) {
+            const uint32_t old = atomicAdd(&s[P * (2 * NB + 2) + p], v);
+            if (old + v < old) atomicAdd(&s[P * (2 * NB + 3) + p], 1u);
+        } else atomicAdd(&g[(size_t)P * (2 * NB + 1) + p], (unsigned long long)v);
+    }
+    __device__ __forceinline__ void knull(int p, uint32_t c) const {
+        if (SMEM) atomicAdd(&s[P * (2 * NB + 4) + p], c);
+        else atomicAdd(&g[(size_t)P * (2 * NB + 2) + p], (unsigned long long)c);
+    }
+};
+
+__device__ __forceinline__ int len_bucket(int len) { return len == 0 ? 0 : 32 - __clz(len); }
+
+// One row = 32 consecutive records, one per lane.  MessageMetrics::handle_message, metric.rs:206-253.
+template <bool SMEM>
+__device__ __forceinline__ void count_row(const Counters<SMEM> &C, bool valid, int p, int kl, int vl, int lane,
+                                          uint32_t &bad) {
+    const unsigned full = 0xffffffffu;
+    const int p0 = __shfl_sync(full, p, 0);
+    const bool ok = valid && (unsigned)p < (unsigned)C.P;
+    const bool uni = __all_sync(full, ok && p == p0 && kl < (1 << 26) && vl < (1 << 26));
+    if (uni) {
+        // the whole row belongs to one partition (the usual shape of a Kafka fetch): aggregate in
+        // the warp, one atomic per distinct (bucket) and per sum
+        const int kb = kl < 0 ? NB : len_bucket(kl);
+        const int vb = vl < 0 ? NB : len_bucket(vl);
+        unsigned rem = full;
+        while (rem) {
+            const int leader = __ffs(rem) - 1;
+            const int b0 = __shfl_sync(full, kb, leader);
+            const unsigned m = __ballot_sync(full, kb == b0);
+            if (lane == leader) {
+                if (b0 == NB) C.knull(p0, __popc(m));   // metric.rs:228
+                else C.khist(p0, b0, __popc(m));        // metric.rs:220 (key_non_null = Σ buckets)
+            }
+            rem &= ~m;
+        }
+        rem = full;
+        while (rem) {
+            const int leader = __ffs(rem) - 1;
+            const int b0 = __shfl_sync(full, vb, leader);
+            const unsigned m = __ballot_sync(full, vb == b0);
+            if (lane == leader && b0 != NB) C.vhist(p0, b0, __popc(m));  // metric.rs:239
+            rem &= ~m;
+        }
+        const uint32_t ks = __reduce_add_sync(full, (uint32_t)(kl > 0 ? kl : 0));
+        const uint32_t vs = __reduce_add_sync(full, (uint32_t)(vl > 0 ? vl : 0));
+        if (lane == 0) {
+            if (ks) C.ksum(p0, ks);  // metric.rs:223
+            if (vs) C.vsum(p0, vs);  // metric.rs:237
+        }
+    } else if (valid) {
+        if (!ok) {
+            bad++;
+        } else {
+            if (kl < 0) C.knull(p, 1u);
+            else {
+                C.khist(p, len_bucket(kl), 1u);
+                if (kl) C.ksum(p, (uint32_t)kl);
+            }
+            if (vl >= 0) {
+                C.vhist(p, len_bucket(vl), 1u);
+                if (vl) C.vsum(p, (uint32_t)vl);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused scan kernel.  HASH = false: counters + histograms + extrema only (20 B/record, no key
+// bytes touched — the reference without -c).  HASH = true: additionally FNV per key from staged
+// shared memory, alive-table stamps (-c) and/or the in-stream HLL sketch (20 + key bytes per record).
+// Persistent grid; tile t is handled by CTA t % gridDim.x.
+// ------------------------------------------------------------------------------------------------
+template <bool HASH, bool SMEM>
+__global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [keybuf0 | keybuf1] (HASH) | mbar[2] | span_g0[2] | warp_tot[WARPS] | red[WARPS*4] | span_staged[2] | counters
+    unsigned char *sp = smem_raw;
+    unsigned char *keybuf = sp;
+    if (HASH) sp += 2 * KEYBUF;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sp); sp += 2 * sizeof(uint64_t);
+    uint64_t *span_g0 = reinterpret_cast<uint64_t *>(sp); sp += 2 * sizeof(uint64_t);
+    uint64_t *warp_tot = reinterpret_cast<uint64_t *>(sp); sp += WARPS * sizeof(uint64_t);
+    long long *red = reinterpret_cast<long long *>(sp); sp += WARPS * 4 * sizeof(long long);
+    uint32_t *span_staged = reinterpret_cast<uint32_t *>(sp); sp += 4 * sizeof(uint32_t);
+    uint32_t *scnt = reinterpret_cast<uint32_t *>(sp);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    const int P = prm.P;
+    Counters<SMEM> C{scnt, prm.sums, P};
+
+    if (SMEM) {
+        const int nw = (int)smem_counter_words(P);
+        for (int i = tid; i < nw; i += THREADS) scnt[i] = 0;
+    }
+    if (HASH && tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // issue the bulk copy of one tile's packed key bytes into buffer b (one thread)
+    auto issue = [&](int64_t tile, int b) {
+        const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
+        const uint64_t a0 = g0 & ~15ull;
+        const uint64_t bytes = ((g1 - a0) + 15ull) & ~15ull;
+        const bool ok = prm.stage_ok && g1 > g0 && bytes <= (uint64_t)KEYBUF_COPY && a0 + bytes <= prm.key_readable;
+        span_g0[b] = g0;
+        span_staged[b] = ok ? 1u : 0u;
+        if (ok) {
+            mbar_arrive_expect_tx(&mbar[b], (uint32_t)bytes);
+            bulk_g2s(keybuf + (size_t)b * KEYBUF, prm.key_bytes + a0, (uint32_t)bytes, &mbar[b]);
+        }
+    };
+
+    long long tmin = INT64_MAX, tmax = INT64_MIN;         // ts_ms extrema (after None → 0)
+    uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema
+    bool sany = false;
+    uint32_t bad = 0;
+    uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
+
+    int64_t tile = blockIdx.x;
+    if (HASH && tid == 0 && tile < prm.ntiles) issue(tile, 0);
+
+    for (int it = 0; tile < prm.ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        __syncthreads();  // (A) everyone is done with buffer buf^1 and with warp_tot
+        if (HASH && tid == 0) {
+            const int64_t next = tile + gridDim.x;
+            if (next < prm.ntiles) issue(next, buf ^ 1);
+        }
+
+        // ---- header columns: 4 rows of 32 consecutive records per warp, fully coalesced ----
+        const int64_t rbase = tile * TILE + warp * (32 * ROWS) + lane;
+        int p[ROWS], kl[ROWS], vl[ROWS];
+        long long ts[ROWS];
+        bool valid[ROWS];
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            const int64_t r = rbase + 32 * k;
+            valid[k] = r < prm.n;
+            if (valid[k]) {
+                p[k] = ld_stream_s32(prm.partition + r);
+                ts[k] = ld_stream_s64(prm.ts_ms + r);
+                kl[k] = ld_stream_s32(prm.key_len + r);
+                vl[k] = ld_stream_s32(prm.value_len + r);
+            } else {
+                p[k] = 0; ts[k] = 0; kl[k] = -1; vl[k] = -1;
+            }
+        }
+
+        // ---- MessageMetrics::handle_message ----
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            count_row<SMEM>(C, valid[k], p[k], kl[k], vl[k], lane, bad);
+            if (valid[k]) {
+                const long long t = ts[k] == -1 ? 0 : ts[k];  // metric.rs:209 unwrap_or(0)
+                tmin = t < tmin ? t : tmin;                   // metric.rs:247 (seconds taken at read-back)
+                tmax = t > tmax ? t : tmax;
+                if (vl[k] >= 0) {                             // metric.rs:249-251: not for tombstones
+                    const uint32_t sz = (uint32_t)(kl[k] > 0 ? kl[k] : 0) + (uint32_t)vl[k];
+                    smin = sz < smin ? sz : smin;
+                    smax = sz > smax ? sz : smax;
+                    sany = true;
+                }
+            }
+        }
+
+        if (HASH) {
+            // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
+            uint64_t off[ROWS];
+            uint64_t carry = 0;
+            int mx = 0;
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) mx = max(mx, kl[k]);
+            if (!__any_sync(full, mx >= (1 << 24))) {
+                uint32_t c32 = 0;
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    const uint32_t v = (uint32_t)(kl[k] > 0 ? kl[k] : 0);
+                    uint32_t inc = v;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(full, inc, d);
+                        if (lane >= d) inc += t;
+                    }
+                    off[k] = c32 + inc - v;
+                    c32 += __shfl_sync(full, inc, 31);
+                }
+                carry = c32;
+            } else {
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    const uint64_t v = (uint64_t)(kl[k] > 0 ? kl[k] : 0);
+                    uint64_t inc = v;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint64_t t = __shfl_up_sync(full, inc, d);
+                        if (lane >= d) inc += t;
+                    }
+                    off[k] = carry + inc - v;
+                    carry += __shfl_sync(full, inc, 31);
+                }
+            }
+            if (lane == 0) warp_tot[warp] = carry;
+            __syncthreads();  // (B)
+            uint64_t wbase = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) wbase += (w < warp) ? warp_tot[w] : 0;
+
+            const uint64_t g0 = span_g0[buf];
+            const bool staged = span_staged[buf] != 0;
+            if (staged) {
+                mbar_wait(&mbar[buf], (phase >> buf) & 1u);
+                phase ^= 1u << buf;
+            }
+            const uint32_t *kb32 = reinterpret_cast<const uint32_t *>(keybuf + (size_t)buf * KEYBUF);
+            const uint32_t a0 = (uint32_t)(g0 & 15ull);
+
+            // ---- LogCompactionInMemoryMetrics::handle_message, metric.rs:288-305 ----
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                if (valid[k] && kl[k] >= 0) {   // metric.rs:291 Some(k); None => {} (:302)
+                    const uint64_t o = wbase + off[k];
+                    const uint32_t h = staged ? fnv_smem(kb32, a0 + (uint32_t)o, kl[k])
+                                              : fnv_global(prm.key_bytes + g0 + o, kl[k]);
+                    const int64_t r = rbase + 32 * k;
+                    if (prm.hash_out) prm.hash_out[r] = h;
+                    if (prm.exact) {
+                        // last-writer-wins per hash in seq order == BitSet insert/remove replayed in
+                        // order (metric.rs:295 mark_key_alive, :298 mark_key_dead)
+                        const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
+                        const unsigned long long stamp = ((seq + 1ull) << 1) | (vl[k] >= 0 ? 1ull : 0ull);
+                        atomicMax(prm.alive_table + h, stamp);
+                        uint8_t *d = prm.alive_dirty + (h >> DIRTY_SHIFT);
+                        if (__ldca(d) == 0) *d = 1;
+                    }
+                    if (prm.hll_p && vl[k] >= 0) hll_update(prm.hll, prm.hll_p, h);
+                } else if (prm.hash_out && valid[k]) {
+                    prm.hash_out[rbase + 32 * k] = 0;
+                }
+            }
+        }
+    }
+
+    // ---- flush CTA-private state ----
+    __syncthreads();
+    if (SMEM) {
+        const int nh = 2 * P * NB;  // khist then vhist, un-swizzle on the way out
+        for (int i = tid; i < nh; i += THREADS) {
+            const int pp = (i / NB) % P, slot = i % NB;
+            const uint32_t v = scnt[i];
+            if (v) {
+                const int b = (slot - pp) & (NB - 1);
+                atomicAdd(&prm.sums[(size_t)(i / NB) * NB + b], (unsigned long long)v);
+            }
+        }
+        for (int i = tid; i < P; i += THREADS) {
+            const unsigned long long ks = (unsigned long long)scnt[P * (2 * NB) + i] |
+                                          ((unsigned long long)scnt[P * (2 * NB + 1) + i] << 32);
+            const unsigned long long vs = (unsigned long long)scnt[P * (2 * NB + 2) + i] |
+                                          ((unsigned long long)scnt[P * (2 * NB + 3) + i] << 32);
+            const uint32_t kn = scnt[P * (2 * NB + 4) + i];
+            if (ks) atomicAdd(&prm.sums[(size_t)P * (2 * NB) + i], ks);
+            if (vs) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 1) + i], vs);
+            if (kn) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 2) + i], (unsigned long long)kn);
+        }
+    }
+    // extrema + bad-partition count: warp shuffle, then one lane per warp, then one thread per CTA
+    long long smin64 = sany ? (long long)smin : INT64_MAX;  // sizes < 2^32, safe in i64
+    long long smax64 = sany ? (long long)smax : -1;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const long long a = __shfl_xor_sync(full, tmin, d), b = __shfl_xor_sync(full, tmax, d);
+        const long long c = __shfl_xor_sync(full, smin64, d), e = __shfl_xor_sync(full, smax64, d);
+        tmin = a < tmin ? a : tmin;
+        tmax = b > tmax ? b : tmax;
+        smin64 = c < smin64 ? c : smin64;
+        smax64 = e > smax64 ? e : smax64;
+        bad += __shfl_xor_sync(full, bad, d);
+    }
+    if (lane == 0) {
+        red[warp * 4 + 0] = tmin; red[warp * 4 + 1] = tmax; red[warp * 4 + 2] = smin64; red[warp * 4 + 3] = smax64;
+        if (bad) atomicAdd(&prm.sums[sums_words(P) - 1], (unsigned long long)bad);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < WARPS; w++) {
+            tmin = red[w * 4 + 0] < tmin ? red[w * 4 + 0] : tmin;
+            tmax = red[w * 4 + 1] > tmax ? red[w * 4 + 1] : tmax;
+            smin64 = red[w * 4 + 2] < smin64 ? red[w * 4 + 2] : smin64;
+            smax64 = red[w * 4 + 3] > smax64 ? red[w * 4 + 3] : smax64;
+        }
+        if (tmin != INT64_MAX) {
+            atomicMin(&prm.minmax[0], tmin);
+            atomicMax(&prm.minmax[1], tmax);
+        }
+        if (smax64 >= 0) {
+            atomicMin(reinterpret_cast<unsigned long long *>(&prm.minmax[2]), (unsigned long long)smin64);
+            atomicMax(reinterpret_cast<unsigned long long *>(&prm.minmax[3]), (unsigned long long)smax64);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// key_tile_base derivation when the caller did not supply it: per-tile byte totals, then one
+// single-CTA exclusive scan over the tile totals.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) tile_key_bytes_kernel(const int32_t *key_len, int64_t n, int64_t ntiles,
+                                                                 uint64_t *tile_base /*[ntiles+1], [t+1] = bytes of tile t*/) {
+    __shared__ uint64_t wsum[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint64_t s = 0;
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            const int64_t r = tile * TILE + k * THREADS + tid;
+            if (r < n) {
+                const int32_t v = key_len[r];
+                s += v > 0 ? (uint64_t)v : 0;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) wsum[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t t = 0;
+            for (int w = 0; w < WARPS; w++) t += wsum[w];
+            tile_base[tile + 1] = t;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid == 0) tile_base[0] = 0;
+}
+
+__global__ void __launch_bounds__(1024) tile_base_scan_kernel(uint64_t *tile_base, int64_t ntiles) {
+    // inclusive scan of tile_base[1..ntiles] in place (tile_base[0] == 0), one CTA, chunks of 1024
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 1; base <= ntiles; base += 1024) {
+        const int64_t i = base + tid;
+        const uint64_t v = i <= ntiles ? tile_base[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint64_t wb = 0;
+        for (int w = 0; w < warp; w++) wb += wsum[w];
+        const uint64_t out = carry_s + wb + inc;
+        if (i <= ntiles) tile_base[i] = out;
+        __syncthreads();
+        if (tid == 1023) carry_s = out;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// alive-key table: resolve / export / import / clear.  Entry = ((seq+1) << 1) | alive of the last
+// record that carried this hash; 0 = never seen.  sum_all_alive (metric.rs:282-284) = #entries with
+// the alive bit set.
+// ------------------------------------------------------------------------------------------------
+constexpr int PAGE_ENTRIES = 1 << DIRTY_SHIFT;
+
+__global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned long long *table, const uint8_t *dirty,
+                                                                uint32_t npages, unsigned long long *alive_count,
+                                                                uint32_t *hll, int hll_p) {
+    unsigned long long local = 0;
+    for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
+        if (!dirty[page]) continue;
+        const unsigned long long *pg = table + ((size_t)page << DIRTY_SHIFT);
+        for (int i = threadIdx.x; i < PAGE_ENTRIES; i += THREADS) {
+            const unsigned long long v = pg[i];
+            if (v & 1ull) {
+                local++;
+                if (hll_p) hll_update(hll, hll_p, (page << DIRTY_SHIFT) + (uint32_t)i);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(alive_count, local);
+}
+
+// mode 0: count non-zero entries; mode 1: append them as (hash, stamp)
+__global__ void __launch_bounds__(THREADS) alive_export_kernel(const unsigned long long *table, const uint8_t *dirty,
+                                                               uint32_t npages, int mode, unsigned long long *counter,
+                                                               uint32_t *out_hash, unsigned long long *out_stamp,
+                                                               unsigned long long cap) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
+        if (!dirty[page]) continue;
+        const unsigned long long *pg = table + ((size_t)page << DIRTY_SHIFT);
+        for (int i = threadIdx.x; i < PAGE_ENTRIES; i += THREADS) {
+            const unsigned long long v = pg[i];
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+            if (!m) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (mode == 1 && v != 0) {
+                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < cap) {
+                    out_hash[slot] = (page << DIRTY_SHIFT) + (uint32_t)i;
+                    out_stamp[slot] = v;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) alive_import_kernel(unsigned long long *table, uint8_t *dirty,
+                                                               const uint32_t *hash, const unsigned long long *stamp,
+                                                               int64_t count) {
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < count; i += (int64_t)gridDim.x * THREADS) {
+        const uint32_t h = hash[i];
+        atomicMax(table + h, stamp[i]);
+        dirty[h >> DIRTY_SHIFT] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) alive_clear_kernel(unsigned long long *table, uint8_t *dirty, uint32_t npages) {
+    for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
+        if (!dirty[page]) continue;  // uniform per CTA
+        ulonglong2 *pg = reinterpret_cast<ulonglong2 *>(table + ((size_t)page << DIRTY_SHIFT));
+        for (int i = threadIdx.x; i < PAGE_ENTRIES / 2; i += THREADS) pg[i] = make_ulonglong2(0ull, 0ull);
+        __syncthreads();
+        if (threadIdx.x == 0) dirty[page] = 0;
+    }
+}
+
+// state (re)initialisation: sums = 0, minmax = {+inf, -inf, u64 max, 0}, hll = 0
+__global__ void state_init_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint32_t *hll, size_t nhll) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsums; i += stride) sums[i] = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nhll; i += stride) hll[i] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        minmax[0] = INT64_MAX;
+        minmax[1] = INT64_MIN;
+        reinterpret_cast<unsigned long long *>(minmax)[2] = ~0ull;
+        reinterpret_cast<unsigned long long *>(minmax)[3] = 0ull;
+    }
+}
+
+// test hook: the reference hash of n packed keys (src/fnv32.rs:92-101)
+__global__ void fnv32_kernel(int64_t n, const int32_t *key_len, const uint64_t *key_off, const uint8_t *key_bytes,
+                             uint32_t *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = key_len[i] < 0 ? 0u : fnv_global(key_bytes + key_off[i], key_len[i]);
+}
+
+// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×hll words] ----
+__global__ void merge_export_kernel(const unsigned long long *sums, size_t nsums, const long long *minmax,
+                                    const uint32_t *hll, size_t nhll, int rank, int world, unsigned long long *buf) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nmm = (size_t)world * 4, total = nsums + nmm + (size_t)world * nhll;
+    for (size_t i = t0; i < total; i += stride) {
+        unsigned long long v = 0;
+        if (i < nsums) v = sums[i];
+        else if (i < nsums + nmm) {
+            const size_t j = i - nsums;
+            // stored biased so that "no contribution" (0) is neutral for every rank slot but ours
+            if ((int)(j / 4) == rank) v = (unsigned long long)minmax[j % 4];
+        } else {
+            const size_t j = i - nsums - nmm;
+            if ((int)(j / nhll) == rank) v = hll[j % nhll];
+        }
+        buf[i] = v;
+    }
+}
+
+__global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint32_t *hll,
+                                    size_t nhll, int world, const unsigned long long *buf) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t0; i < nsums; i += stride) sums[i] = buf[i];
+    const unsigned long long *mm = buf + nsums;
+    const unsigned long long *hb = mm + (size_t)world * 4;
+    for (size_t i = t0; i < nhll; i += stride) {
+        unsigned long long m = 0;
+        for (int r = 0; r < world; r++) m = max(m, hb[(size_t)r * nhll + i]);
+        hll[i] = (uint32_t)m;
+    }
+    if (t0 == 0) {
+        long long tmin = INT64_MAX, tmax = INT64_MIN;
+        unsigned long long smin = ~0ull, smax = 0;
+        for (int r = 0; r < world; r++) {
+            tmin = min(tmin, (long long)mm[r * 4 + 0]);
+            tmax = max(tmax, (long long)mm[r * 4 + 1]);
+            smin = min(smin, mm[r * 4 + 2]);
+            smax = max(smax, mm[r * 4 + 3]);
+        }
+        minmax[0] = tmin;
+        minmax[1] = tmax;
+        reinterpret_cast<unsigned long long *>(minmax)[2] = smin;
+        reinterpret_cast<unsigned long long *>(minmax)[3] = smax;
+    }
+}
+
+}  // namespace kta

