@@ -60,7 +60,6 @@ extern "C" int kta_device_count(void) {
 // ------------------------------------------------------------------------------------------------
 static constexpr int NCHUNK = 3;
 static constexpr int64_t DEFAULT_RING_RECORDS = 1 << 22;  // 4 Mi records per chunk
-static constexpr int SMEM_FIXED = 2 * 8 + 2 * 8 + WARPS * 8 + WARPS * 4 * 8 + 4 * 4;
 
 struct Chunk {
     // device staging (shared by kta_push and kta_push_batch_host)
@@ -87,10 +86,11 @@ struct kta_handle {
     // device state
     unsigned long long *d_sums = nullptr;
     long long *d_minmax = nullptr;
-    uint32_t *d_hll = nullptr;
+    uint8_t *d_hll = nullptr;
+    uint32_t *d_hll_floor = nullptr;
     unsigned long long *d_alive_table = nullptr;
     uint8_t *d_alive_dirty = nullptr;
-    unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export counter
+    unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export counter, [2] hll floor (u32)
     uint32_t *d_hash_out = nullptr;          // test hook
     uint64_t *d_tb_scratch = nullptr;        // key_tile_base scratch for device batches
     int64_t tb_scratch_tiles = 0;
@@ -107,11 +107,11 @@ struct kta_handle {
     bool finalized = false;
     std::vector<uint64_t> h_sums;
     long long h_minmax[4] = {0, 0, 0, 0};
-    std::vector<uint32_t> h_hll;
+    std::vector<uint8_t> h_hll;
     uint64_t h_alive = 0;
     // occupancy-derived grids
-    int grid_scan[2][2] = {{0, 0}, {0, 0}};  // [HASH][SMEM]
-    size_t smem_scan[2][2] = {{0, 0}, {0, 0}};
+    int grid_scan[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // [0 counters, 1 hash, 2 hash+capture][SMEM]
+    size_t smem_scan[3][2] = {{0, 0}, {0, 0}, {0, 0}};
     // stats / timing
     uint64_t launches = 0, records = 0;
     bool timing = false;
@@ -130,20 +130,21 @@ static size_t scan_smem_bytes(bool hash, bool smem, int P) {
     return (hash ? 2 * (size_t)KEYBUF : 0) + SMEM_FIXED + (smem ? smem_counter_words(P) * 4 : 0);
 }
 
-template <bool HASH, bool SMEM>
+template <bool HASH, bool SMEM, bool CAPTURE>
 static int prepare_variant(kta_handle *h) {
     const size_t smem = scan_smem_bytes(HASH, SMEM, h->cfg.num_partitions);
-    CU(cudaFuncSetAttribute(scan_kernel<HASH, SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(scan_kernel<HASH, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<HASH, SMEM>, THREADS, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<HASH, SMEM, CAPTURE>, THREADS, smem));
     if (occ < 1) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", smem);
-    h->grid_scan[HASH][SMEM] = occ * h->sm_count;
-    h->smem_scan[HASH][SMEM] = smem;
+    const int v = CAPTURE ? 2 : (HASH ? 1 : 0);
+    h->grid_scan[v][SMEM] = occ * h->sm_count;
+    h->smem_scan[v][SMEM] = smem;
     return KTA_OK;
 }
 
 static int state_reset_device(kta_handle *h) {
-    state_init_kernel<<<64, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll);
+    state_init_kernel<<<64, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll, h->d_hll_floor);
     h->launches++;
     CU(cudaGetLastError());
     if (h->d_alive_table) {
@@ -213,8 +214,9 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     h->nhll = cfg->hll_precision ? ((size_t)1 << cfg->hll_precision) : 0;
     CU(cudaMalloc(&h->d_sums, h->nsums * 8));
     CU(cudaMalloc(&h->d_minmax, 4 * 8));
-    CU(cudaMalloc(&h->d_scalar, 2 * 8));
-    if (h->nhll) CU(cudaMalloc(&h->d_hll, h->nhll * 4));
+    CU(cudaMalloc(&h->d_scalar, 4 * 8));
+    h->d_hll_floor = reinterpret_cast<uint32_t *>(h->d_scalar + 2);
+    if (h->nhll) CU(cudaMalloc(&h->d_hll, h->nhll));
     if (cfg->count_alive_keys == 1) {
         // direct-mapped last-writer table over the whole 32-bit hash space: 2^32 × 8 B = 32 GiB
         CU(cudaMalloc(&h->d_alive_table, ((size_t)1 << 32) * 8));
@@ -225,11 +227,13 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     const bool smem = P <= PMAX_SMEM;
     int rc;
     if (smem) {
-        if ((rc = prepare_variant<false, true>(h))) return rc;
-        if ((rc = prepare_variant<true, true>(h))) return rc;
+        if ((rc = prepare_variant<false, true, false>(h))) return rc;
+        if ((rc = prepare_variant<true, true, false>(h))) return rc;
+        if ((rc = prepare_variant<true, true, true>(h))) return rc;
     } else {
-        if ((rc = prepare_variant<false, false>(h))) return rc;
-        if ((rc = prepare_variant<true, false>(h))) return rc;
+        if ((rc = prepare_variant<false, false, false>(h))) return rc;
+        if ((rc = prepare_variant<true, false, false>(h))) return rc;
+        if ((rc = prepare_variant<true, false, true>(h))) return rc;
     }
     if ((rc = state_reset_device(h))) return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -283,6 +287,7 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
     prm.sums = h->d_sums;
     prm.minmax = h->d_minmax;
     prm.hll = h->d_hll;
+    prm.hll_floor = h->d_hll_floor;
     prm.alive_table = h->d_alive_table;
     prm.alive_dirty = h->d_alive_dirty;
     prm.hash_out = h->d_hash_out;
@@ -293,8 +298,9 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
         prm.key_readable = (uint64_t)key_readable;
     }
     const bool smem = P <= PMAX_SMEM;
-    const int grid = (int)std::min<int64_t>(prm.ntiles, h->grid_scan[hash][smem]);
-    const size_t sm = h->smem_scan[hash][smem];
+    const int variant = h->d_hash_out ? 2 : (hash ? 1 : 0);
+    const int grid = (int)std::min<int64_t>(prm.ntiles, h->grid_scan[variant][smem]);
+    const size_t sm = h->smem_scan[variant][smem];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         if (h->ev_used == h->ev_pool.size()) {
@@ -308,12 +314,15 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
         h->ev_used++;
         CU(cudaEventRecord(e0, h->stream));
     }
-    if (hash) {
-        if (smem) scan_kernel<true, true><<<grid, THREADS, sm, h->stream>>>(prm);
-        else scan_kernel<true, false><<<grid, THREADS, sm, h->stream>>>(prm);
+    if (variant == 2) {
+        if (smem) scan_kernel<true, true, true><<<grid, THREADS, sm, h->stream>>>(prm);
+        else scan_kernel<true, false, true><<<grid, THREADS, sm, h->stream>>>(prm);
+    } else if (variant == 1) {
+        if (smem) scan_kernel<true, true, false><<<grid, THREADS, sm, h->stream>>>(prm);
+        else scan_kernel<true, false, false><<<grid, THREADS, sm, h->stream>>>(prm);
     } else {
-        if (smem) scan_kernel<false, true><<<grid, THREADS, sm, h->stream>>>(prm);
-        else scan_kernel<false, false><<<grid, THREADS, sm, h->stream>>>(prm);
+        if (smem) scan_kernel<false, true, false><<<grid, THREADS, sm, h->stream>>>(prm);
+        else scan_kernel<false, false, false><<<grid, THREADS, sm, h->stream>>>(prm);
     }
     CU(cudaGetLastError());
     if (h->timing) CU(cudaEventRecord(e1, h->stream));
@@ -614,7 +623,7 @@ extern "C" int kta_finalize(kta_handle *h) {
     cudaStream_t s = h->stream;
     if (h->d_alive_table) {
         CU(cudaMemsetAsync(h->d_scalar, 0, 8, s));
-        if (h->nhll) CU(cudaMemsetAsync(h->d_hll, 0, h->nhll * 4, s));
+        if (h->nhll) CU(cudaMemsetAsync(h->d_hll, 0, h->nhll, s));
         alive_resolve_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, h->d_alive_dirty,
                                                                  1u << (32 - DIRTY_SHIFT), h->d_scalar, h->d_hll,
                                                                  h->cfg.hll_precision);
@@ -625,7 +634,7 @@ extern "C" int kta_finalize(kta_handle *h) {
     h->h_hll.resize(h->nhll);
     CU(cudaMemcpyAsync(h->h_sums.data(), h->d_sums, h->nsums * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h->h_minmax, h->d_minmax, 32, cudaMemcpyDeviceToHost, s));
-    if (h->nhll) CU(cudaMemcpyAsync(h->h_hll.data(), h->d_hll, h->nhll * 4, cudaMemcpyDeviceToHost, s));
+    if (h->nhll) CU(cudaMemcpyAsync(h->h_hll.data(), h->d_hll, h->nhll, cudaMemcpyDeviceToHost, s));
     unsigned long long alive = 0;
     if (h->d_alive_table) CU(cudaMemcpyAsync(&alive, h->d_scalar, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -744,10 +753,16 @@ extern "C" int kta_timestamps(const kta_handle *h, int64_t *earliest_s, int32_t 
     if (rc) return rc;
     // src/metric.rs:39-40,65-72,209-211: seconds = ms / 1000 truncating; earliest starts at Utc::now(),
     // latest at the epoch.  Truncating division is monotone, so min/max commute with it.
+    // The device tracks the extrema of the RAW ts_ms column; "not available" (-1) maps to 0 (metric.rs:209).
+    // That map only moves -1 to 0, so: raw min == -1 ⇒ every other value is >= 0 ⇒ mapped min is 0, otherwise
+    // the mapped min is the raw min; raw max == -1 ⇒ every other value is < -1 ⇒ mapped max is 0, otherwise
+    // the mapped max is the raw max.
     int64_t es = h->cfg.now_s, ls = 0;
     int32_t ens = h->cfg.now_ns;
     if (h->h_minmax[0] != INT64_MAX) {
-        const int64_t mn = h->h_minmax[0] / 1000, mx = h->h_minmax[1] / 1000;
+        const int64_t raw_mn = h->h_minmax[0] == -1 ? 0 : h->h_minmax[0];
+        const int64_t raw_mx = h->h_minmax[1] == -1 ? 0 : h->h_minmax[1];
+        const int64_t mn = raw_mn / 1000, mx = raw_mx / 1000;
         if (es > mn || (es == mn && ens > 0)) { es = mn; ens = 0; }
         if (ls < mx) ls = mx;
     }
@@ -795,10 +810,10 @@ extern "C" int kta_alive_keys_hll(const kta_handle *h, double *out) {
     const int rc = check_read(h, 0, false);
     if (rc) return rc;
     if (!h->nhll) return fail(KTA_ERR_NOT_ENABLED, "hll_precision was 0");
-    const int p = h->cfg.hll_precision, q = 64 - p;
+    const int p = h->cfg.hll_precision, q = 32 - p;
     const double m = (double)h->nhll;
     std::vector<double> C((size_t)q + 2, 0.0);
-    for (uint32_t r : h->h_hll) C[std::min<uint32_t>(r, (uint32_t)q + 1)] += 1.0;
+    for (uint8_t r : h->h_hll) C[std::min<uint32_t>(r, (uint32_t)q + 1)] += 1.0;
     double z = m * hll_tau(1.0 - C[(size_t)q + 1] / m);
     for (int k = q; k >= 1; k--) z = 0.5 * (z + C[(size_t)k]);
     z += m * hll_sigma(C[0] / m);
@@ -812,7 +827,7 @@ extern "C" int kta_hll_registers(const kta_handle *h, uint8_t *out, size_t cap) 
     if (rc) return rc;
     if (!h->nhll) return fail(KTA_ERR_NOT_ENABLED, "hll_precision was 0");
     if (cap < h->nhll) return fail(KTA_ERR_INVALID, "buffer too small: %zu < %zu", cap, h->nhll);
-    for (size_t i = 0; i < h->nhll; i++) out[i] = (uint8_t)h->h_hll[i];
+    memcpy(out, h->h_hll.data(), h->nhll);
     return KTA_OK;
 }
 
@@ -867,7 +882,7 @@ extern "C" int kta_set_hash_capture(kta_handle *h, uint32_t *dev_out) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int64_t kta_merge_words(const kta_handle *h, int32_t world) {
     if (!h || world < 1) return -1;
-    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * h->nhll);
+    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * (h->nhll / 8));
 }
 
 extern "C" int kta_merge_export_device(kta_handle *h, int32_t rank, int32_t world, uint64_t *dev_buf) {
@@ -887,7 +902,8 @@ extern "C" int kta_merge_import_device(kta_handle *h, int32_t world, const uint6
     if (!h || !dev_buf || world < 1) return fail(KTA_ERR_INVALID, "bad argument");
     int rc;
     if ((rc = set_device(h))) return rc;
-    merge_import_kernel<<<h->sm_count, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll, world,
+    merge_import_kernel<<<h->sm_count, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll,
+                                                           h->d_hll_floor, world,
                                                            reinterpret_cast<const unsigned long long *>(dev_buf));
     h->launches++;
     CU(cudaGetLastError());

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/kta.h"
 
 namespace kta {
@@ -22,16 +24,18 @@ constexpr int WARPS = THREADS / 32;
 constexpr int TILE = KTA_KEY_TILE;        // records per tile
 constexpr int ROWS = TILE / THREADS;      // records per thread per tile
 constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
-constexpr int KEYBUF_COPY = 20480;        // max staged bytes per tile (20 B/record average)
+constexpr int KEYBUF_COPY = 18432;        // max staged bytes per tile (18 B/record average)
 constexpr int KEYBUF = KEYBUF_COPY + 128; // + slack for the (harmless) over-read of the last words
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
 constexpr int PMAX_SMEM = 512;            // partitions whose counters fit in shared memory
+constexpr int FOLD_TILES = 32;            // CTA-private 16-bit-split sums are folded every 32 tiles
+constexpr int SMEM_FIXED = 2 * 8 + 2 * 8 + WARPS * 8 + WARPS * 4 * 8 + 4 * 4;
 
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
-// words of the u32 shared-memory mirror: khist | vhist | ksum_lo | ksum_hi | vsum_lo | vsum_hi | knull
+// words of the u32 shared-memory mirror: khist | vhist | ksum_lo16 | ksum_hi | vsum_lo16 | vsum_hi | knull
 __host__ __device__ inline size_t smem_counter_words(int P) { return (size_t)P * (2 * NB + 5); }
 
 struct ScanParams {
@@ -51,11 +55,12 @@ struct ScanParams {
     int32_t stage_ok;                // key_bytes is 16-byte aligned → bulk-copy staging allowed
     uint64_t key_readable;           // bytes that may be read starting at key_bytes (bulk copies round up to 16)
     unsigned long long *sums;        // [sums_words(P)]
-    long long *minmax;               // [0] min ts_ms, [1] max ts_ms, [2] min size, [3] max size (as u64)
-    uint32_t *hll;                   // [1 << hll_p] registers (u32 each, device side)
+    long long *minmax;               // [0] min raw ts_ms, [1] max raw ts_ms, [2] min size, [3] max size (as u64)
+    uint8_t *hll;                    // [1 << hll_p] registers
+    uint32_t *hll_floor;             // lower bound of every register (monotone; lets most records skip the table)
     unsigned long long *alive_table; // [2^32]
     uint8_t *alive_dirty;            // [2^32 >> DIRTY_SHIFT]
-    uint32_t *hash_out;              // optional per-record hash capture (test hook), 0 for null keys
+    uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -107,17 +112,31 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {  // L2-coherent read
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // the reference hash, src/fnv32.rs:92-101: for each byte { hash ^= byte; hash *= 0x811c9dc5 }
+// The integer ALU pipe is the busiest pipe of the fused kernel (ncu, profiles/), so bytes 1..3 of a
+// word are brought down with a multiply-high on the FMA pipe instead of a shift on the ALU pipe;
+// the byte mask is folded into the xor (one LOP3: h ^ (w & 0xff)).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fnv_step(uint32_t h, uint32_t byte) { return (h ^ byte) * FNV_MULT; }
 
+__device__ __forceinline__ uint32_t shr_fma(uint32_t w, uint32_t two_pow_32_minus_s) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(two_pow_32_minus_s));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t fnv_word(uint32_t h, uint32_t w) {
     h = fnv_step(h, w & 0xffu);
-    h = fnv_step(h, (w >> 8) & 0xffu);
-    h = fnv_step(h, (w >> 16) & 0xffu);
-    h = fnv_step(h, w >> 24);
+    h = fnv_step(h, shr_fma(w, 1u << 24) & 0xffu);
+    h = fnv_step(h, shr_fma(w, 1u << 16) & 0xffu);
+    h = fnv_step(h, shr_fma(w, 1u << 8));
     return h;
 }
 
@@ -126,14 +145,6 @@ __device__ __forceinline__ uint32_t fnv_smem(const uint32_t *buf32, uint32_t a, 
     uint32_t h = FNV_BASIS;
     const uint32_t *wp = buf32 + (a >> 2);
     const uint32_t sh = (a & 3u) * 8u;
-    if (sh == 0 && len == 16 && (a & 15u) == 0) {  // the common fixed 16-byte aligned key: one LDS.128
-        const uint4 q = *reinterpret_cast<const uint4 *>(wp);
-        h = fnv_word(h, q.x);
-        h = fnv_word(h, q.y);
-        h = fnv_word(h, q.z);
-        h = fnv_word(h, q.w);
-        return h;
-    }
     uint32_t lo = wp[0];
     int j = 0;
     for (; j + 4 <= len; j += 4) {
@@ -162,28 +173,63 @@ __device__ __forceinline__ uint32_t fnv_global(const uint8_t *key, int len) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXTENSION (not in the reference): HyperLogLog over the 32-bit reference hash
+// EXTENSION (not in the reference): HyperLogLog over the 32-bit reference hash, remixed by murmur3
+// fmix32 (a bijection, so distinct reference hashes stay distinct).  Registers are bytes in global
+// memory (L2 resident); `floor` is a lower bound of every register, so a record whose rho <= floor
+// cannot change anything and never touches the table — after warm-up that is all but 2^-floor of them.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint64_t hll_mix(uint32_t hash) {
-    uint64_t x = (uint64_t)hash + 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+__host__ __device__ __forceinline__ uint32_t hll_mix(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
 }
 
-__device__ __forceinline__ void hll_update(uint32_t *regs, int p, uint32_t hash) {
-    const uint64_t x = hll_mix(hash);
-    const uint32_t idx = (uint32_t)(x >> (64 - p));
-    const uint64_t rest = x << p;
-    const uint32_t rho = rest ? (uint32_t)__clzll((long long)rest) + 1u : (uint32_t)(64 - p + 1);
-    // registers only grow, so a (possibly stale) cached read is a safe filter: most records stop here
-    if (__ldca(regs + idx) < rho) atomicMax(regs + idx, rho);
+__device__ __noinline__ void hll_slow_update(uint8_t *regs, uint32_t idx, uint32_t rho) {
+    uint32_t *w = reinterpret_cast<uint32_t *>(regs + (idx & ~3u));
+    const uint32_t sh = (idx & 3u) * 8u;
+    uint32_t old = ld_cg_u32(w);
+    while (((old >> sh) & 0xffu) < rho) {
+        const uint32_t nw = (old & ~(0xffu << sh)) | (rho << sh);
+        const uint32_t prev = atomicCAS(w, old, nw);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+__device__ __forceinline__ void hll_update(uint8_t *regs, int p, uint32_t floor, uint32_t hash) {
+    const uint32_t x = hll_mix(hash);
+    const uint32_t rest = x << p;
+    const uint32_t rho = min((uint32_t)__clz((int)rest) + 1u, (uint32_t)(32 - p + 1));
+    if (rho > floor) hll_slow_update(regs, x >> (32 - p), rho);
+}
+
+// one CTA recomputes the floor now and then: min over a snapshot of monotone registers is a valid
+// lower bound for every later moment
+__device__ __forceinline__ void hll_refresh_floor(const uint8_t *regs, int p, uint32_t *floor_var, uint32_t *red32) {
+    const uint32_t nwords = (1u << p) >> 2;
+    uint32_t m = 255;
+    for (uint32_t i = threadIdx.x; i < nwords; i += THREADS) {
+        const uint32_t w = ld_cg_u32(reinterpret_cast<const uint32_t *>(regs) + i);
+        m = min(min(m, w & 0xffu), min((w >> 8) & 0xffu, min((w >> 16) & 0xffu, w >> 24)));
+    }
+    m = __reduce_min_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < WARPS; w++) m = min(m, red32[w]);
+        if (m) atomicMax(floor_var, m);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-partition counters.  SMEM = true: CTA-private u32 words in shared memory (64-bit sums kept as
-// lo word + carry word, exact); SMEM = false: straight 64-bit global atomics (P > PMAX_SMEM).
-// src/metric.rs:74-100 (inc_*), derived at read-back:  key_non_null = Σ khist, alive = Σ vhist,
+// per-partition counters.  SMEM = true: CTA-private u32 words in shared memory, native ATOMS without
+// a return value.  64-bit byte sums are kept as two u32 words — Σ(len & 0xffff) and Σ(len >> 16) —
+// which cannot overflow within FOLD_TILES tiles and are folded into the global u64 sums in between
+// (exact).  SMEM = false: straight 64-bit global atomics (P > PMAX_SMEM).
+// src/metric.rs:74-100 (inc_*); derived at read-back:  key_non_null = Σ khist, alive = Σ vhist,
 // total = key_non_null + key_null, tombstones = total − alive.
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM>
@@ -199,37 +245,45 @@ struct Counters {
         if (SMEM) atomicAdd(&s[(P + p) * NB + ((b + p) & (NB - 1))], c);
         else atomicAdd(&g[(size_t)(P + p) * NB + b], (unsigned long long)c);
     }
-    __device__ __forceinline__ void ksum(int p, uint32_t v) const {
+    __device__ __forceinline__ void sum(int which /*0 key, 1 value*/, int p, uint32_t v) const {
         if (SMEM) {
-            const uint32_t old = atomicAdd(&s[P * (2 * NB) + p], v);
-            if (old + v < old) atomicAdd(&s[P * (2 * NB + 1) + p], 1u);
-        } else atomicAdd(&g[(size_t)P * (2 * NB) + p], (unsigned long long)v);
-    }
-    __device__ __forceinline__ void vsum(int p, uint32_t v) const {
-        if (SMEM) {
-            const uint32_t old = atomicAdd(&s[P * (2 * NB + 2) + p], v);
-            if (old + v < old) atomicAdd(&s[P * (2 * NB + 3) + p], 1u);
-        } else atomicAdd(&g[(size_t)P * (2 * NB + 1) + p], (unsigned long long)v);
+            atomicAdd(&s[P * (2 * NB + 2 * which) + p], v & 0xffffu);
+            if (v >> 16) atomicAdd(&s[P * (2 * NB + 2 * which + 1) + p], v >> 16);
+        } else atomicAdd(&g[(size_t)P * (2 * NB + which) + p], (unsigned long long)v);
     }
     __device__ __forceinline__ void knull(int p, uint32_t c) const {
         if (SMEM) atomicAdd(&s[P * (2 * NB + 4) + p], c);
         else atomicAdd(&g[(size_t)P * (2 * NB + 2) + p], (unsigned long long)c);
     }
+    // fold (and zero) the split sums into the global u64 sums; callers bracket this with __syncthreads
+    __device__ __forceinline__ void fold_sums() const {
+        if (!SMEM) return;
+        for (int i = threadIdx.x; i < 2 * P; i += THREADS) {
+            const int which = i >= P, p = which ? i - P : i;
+            uint32_t *lo = &s[P * (2 * NB + 2 * which) + p], *hi = lo + P;
+            const unsigned long long v = (unsigned long long)*lo + ((unsigned long long)*hi << 16);
+            if (v) {
+                atomicAdd(&g[(size_t)P * (2 * NB + which) + p], v);
+                *lo = 0;
+                *hi = 0;
+            }
+        }
+    }
 };
 
-__device__ __forceinline__ int len_bucket(int len) { return len == 0 ? 0 : 32 - __clz(len); }
+__device__ __forceinline__ int len_bucket(int len) { return 32 - __clz(len); }  // len >= 0; clz(0) == 32
 
 // One row = 32 consecutive records, one per lane.  MessageMetrics::handle_message, metric.rs:206-253.
-template <bool SMEM>
+template <bool SMEM, bool FULL>
 __device__ __forceinline__ void count_row(const Counters<SMEM> &C, bool valid, int p, int kl, int vl, int lane,
                                           uint32_t &bad) {
     const unsigned full = 0xffffffffu;
     const int p0 = __shfl_sync(full, p, 0);
-    const bool ok = valid && (unsigned)p < (unsigned)C.P;
-    const bool uni = __all_sync(full, ok && p == p0 && kl < (1 << 26) && vl < (1 << 26));
+    const bool ok = (FULL || valid) && (unsigned)p < (unsigned)C.P;
+    const bool uni = __all_sync(full, ok && p == p0 && (kl | vl) < (1 << 26));
     if (uni) {
         // the whole row belongs to one partition (the usual shape of a Kafka fetch): aggregate in
-        // the warp, one atomic per distinct (bucket) and per sum
+        // the warp, one atomic per distinct bucket and per sum
         const int kb = kl < 0 ? NB : len_bucket(kl);
         const int vb = vl < 0 ? NB : len_bucket(vl);
         unsigned rem = full;
@@ -251,24 +305,24 @@ __device__ __forceinline__ void count_row(const Counters<SMEM> &C, bool valid, i
             if (lane == leader && b0 != NB) C.vhist(p0, b0, __popc(m));  // metric.rs:239
             rem &= ~m;
         }
-        const uint32_t ks = __reduce_add_sync(full, (uint32_t)(kl > 0 ? kl : 0));
-        const uint32_t vs = __reduce_add_sync(full, (uint32_t)(vl > 0 ? vl : 0));
+        const uint32_t ks = __reduce_add_sync(full, (uint32_t)max(kl, 0));
+        const uint32_t vs = __reduce_add_sync(full, (uint32_t)max(vl, 0));
         if (lane == 0) {
-            if (ks) C.ksum(p0, ks);  // metric.rs:223
-            if (vs) C.vsum(p0, vs);  // metric.rs:237
+            if (ks) C.sum(0, p0, ks);  // metric.rs:223
+            if (vs) C.sum(1, p0, vs);  // metric.rs:237
         }
-    } else if (valid) {
+    } else if (FULL || valid) {
         if (!ok) {
             bad++;
         } else {
             if (kl < 0) C.knull(p, 1u);
             else {
                 C.khist(p, len_bucket(kl), 1u);
-                if (kl) C.ksum(p, (uint32_t)kl);
+                C.sum(0, p, (uint32_t)kl);
             }
             if (vl >= 0) {
                 C.vhist(p, len_bucket(vl), 1u);
-                if (vl) C.vsum(p, (uint32_t)vl);
+                C.sum(1, p, (uint32_t)vl);
             }
         }
     }
@@ -278,12 +332,13 @@ __device__ __forceinline__ void count_row(const Counters<SMEM> &C, bool valid, i
 // the fused scan kernel.  HASH = false: counters + histograms + extrema only (20 B/record, no key
 // bytes touched — the reference without -c).  HASH = true: additionally FNV per key from staged
 // shared memory, alive-table stamps (-c) and/or the in-stream HLL sketch (20 + key bytes per record).
+// CAPTURE = true (tests only) also writes every record's hash to prm.hash_out.
 // Persistent grid; tile t is handled by CTA t % gridDim.x.
 // ------------------------------------------------------------------------------------------------
-template <bool HASH, bool SMEM>
-__global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
+template <bool HASH, bool SMEM, bool CAPTURE>
+__global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [keybuf0 | keybuf1] (HASH) | mbar[2] | span_g0[2] | warp_tot[WARPS] | red[WARPS*4] | span_staged[2] | counters
+    // layout: [keybuf0 | keybuf1] (HASH) | mbar[2] | span_g0[2] | warp_tot[WARPS] | red[WARPS*4] | span_info[4] | counters
     unsigned char *sp = smem_raw;
     unsigned char *keybuf = sp;
     if (HASH) sp += 2 * KEYBUF;
@@ -291,13 +346,14 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
     uint64_t *span_g0 = reinterpret_cast<uint64_t *>(sp); sp += 2 * sizeof(uint64_t);
     uint64_t *warp_tot = reinterpret_cast<uint64_t *>(sp); sp += WARPS * sizeof(uint64_t);
     long long *red = reinterpret_cast<long long *>(sp); sp += WARPS * 4 * sizeof(long long);
-    uint32_t *span_staged = reinterpret_cast<uint32_t *>(sp); sp += 4 * sizeof(uint32_t);
+    uint32_t *span_info = reinterpret_cast<uint32_t *>(sp); sp += 4 * sizeof(uint32_t);  // [0,1] staged, [2,3] hll floor
     uint32_t *scnt = reinterpret_cast<uint32_t *>(sp);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int P = prm.P;
-    Counters<SMEM> C{scnt, prm.sums, P};
+    const Counters<SMEM> C{scnt, prm.sums, P};
 
     if (SMEM) {
         const int nw = (int)smem_counter_words(P);
@@ -310,22 +366,23 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
     }
     __syncthreads();
 
-    // issue the bulk copy of one tile's packed key bytes into buffer b (one thread)
+    // one thread: start the bulk copy of a tile's packed key bytes into buffer b, publish its span
     auto issue = [&](int64_t tile, int b) {
         const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
         const uint64_t a0 = g0 & ~15ull;
         const uint64_t bytes = ((g1 - a0) + 15ull) & ~15ull;
         const bool ok = prm.stage_ok && g1 > g0 && bytes <= (uint64_t)KEYBUF_COPY && a0 + bytes <= prm.key_readable;
         span_g0[b] = g0;
-        span_staged[b] = ok ? 1u : 0u;
+        span_info[b] = ok ? 1u : 0u;
+        if (prm.hll_p) span_info[2 + b] = ld_cg_u32(prm.hll_floor);
         if (ok) {
             mbar_arrive_expect_tx(&mbar[b], (uint32_t)bytes);
             bulk_g2s(keybuf + (size_t)b * KEYBUF, prm.key_bytes + a0, (uint32_t)bytes, &mbar[b]);
         }
     };
 
-    long long tmin = INT64_MAX, tmax = INT64_MIN;         // ts_ms extrema (after None → 0)
-    uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema
+    long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
+    uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones)
     bool sany = false;
     uint32_t bad = 0;
     uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
@@ -333,14 +390,9 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
     int64_t tile = blockIdx.x;
     if (HASH && tid == 0 && tile < prm.ntiles) issue(tile, 0);
 
-    for (int it = 0; tile < prm.ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        __syncthreads();  // (A) everyone is done with buffer buf^1 and with warp_tot
-        if (HASH && tid == 0) {
-            const int64_t next = tile + gridDim.x;
-            if (next < prm.ntiles) issue(next, buf ^ 1);
-        }
-
+    // the body of one tile; FULL = every record of the tile exists (no tail predicates)
+    auto body = [&](auto full_tag, int64_t tile, int buf) {
+        constexpr bool FULL = decltype(full_tag)::value;
         // ---- header columns: 4 rows of 32 consecutive records per warp, fully coalesced ----
         const int64_t rbase = tile * TILE + warp * (32 * ROWS) + lane;
         int p[ROWS], kl[ROWS], vl[ROWS];
@@ -349,7 +401,7 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
             const int64_t r = rbase + 32 * k;
-            valid[k] = r < prm.n;
+            valid[k] = FULL || r < prm.n;
             if (valid[k]) {
                 p[k] = ld_stream_s32(prm.partition + r);
                 ts[k] = ld_stream_s64(prm.ts_ms + r);
@@ -363,15 +415,16 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
         // ---- MessageMetrics::handle_message ----
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
-            count_row<SMEM>(C, valid[k], p[k], kl[k], vl[k], lane, bad);
+            count_row<SMEM, FULL>(C, valid[k], p[k], kl[k], vl[k], lane, bad);
             if (valid[k]) {
-                const long long t = ts[k] == -1 ? 0 : ts[k];  // metric.rs:209 unwrap_or(0)
-                tmin = t < tmin ? t : tmin;                   // metric.rs:247 (seconds taken at read-back)
-                tmax = t > tmax ? t : tmax;
+                // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back:
+                // the raw extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps)
+                tmin = ts[k] < tmin ? ts[k] : tmin;
+                tmax = ts[k] > tmax ? ts[k] : tmax;
                 if (vl[k] >= 0) {                             // metric.rs:249-251: not for tombstones
-                    const uint32_t sz = (uint32_t)(kl[k] > 0 ? kl[k] : 0) + (uint32_t)vl[k];
-                    smin = sz < smin ? sz : smin;
-                    smax = sz > smax ? sz : smax;
+                    const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
+                    smin = min(smin, sz);
+                    smax = max(smax, sz);
                     sany = true;
                 }
             }
@@ -379,16 +432,31 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
 
         if (HASH) {
             // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
-            uint64_t off[ROWS];
+            uint32_t off[ROWS];
+            uint64_t off64[ROWS];
             uint64_t carry = 0;
-            int mx = 0;
+            bool fix16 = true, small = true;
 #pragma unroll
-            for (int k = 0; k < ROWS; k++) mx = max(mx, kl[k]);
-            if (!__any_sync(full, mx >= (1 << 24))) {
+            for (int k = 0; k < ROWS; k++) {
+                fix16 = fix16 && (kl[k] < 0 || kl[k] == 16);
+                small = small && kl[k] < (1 << 20);
+            }
+            fix16 = __all_sync(full, fix16);
+            if (fix16) {
+                // every key of this warp is null or 16 bytes: offsets from ballots, no shuffle scan
+                uint32_t before = 0;
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    const unsigned m = __ballot_sync(full, kl[k] >= 0);
+                    off[k] = 16u * (before + __popc(m & lt_mask));
+                    before += __popc(m);
+                }
+                carry = 16u * before;
+            } else if (__all_sync(full, small)) {
                 uint32_t c32 = 0;
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
-                    const uint32_t v = (uint32_t)(kl[k] > 0 ? kl[k] : 0);
+                    const uint32_t v = (uint32_t)max(kl[k], 0);
                     uint32_t inc = v;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -402,56 +470,102 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
             } else {
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
-                    const uint64_t v = (uint64_t)(kl[k] > 0 ? kl[k] : 0);
+                    const uint64_t v = (uint64_t)max(kl[k], 0);
                     uint64_t inc = v;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const uint64_t t = __shfl_up_sync(full, inc, d);
                         if (lane >= d) inc += t;
                     }
-                    off[k] = carry + inc - v;
+                    off64[k] = carry + inc - v;
+                    off[k] = (uint32_t)off64[k];
                     carry += __shfl_sync(full, inc, 31);
                 }
             }
             if (lane == 0) warp_tot[warp] = carry;
             __syncthreads();  // (B)
-            uint64_t wbase = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; w++) wbase += (w < warp) ? warp_tot[w] : 0;
-
+            const bool staged = span_info[buf] != 0;
+            const uint32_t floor = prm.hll_p ? span_info[2 + buf] : 0u;
             const uint64_t g0 = span_g0[buf];
-            const bool staged = span_staged[buf] != 0;
+            const uint32_t *kb32 = reinterpret_cast<const uint32_t *>(keybuf + (size_t)buf * KEYBUF);
+            uint32_t h[ROWS];
+
             if (staged) {
+                // staged ⇒ the tile's keys total <= KEYBUF_COPY bytes: 32-bit offsets, one REDUX for the warp base
+                const uint32_t mine = (lane < warp) ? (uint32_t)warp_tot[lane] : 0u;
+                const uint32_t a0 = (uint32_t)(g0 & 15ull) + __reduce_add_sync(full, mine);
                 mbar_wait(&mbar[buf], (phase >> buf) & 1u);
                 phase ^= 1u << buf;
+                if (fix16 && (a0 & 15u) == 0) {
+                    // four independent FNV chains per thread, one LDS.128 each (null keys hash garbage, unused)
+                    uint4 q[ROWS];
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {
+                        q[k] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(kb32) + a0 + off[k]);
+                        h[k] = FNV_BASIS;
+                    }
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].x);
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].y);
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].z);
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].w);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) h[k] = kl[k] >= 0 ? fnv_smem(kb32, a0 + off[k], kl[k]) : 0u;
+                }
+            } else {
+                uint64_t wbase = 0;
+                for (int w = 0; w < warp; w++) wbase += warp_tot[w];
+                const bool wide = !fix16 && !__all_sync(full, small);
+#pragma unroll
+                for (int k = 0; k < ROWS; k++)
+                    h[k] = (valid[k] && kl[k] >= 0)
+                               ? fnv_global(prm.key_bytes + g0 + wbase + (wide ? off64[k] : (uint64_t)off[k]), kl[k])
+                               : 0u;
             }
-            const uint32_t *kb32 = reinterpret_cast<const uint32_t *>(keybuf + (size_t)buf * KEYBUF);
-            const uint32_t a0 = (uint32_t)(g0 & 15ull);
 
             // ---- LogCompactionInMemoryMetrics::handle_message, metric.rs:288-305 ----
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                if (valid[k] && kl[k] >= 0) {   // metric.rs:291 Some(k); None => {} (:302)
-                    const uint64_t o = wbase + off[k];
-                    const uint32_t h = staged ? fnv_smem(kb32, a0 + (uint32_t)o, kl[k])
-                                              : fnv_global(prm.key_bytes + g0 + o, kl[k]);
-                    const int64_t r = rbase + 32 * k;
-                    if (prm.hash_out) prm.hash_out[r] = h;
+                const int64_t r = rbase + 32 * k;
+                const bool keyed = valid[k] && kl[k] >= 0;   // metric.rs:291 Some(k); None => {} (:302)
+                if (CAPTURE && valid[k]) prm.hash_out[r] = keyed ? h[k] : 0u;
+                if (keyed) {
                     if (prm.exact) {
                         // last-writer-wins per hash in seq order == BitSet insert/remove replayed in
                         // order (metric.rs:295 mark_key_alive, :298 mark_key_dead)
                         const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
                         const unsigned long long stamp = ((seq + 1ull) << 1) | (vl[k] >= 0 ? 1ull : 0ull);
-                        atomicMax(prm.alive_table + h, stamp);
-                        uint8_t *d = prm.alive_dirty + (h >> DIRTY_SHIFT);
+                        atomicMax(prm.alive_table + h[k], stamp);
+                        uint8_t *d = prm.alive_dirty + (h[k] >> DIRTY_SHIFT);
                         if (__ldca(d) == 0) *d = 1;
                     }
-                    if (prm.hll_p && vl[k] >= 0) hll_update(prm.hll, prm.hll_p, h);
-                } else if (prm.hash_out && valid[k]) {
-                    prm.hash_out[rbase + 32 * k] = 0;
+                    if (prm.hll_p && vl[k] >= 0) hll_update(prm.hll, prm.hll_p, floor, h[k]);
                 }
             }
         }
+    };
+
+    for (int it = 0; tile < prm.ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        __syncthreads();  // (A) everyone is done with buffer buf^1, warp_tot and the previous tile's atomics
+        if (SMEM && it && (it & (FOLD_TILES - 1)) == 0) {
+            C.fold_sums();
+            __syncthreads();
+        }
+        if (HASH && prm.hll_p && (tile & 63) == 0) {
+            hll_refresh_floor(prm.hll, prm.hll_p, prm.hll_floor, reinterpret_cast<uint32_t *>(red));
+            __syncthreads();
+        }
+        if (HASH && tid == 0) {
+            const int64_t next = tile + gridDim.x;
+            if (next < prm.ntiles) issue(next, buf ^ 1);
+        }
+        if ((tile + 1) * TILE <= prm.n) body(std::true_type{}, tile, buf);
+        else body(std::false_type{}, tile, buf);
     }
 
     // ---- flush CTA-private state ----
@@ -466,14 +580,9 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
                 atomicAdd(&prm.sums[(size_t)(i / NB) * NB + b], (unsigned long long)v);
             }
         }
+        C.fold_sums();
         for (int i = tid; i < P; i += THREADS) {
-            const unsigned long long ks = (unsigned long long)scnt[P * (2 * NB) + i] |
-                                          ((unsigned long long)scnt[P * (2 * NB + 1) + i] << 32);
-            const unsigned long long vs = (unsigned long long)scnt[P * (2 * NB + 2) + i] |
-                                          ((unsigned long long)scnt[P * (2 * NB + 3) + i] << 32);
             const uint32_t kn = scnt[P * (2 * NB + 4) + i];
-            if (ks) atomicAdd(&prm.sums[(size_t)P * (2 * NB) + i], ks);
-            if (vs) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 1) + i], vs);
             if (kn) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 2) + i], (unsigned long long)kn);
         }
     }
@@ -490,6 +599,7 @@ __global__ void __launch_bounds__(THREADS) scan_kernel(const ScanParams prm) {
         smax64 = e > smax64 ? e : smax64;
         bad += __shfl_xor_sync(full, bad, d);
     }
+    __syncthreads();
     if (lane == 0) {
         red[warp * 4 + 0] = tmin; red[warp * 4 + 1] = tmax; red[warp * 4 + 2] = smin64; red[warp * 4 + 3] = smax64;
         if (bad) atomicAdd(&prm.sums[sums_words(P) - 1], (unsigned long long)bad);
@@ -582,7 +692,7 @@ constexpr int PAGE_ENTRIES = 1 << DIRTY_SHIFT;
 
 __global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned long long *table, const uint8_t *dirty,
                                                                 uint32_t npages, unsigned long long *alive_count,
-                                                                uint32_t *hll, int hll_p) {
+                                                                uint8_t *hll, int hll_p) {
     unsigned long long local = 0;
     for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
         if (!dirty[page]) continue;
@@ -591,7 +701,7 @@ __global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned l
             const unsigned long long v = pg[i];
             if (v & 1ull) {
                 local++;
-                if (hll_p) hll_update(hll, hll_p, (page << DIRTY_SHIFT) + (uint32_t)i);
+                if (hll_p) hll_update(hll, hll_p, 0u, (page << DIRTY_SHIFT) + (uint32_t)i);
             }
         }
     }
@@ -647,16 +757,19 @@ __global__ void __launch_bounds__(THREADS) alive_clear_kernel(unsigned long long
     }
 }
 
-// state (re)initialisation: sums = 0, minmax = {+inf, -inf, u64 max, 0}, hll = 0
-__global__ void state_init_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint32_t *hll, size_t nhll) {
+// state (re)initialisation: sums = 0, minmax = {+inf, -inf, u64 max, 0}, hll = 0, hll floor = 0
+__global__ void state_init_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint8_t *hll, size_t nhll,
+                                  uint32_t *hll_floor) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsums; i += stride) sums[i] = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nhll; i += stride) hll[i] = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nhll / 4; i += stride)
+        reinterpret_cast<uint32_t *>(hll)[i] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         minmax[0] = INT64_MAX;
         minmax[1] = INT64_MIN;
         reinterpret_cast<unsigned long long *>(minmax)[2] = ~0ull;
         reinterpret_cast<unsigned long long *>(minmax)[3] = 0ull;
+        *hll_floor = 0;
     }
 }
 
@@ -667,36 +780,47 @@ __global__ void fnv32_kernel(int64_t n, const int32_t *key_len, const uint64_t *
         out[i] = key_len[i] < 0 ? 0u : fnv_global(key_bytes + key_off[i], key_len[i]);
 }
 
-// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×hll words] ----
+// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×(nhll/8) register words] ----
+// Every rank writes its min/max scalars and HLL registers into its own slot and zeros elsewhere, so ONE
+// SUM all-reduce over u64 delivers every rank's values to every rank; the import folds them.
 __global__ void merge_export_kernel(const unsigned long long *sums, size_t nsums, const long long *minmax,
-                                    const uint32_t *hll, size_t nhll, int rank, int world, unsigned long long *buf) {
+                                    const uint8_t *hll, size_t nhll, int rank, int world, unsigned long long *buf) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nmm = (size_t)world * 4, total = nsums + nmm + (size_t)world * nhll;
+    const size_t nmm = (size_t)world * 4, hw = nhll / 8, total = nsums + nmm + (size_t)world * hw;
     for (size_t i = t0; i < total; i += stride) {
         unsigned long long v = 0;
         if (i < nsums) v = sums[i];
         else if (i < nsums + nmm) {
             const size_t j = i - nsums;
-            // stored biased so that "no contribution" (0) is neutral for every rank slot but ours
             if ((int)(j / 4) == rank) v = (unsigned long long)minmax[j % 4];
         } else {
             const size_t j = i - nsums - nmm;
-            if ((int)(j / nhll) == rank) v = hll[j % nhll];
+            if ((int)(j / hw) == rank) v = reinterpret_cast<const unsigned long long *>(hll)[j % hw];
         }
         buf[i] = v;
     }
 }
 
-__global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint32_t *hll,
-                                    size_t nhll, int world, const unsigned long long *buf) {
+__global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint8_t *hll,
+                                    size_t nhll, uint32_t *hll_floor, int world, const unsigned long long *buf) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = t0; i < nsums; i += stride) sums[i] = buf[i];
     const unsigned long long *mm = buf + nsums;
+    const size_t hw = nhll / 8;
     const unsigned long long *hb = mm + (size_t)world * 4;
-    for (size_t i = t0; i < nhll; i += stride) {
+    for (size_t i = t0; i < hw; i += stride) {
         unsigned long long m = 0;
-        for (int r = 0; r < world; r++) m = max(m, hb[(size_t)r * nhll + i]);
-        hll[i] = (uint32_t)m;
+        for (int r = 0; r < world; r++) {
+            const unsigned long long v = hb[(size_t)r * hw + i];
+            unsigned long long o = 0;
+#pragma unroll
+            for (int b = 0; b < 64; b += 8) {
+                const unsigned long long x = (m >> b) & 0xff, y = (v >> b) & 0xff;
+                o |= (x > y ? x : y) << b;   // bytewise max
+            }
+            m = o;
+        }
+        reinterpret_cast<unsigned long long *>(hll)[i] = m;
     }
     if (t0 == 0) {
         long long tmin = INT64_MAX, tmax = INT64_MIN;
@@ -711,6 +835,7 @@ __global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long
         minmax[1] = tmax;
         reinterpret_cast<unsigned long long *>(minmax)[2] = smin;
         reinterpret_cast<unsigned long long *>(minmax)[3] = smax;
+        *hll_floor = 0;
     }
 }
 

@@ -372,20 +372,23 @@ void kto_hist(const kto *o, int which, int32_t p, uint64_t out[KTO_HIST_BUCKETS]
         out[b] = pmap_get(which ? &o->vhist[b] : &o->khist[b], p);
 }
 
-/* splitmix64 finaliser (Steele, Lea, Flood 2014) applied to the zero-extended 32-bit hash */
-uint64_t kto_hll_mix(uint32_t hash) {
-    uint64_t x = (uint64_t)hash + 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+/* murmur3 fmix32 (Appleby): a bijection on 32 bits, so distinct reference hashes stay distinct */
+uint32_t kto_hll_mix(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
 }
 
-/* Flajolet et al. 2007: register index = top `precision` bits, rho = 1 + leading zeros of the rest */
+/* Flajolet et al. 2007 over the 32-bit mixed hash: register index = top `precision` bits,
+ * rho = 1 + leading zeros of the remaining 32 - precision bits (max 32 - precision + 1) */
 void kto_hll_insert(uint8_t *regs, int precision, uint32_t hash) {
-    uint64_t x = kto_hll_mix(hash);
-    uint32_t idx = (uint32_t)(x >> (64 - precision));
-    uint64_t rest = x << precision;
-    int rho = rest ? __builtin_clzll(rest) + 1 : (64 - precision + 1);
+    uint32_t x = kto_hll_mix(hash);
+    uint32_t idx = x >> (32 - precision);
+    uint32_t rest = x << precision;
+    int rho = rest ? __builtin_clz(rest) + 1 : (32 - precision + 1);
     if (regs[idx] < rho) regs[idx] = (uint8_t)rho;
 }
 
@@ -416,9 +419,9 @@ static double hll_tau(double x) {
 /* Ertl 2017, "New cardinality estimation algorithms for HyperLogLog sketches", improved raw
  * estimator (no empirical bias tables, no small/large-range switch). */
 double kto_hll_estimate(const uint8_t *regs, int precision) {
-    int q = 64 - precision;
+    int q = 32 - precision;
     size_t m = (size_t)1 << precision;
-    double C[66];
+    double C[34];
     for (int k = 0; k <= q + 1; k++) C[k] = 0;
     for (size_t i = 0; i < m; i++) C[regs[i]] += 1.0;
     double z = (double)m * hll_tau(1.0 - C[q + 1] / (double)m);

@@ -89,8 +89,8 @@ void kto_test_set_counter(kto *o, int which, int32_t p, uint64_t v);
 #define KTO_HIST_BUCKETS 32
 /* bucket(len) = len == 0 ? 0 : 1 + floor(log2(len)); null lengths are not counted. */
 void kto_hist(const kto *o, int which /*0 key, 1 value*/, int32_t p, uint64_t out[KTO_HIST_BUCKETS]);
-/* HyperLogLog over 32-bit reference hashes, widened by a splitmix64 finaliser.  precision 4..18. */
-uint64_t kto_hll_mix(uint32_t hash);
+/* HyperLogLog over the 32-bit reference hash, remixed by murmur3 fmix32 (a bijection).  precision 4..18. */
+uint32_t kto_hll_mix(uint32_t hash);
 void kto_hll_insert(uint8_t *regs, int precision, uint32_t hash);
 double kto_hll_estimate(const uint8_t *regs, int precision);
 /* registers of the in-stream sketch: every record with key AND value non-null is inserted. */

@@ -54,7 +54,7 @@ def olib():
         L.kto_alive_contains.restype = C.c_int
         L.kto_alive_contains.argtypes = [P, C.c_uint32]
         L.kto_hist.argtypes = [P, C.c_int, C.c_int32, P]
-        L.kto_hll_mix.restype = u64
+        L.kto_hll_mix.restype = C.c_uint32
         L.kto_hll_mix.argtypes = [C.c_uint32]
         L.kto_hll_insert.argtypes = [P, C.c_int, C.c_uint32]
         L.kto_hll_estimate.restype = C.c_double
