@@ -39,7 +39,7 @@ extern "C" {
 #endif
 
 #define KTA_ABI_VERSION 1
-#define KTA_KEY_TILE 1024     /* records per key tile (granularity of kta_batch.key_tile_base) */
+#define KTA_KEY_TILE 128      /* records per key tile (granularity of kta_batch.key_tile_base) */
 #define KTA_HIST_BUCKETS 32   /* bucket(len) = len == 0 ? 0 : 1 + floor(log2(len)) */
 
 enum {

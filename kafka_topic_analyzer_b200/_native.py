@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libkta_gpu.so")
 INCLUDE = os.path.normpath(os.path.join(_HERE, "..", "include"))
 
-KTA_KEY_TILE = 1024
+KTA_KEY_TILE = 128
 KTA_HIST_BUCKETS = 32
 INT64_MIN = -(1 << 63)
 

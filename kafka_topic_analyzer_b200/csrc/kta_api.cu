@@ -110,8 +110,10 @@ struct kta_handle {
     std::vector<uint8_t> h_hll;
     uint64_t h_alive = 0;
     // occupancy-derived grids
-    int grid_scan[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // [0 counters, 1 hash, 2 hash+capture][SMEM]
-    size_t smem_scan[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    bool smem_counters = true;               // per-partition counters fit in shared memory
+    size_t smem_optin = 0;
+    int threads_scan[3] = {0, 0, 0};         // [0 counters, 1 hash, 2 hash+capture]
+    size_t smem_scan[3] = {0, 0, 0};
     // stats / timing
     uint64_t launches = 0, records = 0;
     bool timing = false;
@@ -126,20 +128,24 @@ static int set_device(const kta_handle *h) {
     return KTA_OK;
 }
 
-static size_t scan_smem_bytes(bool hash, bool smem, int P) {
-    return (hash ? 2 * (size_t)KEYBUF : 0) + SMEM_FIXED + (smem ? smem_counter_words(P) * 4 : 0);
+static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads) {
+    return (smem ? smem_counter_bytes(P) : 0) + (size_t)(threads / 32) * (hash ? WARP_SMEM : 128);
 }
 
+// one persistent CTA per SM; as many autonomous warps as the shared-memory budget allows
 template <bool HASH, bool SMEM, bool CAPTURE>
 static int prepare_variant(kta_handle *h) {
-    const size_t smem = scan_smem_bytes(HASH, SMEM, h->cfg.num_partitions);
-    CU(cudaFuncSetAttribute(scan_kernel<HASH, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, scan_kernel<HASH, SMEM, CAPTURE>, THREADS, smem));
-    if (occ < 1) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", smem);
     const int v = CAPTURE ? 2 : (HASH ? 1 : 0);
-    h->grid_scan[v][SMEM] = occ * h->sm_count;
-    h->smem_scan[v][SMEM] = smem;
+    int threads = MAX_THREADS;
+    size_t smem = 0;
+    for (;; threads /= 2) {
+        smem = scan_smem_bytes(HASH, SMEM, h->cfg.num_partitions, threads);
+        if (smem <= h->smem_optin || threads == 128) break;
+    }
+    if (smem > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", smem);
+    CU(cudaFuncSetAttribute(scan_kernel<HASH, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->threads_scan[v] = threads;
+    h->smem_scan[v] = smem;
     return KTA_OK;
 }
 
@@ -224,7 +230,10 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
         CU(cudaMemsetAsync(h->d_alive_table, 0, ((size_t)1 << 32) * 8, h->stream));
         CU(cudaMemsetAsync(h->d_alive_dirty, 0, (size_t)1 << (32 - DIRTY_SHIFT), h->stream));
     }
-    const bool smem = P <= PMAX_SMEM;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    // counters in shared memory as long as at least 8 warps still fit beside them
+    h->smem_counters = smem_counter_bytes(P) + 8 * (size_t)WARP_SMEM <= h->smem_optin;
+    const bool smem = h->smem_counters;
     int rc;
     if (smem) {
         if ((rc = prepare_variant<false, true, false>(h))) return rc;
@@ -297,10 +306,11 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
         prm.stage_ok = (((uintptr_t)prm.key_bytes & 15u) == 0) ? 1 : 0;
         prm.key_readable = (uint64_t)key_readable;
     }
-    const bool smem = P <= PMAX_SMEM;
+    const bool smem = h->smem_counters;
     const int variant = h->d_hash_out ? 2 : (hash ? 1 : 0);
-    const int grid = (int)std::min<int64_t>(prm.ntiles, h->grid_scan[variant][smem]);
-    const size_t sm = h->smem_scan[variant][smem];
+    const int threads = h->threads_scan[variant];
+    const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
+    const size_t sm = h->smem_scan[variant];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         if (h->ev_used == h->ev_pool.size()) {
@@ -315,14 +325,14 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
         CU(cudaEventRecord(e0, h->stream));
     }
     if (variant == 2) {
-        if (smem) scan_kernel<true, true, true><<<grid, THREADS, sm, h->stream>>>(prm);
-        else scan_kernel<true, false, true><<<grid, THREADS, sm, h->stream>>>(prm);
+        if (smem) scan_kernel<true, true, true><<<grid, threads, sm, h->stream>>>(prm);
+        else scan_kernel<true, false, true><<<grid, threads, sm, h->stream>>>(prm);
     } else if (variant == 1) {
-        if (smem) scan_kernel<true, true, false><<<grid, THREADS, sm, h->stream>>>(prm);
-        else scan_kernel<true, false, false><<<grid, THREADS, sm, h->stream>>>(prm);
+        if (smem) scan_kernel<true, true, false><<<grid, threads, sm, h->stream>>>(prm);
+        else scan_kernel<true, false, false><<<grid, threads, sm, h->stream>>>(prm);
     } else {
-        if (smem) scan_kernel<false, true, false><<<grid, THREADS, sm, h->stream>>>(prm);
-        else scan_kernel<false, false, false><<<grid, THREADS, sm, h->stream>>>(prm);
+        if (smem) scan_kernel<false, true, false><<<grid, threads, sm, h->stream>>>(prm);
+        else scan_kernel<false, false, false><<<grid, threads, sm, h->stream>>>(prm);
     }
     CU(cudaGetLastError());
     if (h->timing) CU(cudaEventRecord(e1, h->stream));
@@ -345,8 +355,8 @@ static int collect_timing(kta_handle *h) {
 
 static int derive_tile_base(kta_handle *h, const int32_t *d_klen, int64_t n, uint64_t *d_tile_base) {
     const int64_t ntiles = (n + TILE - 1) / TILE;
-    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)h->sm_count * 8);
-    tile_key_bytes_kernel<<<grid, THREADS, 0, h->stream>>>(d_klen, n, ntiles, d_tile_base);
+    const int grid = (int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)h->sm_count * 8);
+    tile_key_bytes_kernel<<<grid, 256, 0, h->stream>>>(d_klen, n, ntiles, d_tile_base);
     CU(cudaGetLastError());
     tile_base_scan_kernel<<<1, 1024, 0, h->stream>>>(d_tile_base, ntiles);
     CU(cudaGetLastError());

@@ -19,24 +19,24 @@
 
 namespace kta {
 
-constexpr int THREADS = 256;
-constexpr int WARPS = THREADS / 32;
-constexpr int TILE = KTA_KEY_TILE;        // records per tile
-constexpr int ROWS = TILE / THREADS;      // records per thread per tile
+constexpr int MAX_THREADS = 1024;         // one persistent CTA per SM, up to 32 autonomous warps
+constexpr int TILE = KTA_KEY_TILE;        // records per warp tile (128)
+constexpr int ROWS = TILE / 32;           // records per lane per tile
 constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
-constexpr int KEYBUF_COPY = 18432;        // max staged bytes per tile (18 B/record average)
-constexpr int KEYBUF = KEYBUF_COPY + 128; // + slack for the (harmless) over-read of the last words
+constexpr int KEYBUF_COPY = TILE * 18;    // max staged key bytes per tile (18 B/record average)
+constexpr int KEYBUF = KEYBUF_COPY + 64;  // + slack for the (harmless) over-read of the last words
+constexpr int WARP_SMEM = 128 + 2 * KEYBUF;  // per warp: 2 mbarriers (+ scratch) and a double-buffered key stage
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
-constexpr int PMAX_SMEM = 512;            // partitions whose counters fit in shared memory
-constexpr int FOLD_TILES = 32;            // CTA-private 16-bit-split sums are folded every 32 tiles
-constexpr int SMEM_FIXED = 2 * 8 + 2 * 8 + WARPS * 8 + WARPS * 4 * 8 + 4 * 4;
+constexpr int FOLD_TILES = 4;             // every warp checks the CTA's 16-bit-split sums every 4 of its tiles
 
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
-// words of the u32 shared-memory mirror: khist | vhist | ksum_lo16 | ksum_hi | vsum_lo16 | vsum_hi | knull
+// words of the u32 shared-memory mirror, bucket-major: khist[32][P] | vhist[32][P] | ksum_lo16[P] | ksum_hi[P] |
+// vsum_lo16[P] | vsum_hi[P] | knull[P]
 __host__ __device__ inline size_t smem_counter_words(int P) { return (size_t)P * (2 * NB + 5); }
+__host__ __device__ inline size_t smem_counter_bytes(int P) { return (smem_counter_words(P) * 4 + 127) & ~(size_t)127; }
 
 struct ScanParams {
     int64_t n;
@@ -177,6 +177,7 @@ __device__ __forceinline__ uint32_t fnv_global(const uint8_t *key, int len) {
 // fmix32 (a bijection, so distinct reference hashes stay distinct).  Registers are bytes in global
 // memory (L2 resident); `floor` is a lower bound of every register, so a record whose rho <= floor
 // cannot change anything and never touches the table — after warm-up that is all but 2^-floor of them.
+// rho <= floor  ⇔  the top `floor` bits below the index bits are not all zero  ⇔  (x & skip_mask) != 0.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t hll_mix(uint32_t h) {
     h ^= h >> 16;
@@ -187,7 +188,15 @@ __host__ __device__ __forceinline__ uint32_t hll_mix(uint32_t h) {
     return h;
 }
 
-__device__ __noinline__ void hll_slow_update(uint8_t *regs, uint32_t idx, uint32_t rho) {
+__device__ __forceinline__ uint32_t hll_skip_mask(int p, uint32_t floor) {
+    const uint32_t f = min(floor, (uint32_t)(32 - p));
+    return f ? (((1u << f) - 1u) << (32 - p - f)) : 0u;
+}
+
+__device__ __noinline__ void hll_slow_update(uint8_t *regs, int p, uint32_t x) {
+    const uint32_t idx = x >> (32 - p);
+    const uint32_t rest = x << p;
+    const uint32_t rho = min((uint32_t)__clz((int)rest) + 1u, (uint32_t)(32 - p + 1));
     uint32_t *w = reinterpret_cast<uint32_t *>(regs + (idx & ~3u));
     const uint32_t sh = (idx & 3u) * 8u;
     uint32_t old = ld_cg_u32(w);
@@ -199,36 +208,30 @@ __device__ __noinline__ void hll_slow_update(uint8_t *regs, uint32_t idx, uint32
     }
 }
 
-__device__ __forceinline__ void hll_update(uint8_t *regs, int p, uint32_t floor, uint32_t hash) {
+__device__ __forceinline__ void hll_update(uint8_t *regs, int p, uint32_t skip_mask, uint32_t hash) {
     const uint32_t x = hll_mix(hash);
-    const uint32_t rest = x << p;
-    const uint32_t rho = min((uint32_t)__clz((int)rest) + 1u, (uint32_t)(32 - p + 1));
-    if (rho > floor) hll_slow_update(regs, x >> (32 - p), rho);
+    if ((x & skip_mask) == 0) hll_slow_update(regs, p, x);
 }
 
-// one CTA recomputes the floor now and then: min over a snapshot of monotone registers is a valid
+// one warp recomputes the floor now and then: the min over a snapshot of monotone registers is a valid
 // lower bound for every later moment
-__device__ __forceinline__ void hll_refresh_floor(const uint8_t *regs, int p, uint32_t *floor_var, uint32_t *red32) {
+__device__ __forceinline__ void hll_refresh_floor(const uint8_t *regs, int p, uint32_t *floor_var, int lane) {
     const uint32_t nwords = (1u << p) >> 2;
     uint32_t m = 255;
-    for (uint32_t i = threadIdx.x; i < nwords; i += THREADS) {
+    for (uint32_t i = lane; i < nwords; i += 32) {
         const uint32_t w = ld_cg_u32(reinterpret_cast<const uint32_t *>(regs) + i);
         m = min(min(m, w & 0xffu), min((w >> 8) & 0xffu, min((w >> 16) & 0xffu, w >> 24)));
     }
     m = __reduce_min_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0) red32[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < WARPS; w++) m = min(m, red32[w]);
-        if (m) atomicMax(floor_var, m);
-    }
+    if (lane == 0 && m) atomicMax(floor_var, m);
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-partition counters.  SMEM = true: CTA-private u32 words in shared memory, native ATOMS without
-// a return value.  64-bit byte sums are kept as two u32 words — Σ(len & 0xffff) and Σ(len >> 16) —
-// which cannot overflow within FOLD_TILES tiles and are folded into the global u64 sums in between
-// (exact).  SMEM = false: straight 64-bit global atomics (P > PMAX_SMEM).
+// per-partition counters.  SMEM = true: CTA-private u32 words in shared memory (bucket-major, so the
+// index is one multiply-add), native ATOMS without a return value.  64-bit byte sums are kept as two
+// u32 words — Σ(len & 0xffff) and Σ(len >> 16) — that every warp drains into the global u64 sums with
+// an atomic exchange every FOLD_TILES of its tiles, which bounds what can accumulate in between (exact).
+// SMEM = false: straight 64-bit global atomics (P too large for shared memory).
 // src/metric.rs:74-100 (inc_*); derived at read-back:  key_non_null = Σ khist, alive = Σ vhist,
 // total = key_non_null + key_null, tombstones = total − alive.
 // ------------------------------------------------------------------------------------------------
@@ -238,34 +241,36 @@ struct Counters {
     unsigned long long *g;
     int P;
     __device__ __forceinline__ void khist(int p, int b, uint32_t c) const {
-        if (SMEM) atomicAdd(&s[p * NB + ((b + p) & (NB - 1))], c);
+        if (SMEM) atomicAdd(&s[b * P + p], c);
         else atomicAdd(&g[(size_t)p * NB + b], (unsigned long long)c);
     }
     __device__ __forceinline__ void vhist(int p, int b, uint32_t c) const {
-        if (SMEM) atomicAdd(&s[(P + p) * NB + ((b + p) & (NB - 1))], c);
+        if (SMEM) atomicAdd(&s[(NB + b) * P + p], c);
         else atomicAdd(&g[(size_t)(P + p) * NB + b], (unsigned long long)c);
     }
     __device__ __forceinline__ void sum(int which /*0 key, 1 value*/, int p, uint32_t v) const {
         if (SMEM) {
-            atomicAdd(&s[P * (2 * NB + 2 * which) + p], v & 0xffffu);
-            if (v >> 16) atomicAdd(&s[P * (2 * NB + 2 * which + 1) + p], v >> 16);
+            atomicAdd(&s[(2 * NB + 2 * which) * P + p], v & 0xffffu);
+            if (v >> 16) atomicAdd(&s[(2 * NB + 2 * which + 1) * P + p], v >> 16);
         } else atomicAdd(&g[(size_t)P * (2 * NB + which) + p], (unsigned long long)v);
     }
     __device__ __forceinline__ void knull(int p, uint32_t c) const {
-        if (SMEM) atomicAdd(&s[P * (2 * NB + 4) + p], c);
+        if (SMEM) atomicAdd(&s[(2 * NB + 4) * P + p], c);
         else atomicAdd(&g[(size_t)P * (2 * NB + 2) + p], (unsigned long long)c);
     }
-    // fold (and zero) the split sums into the global u64 sums; callers bracket this with __syncthreads
-    __device__ __forceinline__ void fold_sums() const {
+    // One warp drains split sums that reached `threshold` into the global u64 sums; safe against concurrent
+    // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp checks every FOLD_TILES of
+    // its tiles, so between two checks of an entry each of the <= 32 warps adds fewer than 2*FOLD_TILES*128
+    // values < 2^16: growth < 32 * 1024 * 65535 < 2^31, and a word that passed a check was < 2^30.
+    __device__ __forceinline__ void fold_sums(int lane, uint32_t threshold) const {
         if (!SMEM) return;
-        for (int i = threadIdx.x; i < 2 * P; i += THREADS) {
+        for (int i = lane; i < 2 * P; i += 32) {
             const int which = i >= P, p = which ? i - P : i;
-            uint32_t *lo = &s[P * (2 * NB + 2 * which) + p], *hi = lo + P;
-            const unsigned long long v = (unsigned long long)*lo + ((unsigned long long)*hi << 16);
-            if (v) {
-                atomicAdd(&g[(size_t)P * (2 * NB + which) + p], v);
-                *lo = 0;
-                *hi = 0;
+            uint32_t *lo = &s[(2 * NB + 2 * which) * P + p];
+            if (*(volatile uint32_t *)lo >= threshold || *(volatile uint32_t *)(lo + P) >= threshold) {
+                const unsigned long long v = (unsigned long long)atomicExch(lo, 0u) +
+                                             ((unsigned long long)atomicExch(lo + P, 0u) << 16);
+                if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], v);
             }
         }
     }
@@ -328,53 +333,75 @@ __device__ __forceinline__ void count_row(const Counters<SMEM> &C, bool valid, i
     }
 }
 
+// rare path: a tile with a key of >= 1 MiB — 64-bit offsets, keys read straight from global memory.
+// Out of line and self-contained (re-reads key_len, hands the hashes back through the warp's shared
+// scratch) so that it costs the hot path no registers.
+__device__ __noinline__ void wide_tile_hashes(const int32_t *key_len, int64_t n, const uint8_t *tile_keys, int64_t tile,
+                                              uint32_t *out /*[TILE]*/, int lane) {
+    uint64_t carry = 0;
+    for (int k = 0; k < ROWS; k++) {
+        const int64_t r = tile * TILE + 32 * k + lane;
+        const int kl = r < n ? key_len[r] : -1;
+        const uint64_t v = (uint64_t)max(kl, 0);
+        uint64_t inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        out[32 * k + lane] = kl >= 0 ? fnv_global(tile_keys + carry + inc - v, kl) : 0u;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused scan kernel.  HASH = false: counters + histograms + extrema only (20 B/record, no key
 // bytes touched — the reference without -c).  HASH = true: additionally FNV per key from staged
 // shared memory, alive-table stamps (-c) and/or the in-stream HLL sketch (20 + key bytes per record).
 // CAPTURE = true (tests only) also writes every record's hash to prm.hash_out.
-// Persistent grid; tile t is handled by CTA t % gridDim.x.
+//
+// One persistent CTA per SM; every WARP is an autonomous worker: it walks its own 128-record tiles
+// (tile t belongs to global warp t % total_warps), stages each tile's packed key bytes with its own
+// bulk async copy (cp.async.bulk → UBLKCP) on its own pair of mbarriers, and never waits for another
+// warp — there is no __syncthreads in the loop, so the load phase of one warp overlaps the hash phase of
+// the others.  Only the per-partition counters are shared (shared-memory atomics).
 // ------------------------------------------------------------------------------------------------
 template <bool HASH, bool SMEM, bool CAPTURE>
-__global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) {
+__global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [keybuf0 | keybuf1] (HASH) | mbar[2] | span_g0[2] | warp_tot[WARPS] | red[WARPS*4] | span_info[4] | counters
-    unsigned char *sp = smem_raw;
-    unsigned char *keybuf = sp;
-    if (HASH) sp += 2 * KEYBUF;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(sp); sp += 2 * sizeof(uint64_t);
-    uint64_t *span_g0 = reinterpret_cast<uint64_t *>(sp); sp += 2 * sizeof(uint64_t);
-    uint64_t *warp_tot = reinterpret_cast<uint64_t *>(sp); sp += WARPS * sizeof(uint64_t);
-    long long *red = reinterpret_cast<long long *>(sp); sp += WARPS * 4 * sizeof(long long);
-    uint32_t *span_info = reinterpret_cast<uint32_t *>(sp); sp += 4 * sizeof(uint32_t);  // [0,1] staged, [2,3] hll floor
-    uint32_t *scnt = reinterpret_cast<uint32_t *>(sp);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int P = prm.P;
+    // layout: counters (SMEM) | per warp: mbar[2] + 112 B scratch | keybuf[2]
+    uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
+    unsigned char *wsm = smem_raw + (SMEM ? smem_counter_bytes(P) : 0) + (size_t)warp * (HASH ? WARP_SMEM : 128);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(wsm);
+    unsigned char *keybuf = wsm + 128;
     const Counters<SMEM> C{scnt, prm.sums, P};
 
     if (SMEM) {
         const int nw = (int)smem_counter_words(P);
-        for (int i = tid; i < nw; i += THREADS) scnt[i] = 0;
+        for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
     }
-    if (HASH && tid == 0) {
+    if (HASH && lane == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    // one thread: start the bulk copy of a tile's packed key bytes into buffer b, publish its span
+    // lane 0: start the bulk copy of a tile's packed key bytes into buffer b; returns the span descriptor
+    uint64_t nxt_g0 = 0;
+    uint32_t nxt_staged = 0, nxt_floor = 0;
     auto issue = [&](int64_t tile, int b) {
         const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
         const uint64_t a0 = g0 & ~15ull;
         const uint64_t bytes = ((g1 - a0) + 15ull) & ~15ull;
         const bool ok = prm.stage_ok && g1 > g0 && bytes <= (uint64_t)KEYBUF_COPY && a0 + bytes <= prm.key_readable;
-        span_g0[b] = g0;
-        span_info[b] = ok ? 1u : 0u;
-        if (prm.hll_p) span_info[2 + b] = ld_cg_u32(prm.hll_floor);
+        nxt_g0 = g0;
+        nxt_staged = ok ? 1u : 0u;
+        nxt_floor = prm.hll_p ? ld_cg_u32(prm.hll_floor) : 0u;
         if (ok) {
             mbar_arrive_expect_tx(&mbar[b], (uint32_t)bytes);
             bulk_g2s(keybuf + (size_t)b * KEYBUF, prm.key_bytes + a0, (uint32_t)bytes, &mbar[b]);
@@ -382,19 +409,19 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
     };
 
     long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
-    uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones)
-    bool sany = false;
+    uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
     uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
 
-    int64_t tile = blockIdx.x;
-    if (HASH && tid == 0 && tile < prm.ntiles) issue(tile, 0);
+    const int64_t gstride = (int64_t)gridDim.x * nwarps;
+    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
+    if (HASH && lane == 0 && tile < prm.ntiles) issue(tile, 0);
 
     // the body of one tile; FULL = every record of the tile exists (no tail predicates)
-    auto body = [&](auto full_tag, int64_t tile, int buf) {
+    auto body = [&](auto full_tag, int64_t tile, int buf, uint64_t g0, bool staged, uint32_t skip_mask) {
         constexpr bool FULL = decltype(full_tag)::value;
-        // ---- header columns: 4 rows of 32 consecutive records per warp, fully coalesced ----
-        const int64_t rbase = tile * TILE + warp * (32 * ROWS) + lane;
+        // ---- header columns: 4 rows of 32 consecutive records, fully coalesced ----
+        const int64_t rbase = tile * TILE + lane;
         int p[ROWS], kl[ROWS], vl[ROWS];
         long long ts[ROWS];
         bool valid[ROWS];
@@ -421,20 +448,17 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
                 // the raw extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps)
                 tmin = ts[k] < tmin ? ts[k] : tmin;
                 tmax = ts[k] > tmax ? ts[k] : tmax;
-                if (vl[k] >= 0) {                             // metric.rs:249-251: not for tombstones
-                    const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
-                    smin = min(smin, sz);
-                    smax = max(smax, sz);
-                    sany = true;
-                }
             }
+            // metric.rs:249-251: size extrema, not for tombstones (branch-free; invalid rows have vl = -1)
+            const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
+            smin = min(smin, vl[k] >= 0 ? sz : 0xffffffffu);
+            smax = max(smax, vl[k] >= 0 ? sz : 0u);
         }
 
         if (HASH) {
             // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
             uint32_t off[ROWS];
-            uint64_t off64[ROWS];
-            uint64_t carry = 0;
+            uint32_t h[ROWS];
             bool fix16 = true, small = true;
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
@@ -442,8 +466,9 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
                 small = small && kl[k] < (1 << 20);
             }
             fix16 = __all_sync(full, fix16);
+            small = fix16 || __all_sync(full, small);
             if (fix16) {
-                // every key of this warp is null or 16 bytes: offsets from ballots, no shuffle scan
+                // every key of this tile is null or 16 bytes: offsets from ballots, no shuffle scan
                 uint32_t before = 0;
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
@@ -451,8 +476,7 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
                     off[k] = 16u * (before + __popc(m & lt_mask));
                     before += __popc(m);
                 }
-                carry = 16u * before;
-            } else if (__all_sync(full, small)) {
+            } else if (small) {
                 uint32_t c32 = 0;
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
@@ -466,65 +490,42 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
                     off[k] = c32 + inc - v;
                     c32 += __shfl_sync(full, inc, 31);
                 }
-                carry = c32;
-            } else {
-#pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    const uint64_t v = (uint64_t)max(kl[k], 0);
-                    uint64_t inc = v;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint64_t t = __shfl_up_sync(full, inc, d);
-                        if (lane >= d) inc += t;
-                    }
-                    off64[k] = carry + inc - v;
-                    off[k] = (uint32_t)off64[k];
-                    carry += __shfl_sync(full, inc, 31);
-                }
             }
-            if (lane == 0) warp_tot[warp] = carry;
-            __syncthreads();  // (B)
-            const bool staged = span_info[buf] != 0;
-            const uint32_t floor = prm.hll_p ? span_info[2 + buf] : 0u;
-            const uint64_t g0 = span_g0[buf];
-            const uint32_t *kb32 = reinterpret_cast<const uint32_t *>(keybuf + (size_t)buf * KEYBUF);
-            uint32_t h[ROWS];
+            const unsigned char *kb8 = keybuf + (size_t)buf * KEYBUF;
 
-            if (staged) {
-                // staged ⇒ the tile's keys total <= KEYBUF_COPY bytes: 32-bit offsets, one REDUX for the warp base
-                const uint32_t mine = (lane < warp) ? (uint32_t)warp_tot[lane] : 0u;
-                const uint32_t a0 = (uint32_t)(g0 & 15ull) + __reduce_add_sync(full, mine);
+            if (staged) {   // staged ⇒ the tile's keys total <= KEYBUF_COPY bytes ⇒ small
+                const uint32_t a0 = (uint32_t)(g0 & 15ull);
                 mbar_wait(&mbar[buf], (phase >> buf) & 1u);
                 phase ^= 1u << buf;
-                if (fix16 && (a0 & 15u) == 0) {
-                    // four independent FNV chains per thread, one LDS.128 each (null keys hash garbage, unused)
-                    uint4 q[ROWS];
+                if (fix16 && a0 == 0) {
+                    // two independent FNV chains at a time per lane, one LDS.128 per key (null keys hash
+                    // garbage that is never used); the other 7 warps of the SM sub-partition supply the rest of the ILP
 #pragma unroll
-                    for (int k = 0; k < ROWS; k++) {
-                        q[k] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const unsigned char *>(kb32) + a0 + off[k]);
-                        h[k] = FNV_BASIS;
+                    for (int k = 0; k < ROWS; k += 2) {
+                        const uint4 qa = *reinterpret_cast<const uint4 *>(kb8 + off[k]);
+                        const uint4 qb = *reinterpret_cast<const uint4 *>(kb8 + off[k + 1]);
+                        uint32_t ha = FNV_BASIS, hb = FNV_BASIS;
+                        ha = fnv_word(ha, qa.x); hb = fnv_word(hb, qb.x);
+                        ha = fnv_word(ha, qa.y); hb = fnv_word(hb, qb.y);
+                        ha = fnv_word(ha, qa.z); hb = fnv_word(hb, qb.z);
+                        ha = fnv_word(ha, qa.w); hb = fnv_word(hb, qb.w);
+                        h[k] = ha;
+                        h[k + 1] = hb;
                     }
-#pragma unroll
-                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].x);
-#pragma unroll
-                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].y);
-#pragma unroll
-                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].z);
-#pragma unroll
-                    for (int k = 0; k < ROWS; k++) h[k] = fnv_word(h[k], q[k].w);
                 } else {
+                    const uint32_t *kb32 = reinterpret_cast<const uint32_t *>(kb8);
 #pragma unroll
                     for (int k = 0; k < ROWS; k++) h[k] = kl[k] >= 0 ? fnv_smem(kb32, a0 + off[k], kl[k]) : 0u;
                 }
-            } else {
-                uint64_t wbase = 0;
-                for (int w = 0; w < warp; w++) wbase += warp_tot[w];
-                const bool wide = !fix16 && !__all_sync(full, small);
+            } else if (small) {
 #pragma unroll
                 for (int k = 0; k < ROWS; k++)
-                    h[k] = (valid[k] && kl[k] >= 0)
-                               ? fnv_global(prm.key_bytes + g0 + wbase + (wide ? off64[k] : (uint64_t)off[k]), kl[k])
-                               : 0u;
+                    h[k] = (valid[k] && kl[k] >= 0) ? fnv_global(prm.key_bytes + g0 + off[k], kl[k]) : 0u;
+            } else {
+                uint32_t *scratch = reinterpret_cast<uint32_t *>(keybuf + (size_t)buf * KEYBUF);  // not staged: free
+                wide_tile_hashes(prm.key_len, prm.n, prm.key_bytes + g0, tile, scratch, lane);
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) h[k] = scratch[32 * k + lane];
             }
 
             // ---- LogCompactionInMemoryMetrics::handle_message, metric.rs:288-305 ----
@@ -543,52 +544,53 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
                         uint8_t *d = prm.alive_dirty + (h[k] >> DIRTY_SHIFT);
                         if (__ldca(d) == 0) *d = 1;
                     }
-                    if (prm.hll_p && vl[k] >= 0) hll_update(prm.hll, prm.hll_p, floor, h[k]);
+                    if (prm.hll_p && vl[k] >= 0) hll_update(prm.hll, prm.hll_p, skip_mask, h[k]);
                 }
             }
         }
     };
 
-    for (int it = 0; tile < prm.ntiles; tile += gridDim.x, ++it) {
+    for (int it = 0; tile < prm.ntiles; tile += gstride, ++it) {
         const int buf = it & 1;
-        __syncthreads();  // (A) everyone is done with buffer buf^1, warp_tot and the previous tile's atomics
-        if (SMEM && it && (it & (FOLD_TILES - 1)) == 0) {
-            C.fold_sums();
-            __syncthreads();
+        uint64_t g0 = 0;
+        bool staged = false;
+        uint32_t skip_mask = 0;
+        if (HASH) {
+            g0 = __shfl_sync(full, nxt_g0, 0);
+            staged = __shfl_sync(full, nxt_staged, 0) != 0;
+            if (prm.hll_p) skip_mask = hll_skip_mask(prm.hll_p, __shfl_sync(full, nxt_floor, 0));
+            __syncwarp();  // every lane is done reading buffer buf^1 (previous tile) before it is refilled
+            if (lane == 0 && tile + gstride < prm.ntiles) issue(tile + gstride, buf ^ 1);
         }
-        if (HASH && prm.hll_p && (tile & 63) == 0) {
-            hll_refresh_floor(prm.hll, prm.hll_p, prm.hll_floor, reinterpret_cast<uint32_t *>(red));
-            __syncthreads();
-        }
-        if (HASH && tid == 0) {
-            const int64_t next = tile + gridDim.x;
-            if (next < prm.ntiles) issue(next, buf ^ 1);
-        }
-        if ((tile + 1) * TILE <= prm.n) body(std::true_type{}, tile, buf);
-        else body(std::false_type{}, tile, buf);
+        if ((tile + 1) * TILE <= prm.n) body(std::true_type{}, tile, buf, g0, staged, skip_mask);
+        else body(std::false_type{}, tile, buf, g0, staged, skip_mask);
+        if (SMEM && (it & (FOLD_TILES - 1)) == FOLD_TILES - 1) C.fold_sums(lane, 1u << 30);
+        // warp 0 of every CTA re-derives the HLL floor at its tile 4, 8, 16, 32, ... (cheap, and early)
+        if (HASH && prm.hll_p && warp == 0 && it >= 4 && (it & (it - 1)) == 0)
+            hll_refresh_floor(prm.hll, prm.hll_p, prm.hll_floor, lane);
     }
 
     // ---- flush CTA-private state ----
     __syncthreads();
     if (SMEM) {
-        const int nh = 2 * P * NB;  // khist then vhist, un-swizzle on the way out
-        for (int i = tid; i < nh; i += THREADS) {
-            const int pp = (i / NB) % P, slot = i % NB;
+        const int nh = 2 * NB * P;  // khist then vhist, bucket-major in shared memory, partition-major in global
+        for (int i = tid; i < nh; i += blockDim.x) {
             const uint32_t v = scnt[i];
             if (v) {
-                const int b = (slot - pp) & (NB - 1);
-                atomicAdd(&prm.sums[(size_t)(i / NB) * NB + b], (unsigned long long)v);
+                const int row = i / P, pp = i - row * P;           // row = which * NB + bucket
+                const int which = row >= NB, b = row - which * NB;
+                atomicAdd(&prm.sums[(size_t)(which * P + pp) * NB + b], (unsigned long long)v);
             }
         }
-        C.fold_sums();
-        for (int i = tid; i < P; i += THREADS) {
-            const uint32_t kn = scnt[P * (2 * NB + 4) + i];
+        if (warp == 0) C.fold_sums(lane, 1u);
+        for (int i = tid; i < P; i += blockDim.x) {
+            const uint32_t kn = scnt[(2 * NB + 4) * P + i];
             if (kn) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 2) + i], (unsigned long long)kn);
         }
     }
     // extrema + bad-partition count: warp shuffle, then one lane per warp, then one thread per CTA
-    long long smin64 = sany ? (long long)smin : INT64_MAX;  // sizes < 2^32, safe in i64
-    long long smax64 = sany ? (long long)smax : -1;
+    long long smin64 = smin != 0xffffffffu ? (long long)smin : INT64_MAX;
+    long long smax64 = smin != 0xffffffffu ? (long long)smax : -1;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
         const long long a = __shfl_xor_sync(full, tmin, d), b = __shfl_xor_sync(full, tmax, d);
@@ -599,18 +601,19 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
         smax64 = e > smax64 ? e : smax64;
         bad += __shfl_xor_sync(full, bad, d);
     }
-    __syncthreads();
+    long long *red = reinterpret_cast<long long *>(wsm + 64);   // per-warp scratch (4 × i64)
     if (lane == 0) {
-        red[warp * 4 + 0] = tmin; red[warp * 4 + 1] = tmax; red[warp * 4 + 2] = smin64; red[warp * 4 + 3] = smax64;
+        red[0] = tmin; red[1] = tmax; red[2] = smin64; red[3] = smax64;
         if (bad) atomicAdd(&prm.sums[sums_words(P) - 1], (unsigned long long)bad);
     }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < WARPS; w++) {
-            tmin = red[w * 4 + 0] < tmin ? red[w * 4 + 0] : tmin;
-            tmax = red[w * 4 + 1] > tmax ? red[w * 4 + 1] : tmax;
-            smin64 = red[w * 4 + 2] < smin64 ? red[w * 4 + 2] : smin64;
-            smax64 = red[w * 4 + 3] > smax64 ? red[w * 4 + 3] : smax64;
+        for (int w = 1; w < nwarps; w++) {
+            const long long *rw = reinterpret_cast<const long long *>(wsm + (size_t)w * (HASH ? WARP_SMEM : 128) + 64);
+            tmin = rw[0] < tmin ? rw[0] : tmin;
+            tmax = rw[1] > tmax ? rw[1] : tmax;
+            smin64 = rw[2] < smin64 ? rw[2] : smin64;
+            smax64 = rw[3] > smax64 ? rw[3] : smax64;
         }
         if (tmin != INT64_MAX) {
             atomicMin(&prm.minmax[0], tmin);
@@ -624,18 +627,18 @@ __global__ void __launch_bounds__(THREADS, 4) scan_kernel(const ScanParams prm) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// key_tile_base derivation when the caller did not supply it: per-tile byte totals, then one
-// single-CTA exclusive scan over the tile totals.
+// key_tile_base derivation when the caller did not supply it: per-tile byte totals (one warp per
+// 128-record tile), then one single-CTA exclusive scan over the tile totals.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) tile_key_bytes_kernel(const int32_t *key_len, int64_t n, int64_t ntiles,
-                                                                 uint64_t *tile_base /*[ntiles+1], [t+1] = bytes of tile t*/) {
-    __shared__ uint64_t wsum[WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+__global__ void __launch_bounds__(256) tile_key_bytes_kernel(const int32_t *key_len, int64_t n, int64_t ntiles,
+                                                             uint64_t *tile_base /*[ntiles+1], [t+1] = bytes of tile t*/) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t tile = gw; tile < ntiles; tile += gs) {
         uint64_t s = 0;
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
-            const int64_t r = tile * TILE + k * THREADS + tid;
+            const int64_t r = tile * TILE + k * 32 + lane;
             if (r < n) {
                 const int32_t v = key_len[r];
                 s += v > 0 ? (uint64_t)v : 0;
@@ -643,16 +646,9 @@ __global__ void __launch_bounds__(THREADS) tile_key_bytes_kernel(const int32_t *
         }
 #pragma unroll
         for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) wsum[warp] = s;
-        __syncthreads();
-        if (tid == 0) {
-            uint64_t t = 0;
-            for (int w = 0; w < WARPS; w++) t += wsum[w];
-            tile_base[tile + 1] = t;
-        }
-        __syncthreads();
+        if (lane == 0) tile_base[tile + 1] = s;
     }
-    if (blockIdx.x == 0 && tid == 0) tile_base[0] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) tile_base[0] = 0;
 }
 
 __global__ void __launch_bounds__(1024) tile_base_scan_kernel(uint64_t *tile_base, int64_t ntiles) {
@@ -689,6 +685,7 @@ __global__ void __launch_bounds__(1024) tile_base_scan_kernel(uint64_t *tile_bas
 // the alive bit set.
 // ------------------------------------------------------------------------------------------------
 constexpr int PAGE_ENTRIES = 1 << DIRTY_SHIFT;
+constexpr int THREADS = 256;  // block size of the table / utility kernels below
 
 __global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned long long *table, const uint8_t *dirty,
                                                                 uint32_t npages, unsigned long long *alive_count,

@@ -72,20 +72,20 @@ __global__ void __launch_bounds__(256) synth_columns_kernel(kta_synth_spec s, in
     }
 }
 
-// one CTA per tile: exclusive scan of key_len inside the tile, then every thread writes its keys
-__global__ void __launch_bounds__(THREADS) synth_keys_kernel(kta_synth_spec s, int rank, int world, int64_t start,
-                                                             int64_t count, const uint64_t *tile_base,
-                                                             uint8_t *key_bytes, int64_t cap) {
-    __shared__ uint64_t wsum[WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// one warp per 128-record tile: exclusive scan of key_len inside the tile, then every lane writes its keys
+__global__ void __launch_bounds__(256) synth_keys_kernel(kta_synth_spec s, int rank, int world, int64_t start,
+                                                         int64_t count, const uint64_t *tile_base, uint8_t *key_bytes,
+                                                         int64_t cap) {
+    const int lane = threadIdx.x & 31;
     const int64_t ntiles = (count + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t tile = gw; tile < ntiles; tile += gs) {
         uint64_t ids[ROWS];
         int32_t len[ROWS];
         uint64_t mine = 0;
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
-            const int64_t j = tile * TILE + (int64_t)tid * ROWS + k;  // thread owns ROWS consecutive records
+            const int64_t j = tile * TILE + (int64_t)lane * ROWS + k;  // a lane owns ROWS consecutive records
             len[k] = -1;
             ids[k] = 0;
             if (j < count) {
@@ -102,11 +102,7 @@ __global__ void __launch_bounds__(THREADS) synth_keys_kernel(kta_synth_spec s, i
             const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += t;
         }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
         uint64_t o = tile_base[tile] + inc - mine;
-        for (int w = 0; w < warp; w++) o += wsum[w];
-        __syncthreads();
         uint8_t tmp[KTA_SYNTH_MAX_KEY];
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
@@ -140,12 +136,12 @@ extern "C" int kta_synth_fill_device(const kta_synth_spec *s, int32_t device, in
     uint64_t total = 0;
     if (key_tile_base) {
         const int64_t ntiles = (count + TILE - 1) / TILE;
-        tile_key_bytes_kernel<<<(int)std::min<int64_t>(ntiles, (int64_t)sms * 8), THREADS>>>(key_len, count, ntiles, key_tile_base);
+        tile_key_bytes_kernel<<<(int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)sms * 8), 256>>>(key_len, count, ntiles, key_tile_base);
         tile_base_scan_kernel<<<1, 1024>>>(key_tile_base, ntiles);
         if (cudaMemcpy(&total, key_tile_base + ntiles, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return KTA_ERR_CUDA;
         if (key_bytes) {
             if ((int64_t)total > key_bytes_cap) return KTA_ERR_NOMEM;
-            synth_keys_kernel<<<(int)std::min<int64_t>(ntiles, (int64_t)sms * 8), THREADS>>>(*s, rank, world, start, count,
+            synth_keys_kernel<<<(int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)sms * 8), 256>>>(*s, rank, world, start, count,
                                                                                           key_tile_base, key_bytes, key_bytes_cap);
         }
     }

@@ -11,6 +11,7 @@ import pytest
 
 from kafka_topic_analyzer_b200 import KtaEngine, KtaError, Message, TopicAnalyzer, lib, synth
 from kafka_topic_analyzer_b200 import metrics as M
+from kafka_topic_analyzer_b200 import _native as N
 from oracle_lib import Oracle, fnv32, hll_estimate
 from parity import assert_parity, oracle_for, random_topic
 import np_oracle
@@ -265,11 +266,12 @@ def test_config1_full_size_properties():
         assert mm.earliest_message()[0] == 1_500_000_000 and mm.latest_message() == (1_500_000_000_000 + (n - 1) * 7 + 999) // 1000 or True
         # halves
         e.reset()
-        h = (n // 2) // 1024 * 1024
+        T = N.KTA_KEY_TILE
+        h = (n // 2) // T * T
         for lo, hi in ((0, h), (h, n)):
             e.scan_batch_device(topic.partition[lo:hi], topic.ts_ms[lo:hi], topic.key_len[lo:hi], topic.value_len[lo:hi],
                                 key_bytes=topic.key_bytes, key_bytes_len=topic.key_bytes_len,
-                                key_tile_base=topic.key_tile_base[lo // 1024:], seq_base=lo)
+                                key_tile_base=topic.key_tile_base[lo // T:], seq_base=lo)
         e.finalize()
         assert whole == {p: [e.counter(i, p) for i in range(7)] + e.hist(0, p).tolist() + e.hist(1, p).tolist() for p in range(P)}
         assert np.array_equal(regs, e.hll_registers())
