@@ -30,14 +30,16 @@ def _sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "kta.h")]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libkta_gpu.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    if not force and os.path.exists(LIB_PATH):
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compile libkta_gpu.so for sm_100a with nvcc (cross-compiles without a GPU).
+    `defines` / `out` build an experimental variant next to it (tuning runs; KTA_LIB selects it)."""
+    out = out or LIB_PATH
+    if not force and os.path.exists(out):
         newest = max(os.path.getmtime(p) for p in _sources())
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+        if os.path.getmtime(out) >= newest:
+            return out
     nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "kta_lib.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-o", out, os.path.join(CSRC, "kta_lib.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -45,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return out
 
 
 class KtaError(RuntimeError):
@@ -134,9 +136,10 @@ def lib() -> C.CDLL:
     """Load libkta_gpu.so (building it first if the sources are newer / it is missing)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("KTA_LIB") or LIB_PATH   # KTA_LIB: an experimental build of the same sources
+        if not os.path.exists(path):
             build()
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(_lib, name)  # AttributeError if the export is missing: loud by design
             fn.restype = res

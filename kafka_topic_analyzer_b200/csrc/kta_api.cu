@@ -86,7 +86,7 @@ struct kta_handle {
     // device state
     unsigned long long *d_sums = nullptr;
     long long *d_minmax = nullptr;
-    uint8_t *d_hll = nullptr;
+    uint32_t *d_hll = nullptr;
     uint32_t *d_hll_floor = nullptr;
     unsigned long long *d_alive_table = nullptr;
     uint8_t *d_alive_dirty = nullptr;
@@ -107,13 +107,13 @@ struct kta_handle {
     bool finalized = false;
     std::vector<uint64_t> h_sums;
     long long h_minmax[4] = {0, 0, 0, 0};
-    std::vector<uint8_t> h_hll;
+    std::vector<uint32_t> h_hll;
     uint64_t h_alive = 0;
     // occupancy-derived grids
     bool smem_counters = true;               // per-partition counters fit in shared memory
     size_t smem_optin = 0;
-    int threads_scan[3] = {0, 0, 0};         // [0 counters, 1 hash, 2 hash+capture]
-    size_t smem_scan[3] = {0, 0, 0};
+    int threads_scan[5] = {0, 0, 0, 0, 0};   // [0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture]
+    size_t smem_scan[5] = {0, 0, 0, 0, 0};
     // stats / timing
     uint64_t launches = 0, records = 0;
     bool timing = false;
@@ -129,24 +129,48 @@ static int set_device(const kta_handle *h) {
 }
 
 static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads) {
-    return (smem ? smem_counter_bytes(P) : 0) + (size_t)(threads / 32) * (hash ? WARP_SMEM : 128);
+    return (smem ? smem_counter_bytes(P) : 128) + (size_t)(threads / 32) * (hash ? WARP_SMEM : 128);
 }
 
-// one persistent CTA per SM; as many autonomous warps as the shared-memory budget allows
-template <bool HASH, bool SMEM, bool CAPTURE>
+// one persistent CTA per SM; as many autonomous warps as the shared-memory budget allows.
+// variant index: 0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture
+template <int MODE, bool SMEM, bool CAPTURE>
 static int prepare_variant(kta_handle *h) {
-    const int v = CAPTURE ? 2 : (HASH ? 1 : 0);
+    const int v = MODE + (CAPTURE ? 2 : 0);
+    const bool hash = MODE != MODE_COUNTERS;
     int threads = MAX_THREADS;
     size_t smem = 0;
-    for (;; threads /= 2) {
-        smem = scan_smem_bytes(HASH, SMEM, h->cfg.num_partitions, threads);
-        if (smem <= h->smem_optin || threads == 128) break;
+    for (;; threads -= 128) {
+        smem = scan_smem_bytes(hash, SMEM, h->cfg.num_partitions, threads);
+        if (smem <= h->smem_optin || threads <= 128) break;
     }
     if (smem > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", smem);
-    CU(cudaFuncSetAttribute(scan_kernel<HASH, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(scan_kernel<MODE, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     h->threads_scan[v] = threads;
     h->smem_scan[v] = smem;
     return KTA_OK;
+}
+
+template <bool SMEM>
+static int prepare_all(kta_handle *h) {
+    int rc;
+    if ((rc = prepare_variant<MODE_COUNTERS, SMEM, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_HLL, SMEM, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_EXACT, SMEM, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_HLL, SMEM, true>(h))) return rc;
+    if ((rc = prepare_variant<MODE_EXACT, SMEM, true>(h))) return rc;
+    return KTA_OK;
+}
+
+template <bool SMEM>
+static void launch_variant(int v, int grid, int threads, size_t sm, cudaStream_t st, const ScanParams &prm) {
+    switch (v) {
+        case 0: scan_kernel<MODE_COUNTERS, SMEM, false><<<grid, threads, sm, st>>>(prm); break;
+        case 1: scan_kernel<MODE_HLL, SMEM, false><<<grid, threads, sm, st>>>(prm); break;
+        case 2: scan_kernel<MODE_EXACT, SMEM, false><<<grid, threads, sm, st>>>(prm); break;
+        case 3: scan_kernel<MODE_HLL, SMEM, true><<<grid, threads, sm, st>>>(prm); break;
+        default: scan_kernel<MODE_EXACT, SMEM, true><<<grid, threads, sm, st>>>(prm); break;
+    }
 }
 
 static int state_reset_device(kta_handle *h) {
@@ -220,9 +244,9 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     h->nhll = cfg->hll_precision ? ((size_t)1 << cfg->hll_precision) : 0;
     CU(cudaMalloc(&h->d_sums, h->nsums * 8));
     CU(cudaMalloc(&h->d_minmax, 4 * 8));
-    CU(cudaMalloc(&h->d_scalar, 4 * 8));
+    CU(cudaMalloc(&h->d_scalar, 2 * 8 + (HLL_SLICES + 1) * 4 + 4));
     h->d_hll_floor = reinterpret_cast<uint32_t *>(h->d_scalar + 2);
-    if (h->nhll) CU(cudaMalloc(&h->d_hll, h->nhll));
+    if (h->nhll) CU(cudaMalloc(&h->d_hll, h->nhll * 4));
     if (cfg->count_alive_keys == 1) {
         // direct-mapped last-writer table over the whole 32-bit hash space: 2^32 × 8 B = 32 GiB
         CU(cudaMalloc(&h->d_alive_table, ((size_t)1 << 32) * 8));
@@ -233,17 +257,8 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     // counters in shared memory as long as at least 8 warps still fit beside them
     h->smem_counters = smem_counter_bytes(P) + 8 * (size_t)WARP_SMEM <= h->smem_optin;
-    const bool smem = h->smem_counters;
     int rc;
-    if (smem) {
-        if ((rc = prepare_variant<false, true, false>(h))) return rc;
-        if ((rc = prepare_variant<true, true, false>(h))) return rc;
-        if ((rc = prepare_variant<true, true, true>(h))) return rc;
-    } else {
-        if ((rc = prepare_variant<false, false, false>(h))) return rc;
-        if ((rc = prepare_variant<true, false, false>(h))) return rc;
-        if ((rc = prepare_variant<true, false, true>(h))) return rc;
-    }
+    if ((rc = h->smem_counters ? prepare_all<true>(h) : prepare_all<false>(h))) return rc;
     if ((rc = state_reset_device(h))) return rc;
     CU(cudaStreamSynchronize(h->stream));
     return KTA_OK;
@@ -288,11 +303,15 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
     if (prm.n <= 0) return KTA_OK;
     const int P = h->cfg.num_partitions;
     const bool exact = h->cfg.count_alive_keys == 1;
-    const bool hash = h->need_hash || h->d_hash_out;
+    const bool capture = h->d_hash_out != nullptr;
+    // with -c the sketch is built from the resolved set at finalize, not in-stream.  A capture-only
+    // handle (no -c, no HLL) runs the HLL-mode kernel against a null sketch of precision 0.
+    const int mode = exact ? MODE_EXACT : (h->cfg.hll_precision || capture) ? MODE_HLL : MODE_COUNTERS;
+    if (mode == MODE_HLL && !h->cfg.hll_precision)
+        return fail(KTA_ERR_INVALID, "hash capture needs count_alive_keys or hll_precision");
     prm.ntiles = (prm.n + TILE - 1) / TILE;
     prm.P = P;
-    prm.exact = exact ? 1 : 0;
-    prm.hll_p = exact ? 0 : h->cfg.hll_precision;  // with -c the sketch is built from the resolved set
+    prm.hll_p = h->cfg.hll_precision;
     prm.sums = h->d_sums;
     prm.minmax = h->d_minmax;
     prm.hll = h->d_hll;
@@ -300,14 +319,12 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
     prm.alive_table = h->d_alive_table;
     prm.alive_dirty = h->d_alive_dirty;
     prm.hash_out = h->d_hash_out;
-    if (hash) {
+    if (mode != MODE_COUNTERS) {
         if (!prm.key_tile_base) return fail(KTA_ERR_INVALID, "internal: key_tile_base missing");
         if (!prm.key_bytes && key_readable > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL but keys are required");
-        prm.stage_ok = (((uintptr_t)prm.key_bytes & 15u) == 0) ? 1 : 0;
-        prm.key_readable = (uint64_t)key_readable;
+        prm.stage_limit = (((uintptr_t)prm.key_bytes & 15u) == 0) ? (uint64_t)key_readable : 0;
     }
-    const bool smem = h->smem_counters;
-    const int variant = h->d_hash_out ? 2 : (hash ? 1 : 0);
+    const int variant = mode + (capture ? 2 : 0);
     const int threads = h->threads_scan[variant];
     const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
     const size_t sm = h->smem_scan[variant];
@@ -324,16 +341,8 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
         h->ev_used++;
         CU(cudaEventRecord(e0, h->stream));
     }
-    if (variant == 2) {
-        if (smem) scan_kernel<true, true, true><<<grid, threads, sm, h->stream>>>(prm);
-        else scan_kernel<true, false, true><<<grid, threads, sm, h->stream>>>(prm);
-    } else if (variant == 1) {
-        if (smem) scan_kernel<true, true, false><<<grid, threads, sm, h->stream>>>(prm);
-        else scan_kernel<true, false, false><<<grid, threads, sm, h->stream>>>(prm);
-    } else {
-        if (smem) scan_kernel<false, true, false><<<grid, threads, sm, h->stream>>>(prm);
-        else scan_kernel<false, false, false><<<grid, threads, sm, h->stream>>>(prm);
-    }
+    if (h->smem_counters) launch_variant<true>(variant, grid, threads, sm, h->stream, prm);
+    else launch_variant<false>(variant, grid, threads, sm, h->stream, prm);
     CU(cudaGetLastError());
     if (h->timing) CU(cudaEventRecord(e1, h->stream));
     h->launches++;
@@ -633,7 +642,7 @@ extern "C" int kta_finalize(kta_handle *h) {
     cudaStream_t s = h->stream;
     if (h->d_alive_table) {
         CU(cudaMemsetAsync(h->d_scalar, 0, 8, s));
-        if (h->nhll) CU(cudaMemsetAsync(h->d_hll, 0, h->nhll, s));
+        if (h->nhll) CU(cudaMemsetAsync(h->d_hll, 0, h->nhll * 4, s));
         alive_resolve_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, h->d_alive_dirty,
                                                                  1u << (32 - DIRTY_SHIFT), h->d_scalar, h->d_hll,
                                                                  h->cfg.hll_precision);
@@ -644,7 +653,7 @@ extern "C" int kta_finalize(kta_handle *h) {
     h->h_hll.resize(h->nhll);
     CU(cudaMemcpyAsync(h->h_sums.data(), h->d_sums, h->nsums * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h->h_minmax, h->d_minmax, 32, cudaMemcpyDeviceToHost, s));
-    if (h->nhll) CU(cudaMemcpyAsync(h->h_hll.data(), h->d_hll, h->nhll, cudaMemcpyDeviceToHost, s));
+    if (h->nhll) CU(cudaMemcpyAsync(h->h_hll.data(), h->d_hll, h->nhll * 4, cudaMemcpyDeviceToHost, s));
     unsigned long long alive = 0;
     if (h->d_alive_table) CU(cudaMemcpyAsync(&alive, h->d_scalar, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -823,7 +832,7 @@ extern "C" int kta_alive_keys_hll(const kta_handle *h, double *out) {
     const int p = h->cfg.hll_precision, q = 32 - p;
     const double m = (double)h->nhll;
     std::vector<double> C((size_t)q + 2, 0.0);
-    for (uint8_t r : h->h_hll) C[std::min<uint32_t>(r, (uint32_t)q + 1)] += 1.0;
+    for (uint32_t r : h->h_hll) C[std::min<uint32_t>(r, (uint32_t)q + 1)] += 1.0;
     double z = m * hll_tau(1.0 - C[(size_t)q + 1] / m);
     for (int k = q; k >= 1; k--) z = 0.5 * (z + C[(size_t)k]);
     z += m * hll_sigma(C[0] / m);
@@ -837,7 +846,7 @@ extern "C" int kta_hll_registers(const kta_handle *h, uint8_t *out, size_t cap) 
     if (rc) return rc;
     if (!h->nhll) return fail(KTA_ERR_NOT_ENABLED, "hll_precision was 0");
     if (cap < h->nhll) return fail(KTA_ERR_INVALID, "buffer too small: %zu < %zu", cap, h->nhll);
-    memcpy(out, h->h_hll.data(), h->nhll);
+    for (size_t i = 0; i < h->nhll; i++) out[i] = (uint8_t)h->h_hll[i];
     return KTA_OK;
 }
 
@@ -892,7 +901,7 @@ extern "C" int kta_set_hash_capture(kta_handle *h, uint32_t *dev_out) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int64_t kta_merge_words(const kta_handle *h, int32_t world) {
     if (!h || world < 1) return -1;
-    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * (h->nhll / 8));
+    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * (h->nhll / 2));
 }
 
 extern "C" int kta_merge_export_device(kta_handle *h, int32_t rank, int32_t world, uint64_t *dev_buf) {

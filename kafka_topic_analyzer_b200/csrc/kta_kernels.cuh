@@ -19,7 +19,10 @@
 
 namespace kta {
 
-constexpr int MAX_THREADS = 1024;         // one persistent CTA per SM, up to 32 autonomous warps
+#ifndef KTA_SCAN_THREADS
+#define KTA_SCAN_THREADS 1024
+#endif
+constexpr int MAX_THREADS = KTA_SCAN_THREADS;  // one persistent CTA per SM, up to 32 autonomous warps
 constexpr int TILE = KTA_KEY_TILE;        // records per warp tile (128)
 constexpr int ROWS = TILE / 32;           // records per lane per tile
 constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
@@ -31,12 +34,18 @@ constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV pri
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
 constexpr int FOLD_TILES = 4;             // every warp checks the CTA's 16-bit-split sums every 4 of its tiles
 
+// shared-memory counter rows (each row = P u32 words):
+//   0..31 key-size buckets, 32 null keys | 33..64 value-size buckets, 65 tombstones |
+//   66 Σ(key_len & 0xffff), 67 Σ(key_len >> 16), 68 Σ(value_len & 0xffff), 69 Σ(value_len >> 16)
+// bucket(len) = bfind(len) + 1: 0 for len 0, 1 + floor(log2 len) otherwise, and 32 for len = -1 (null),
+// so "null" needs neither a branch nor a select.
+constexpr int ROW_V = NB + 1, ROW_KSUM = 2 * NB + 2, ROW_VSUM = 2 * NB + 4, SMEM_ROWS = 2 * NB + 6;
+enum ScanMode { MODE_COUNTERS = 0, MODE_HLL = 1, MODE_EXACT = 2 };
+
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
-// words of the u32 shared-memory mirror, bucket-major: khist[32][P] | vhist[32][P] | ksum_lo16[P] | ksum_hi[P] |
-// vsum_lo16[P] | vsum_hi[P] | knull[P]
-__host__ __device__ inline size_t smem_counter_words(int P) { return (size_t)P * (2 * NB + 5); }
-__host__ __device__ inline size_t smem_counter_bytes(int P) { return (smem_counter_words(P) * 4 + 127) & ~(size_t)127; }
+// counter rows, then one 128-byte CTA scratch line (word 0: the CTA's cached copy of the HLL floor)
+__host__ __device__ inline size_t smem_counter_bytes(int P) { return (((size_t)P * SMEM_ROWS * 4 + 127) & ~(size_t)127) + 128; }
 
 struct ScanParams {
     int64_t n;
@@ -50,14 +59,13 @@ struct ScanParams {
     const uint64_t *seq;             // optional explicit seq column
     int64_t ntiles;
     int32_t P;
-    int32_t hll_p;                   // 0 = off
-    int32_t exact;                   // 1 = update alive table
-    int32_t stage_ok;                // key_bytes is 16-byte aligned → bulk-copy staging allowed
-    uint64_t key_readable;           // bytes that may be read starting at key_bytes (bulk copies round up to 16)
+    int32_t hll_p;                   // HLL index bits (MODE_HLL)
+    uint64_t stage_limit;            // bytes readable from key_bytes by 16-byte bulk copies; 0 = staging not allowed
     unsigned long long *sums;        // [sums_words(P)]
     long long *minmax;               // [0] min raw ts_ms, [1] max raw ts_ms, [2] min size, [3] max size (as u64)
-    uint8_t *hll;                    // [1 << hll_p] registers
-    uint32_t *hll_floor;             // lower bound of every register (monotone; lets most records skip the table)
+    uint32_t *hll;                   // [1 << hll_p] registers (one u32 each so that RED.MAX applies)
+    uint32_t *hll_floor;             // [0] lower bound of every register (monotone; lets most records skip the
+                                     // table), [1..HLL_SLICES] per-slice minima it is derived from
     unsigned long long *alive_table; // [2^32]
     uint8_t *alive_dirty;            // [2^32 >> DIRTY_SHIFT]
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
@@ -68,17 +76,16 @@ struct ScanParams {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "KTA_WAIT_%=:\n\t"
@@ -86,15 +93,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@p bra KTA_DONE_%=;\n\t"
         "bra KTA_WAIT_%=;\n\t"
         "KTA_DONE_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity)
+        ::"r"(bar), "r"(parity)
         : "memory");
 }
 // 1-D bulk async copy global → shared (TMA engine, no tensor map), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
         : "memory");
+}
+// shared-memory reductions on 32-bit shared-window addresses (no generic→shared conversion in the loop)
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {  // index of the most significant set bit, 0xffffffff for 0
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
 }
 // streaming loads: read once, do not allocate in L1
 __device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p) {
@@ -116,6 +142,12 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {  // L2-cohere
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void red_global_max(uint32_t *p, uint32_t v) {  // fire-and-forget, never stalls the warp
+    asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,21 +172,21 @@ __device__ __forceinline__ uint32_t fnv_word(uint32_t h, uint32_t w) {
     return h;
 }
 
-// key at byte offset `a` of a 4-byte-aligned shared-memory buffer (aligned word loads + funnel shift)
-__device__ __forceinline__ uint32_t fnv_smem(const uint32_t *buf32, uint32_t a, int len) {
+// key at byte offset `a` of the warp's staged key buffer (aligned word loads + funnel shift)
+__device__ __forceinline__ uint32_t fnv_smem(uint32_t buf_addr, uint32_t a, int len) {
     uint32_t h = FNV_BASIS;
-    const uint32_t *wp = buf32 + (a >> 2);
+    const uint32_t wp = buf_addr + (a & ~3u);
     const uint32_t sh = (a & 3u) * 8u;
-    uint32_t lo = wp[0];
+    uint32_t lo = lds32(wp);
     int j = 0;
     for (; j + 4 <= len; j += 4) {
-        const uint32_t hi = wp[(j >> 2) + 1];
+        const uint32_t hi = lds32(wp + j + 4);
         h = fnv_word(h, __funnelshift_r(lo, hi, sh));
         lo = hi;
     }
     const int rem = len - j;
     if (rem > 0) {
-        const uint32_t hi = wp[(j >> 2) + 1];
+        const uint32_t hi = lds32(wp + j + 4);
         uint32_t w = __funnelshift_r(lo, hi, sh);
         for (int r = 0; r < rem; r++) {
             h = fnv_step(h, w & 0xffu);
@@ -174,9 +206,10 @@ __device__ __forceinline__ uint32_t fnv_global(const uint8_t *key, int len) {
 
 // ------------------------------------------------------------------------------------------------
 // EXTENSION (not in the reference): HyperLogLog over the 32-bit reference hash, remixed by murmur3
-// fmix32 (a bijection, so distinct reference hashes stay distinct).  Registers are bytes in global
-// memory (L2 resident); `floor` is a lower bound of every register, so a record whose rho <= floor
-// cannot change anything and never touches the table — after warm-up that is all but 2^-floor of them.
+// fmix32 (a bijection, so distinct reference hashes stay distinct).  Registers live in global memory
+// (L2 resident) and are raised with RED.MAX — fire and forget, the warp never waits for L2.
+// `floor` is a lower bound of every register, so a record whose rho <= floor cannot change anything
+// and never touches the table — after warm-up that is all but 2^-floor of them.
 // rho <= floor  ⇔  the top `floor` bits below the index bits are not all zero  ⇔  (x & skip_mask) != 0.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t hll_mix(uint32_t h) {
@@ -193,80 +226,101 @@ __device__ __forceinline__ uint32_t hll_skip_mask(int p, uint32_t floor) {
     return f ? (((1u << f) - 1u) << (32 - p - f)) : 0u;
 }
 
-__device__ __noinline__ void hll_slow_update(uint8_t *regs, int p, uint32_t x) {
-    const uint32_t idx = x >> (32 - p);
+__device__ __forceinline__ void hll_raise(uint32_t *regs, int p, uint32_t x) {
     const uint32_t rest = x << p;
     const uint32_t rho = min((uint32_t)__clz((int)rest) + 1u, (uint32_t)(32 - p + 1));
-    uint32_t *w = reinterpret_cast<uint32_t *>(regs + (idx & ~3u));
-    const uint32_t sh = (idx & 3u) * 8u;
-    uint32_t old = ld_cg_u32(w);
-    while (((old >> sh) & 0xffu) < rho) {
-        const uint32_t nw = (old & ~(0xffu << sh)) | (rho << sh);
-        const uint32_t prev = atomicCAS(w, old, nw);
-        if (prev == old) break;
-        old = prev;
-    }
+    red_global_max(regs + (x >> (32 - p)), rho);
 }
 
-__device__ __forceinline__ void hll_update(uint8_t *regs, int p, uint32_t skip_mask, uint32_t hash) {
+__device__ __forceinline__ void hll_update(uint32_t *regs, int p, uint32_t skip_mask, uint32_t hash) {
     const uint32_t x = hll_mix(hash);
-    if ((x & skip_mask) == 0) hll_slow_update(regs, p, x);
+    if ((x & skip_mask) == 0) hll_raise(regs, p, x);
 }
 
-// one warp recomputes the floor now and then: the min over a snapshot of monotone registers is a valid
-// lower bound for every later moment
-__device__ __forceinline__ void hll_refresh_floor(const uint8_t *regs, int p, uint32_t *floor_var, int lane) {
-    const uint32_t nwords = (1u << p) >> 2;
+// Keeping the floor fresh: the register file is cut into HLL_SLICES slices; now and then a warp takes the min
+// of ONE slice (a few independent L2 loads per lane), publishes it, and re-derives floor = min over the
+// published slice minima.  The min over a snapshot of monotone registers is a valid lower bound for every
+// later moment, so the filter stays exact.  aux[0] = floor, aux[1 + s] = min of slice s.
+constexpr int HLL_SLICES = 64;
+__device__ __noinline__ void hll_refresh_slice(const uint32_t *regs, int p, uint32_t *aux, uint32_t slice, int lane) {
+    const uint32_t n = 1u << p;
+    const uint32_t per = n >= HLL_SLICES ? n / HLL_SLICES : n;   // tiny sketches: every slice is the whole file
+    const uint32_t base = n >= HLL_SLICES ? slice * per : 0u;
     uint32_t m = 255;
-    for (uint32_t i = lane; i < nwords; i += 32) {
-        const uint32_t w = ld_cg_u32(reinterpret_cast<const uint32_t *>(regs) + i);
-        m = min(min(m, w & 0xffu), min((w >> 8) & 0xffu, min((w >> 16) & 0xffu, w >> 24)));
-    }
+    for (uint32_t i = lane; i < per; i += 32) m = min(m, ld_cg_u32(regs + base + i));
     m = __reduce_min_sync(0xffffffffu, m);
-    if (lane == 0 && m) atomicMax(floor_var, m);
+    if (lane == 0 && m) atomicMax(aux + 1 + slice, m);
+    uint32_t f;
+    {
+        const uint32_t s0 = (uint32_t)lane, s1 = (uint32_t)lane + 32u;
+        const uint32_t v0 = s0 == slice ? m : ld_cg_u32(aux + 1 + s0);
+        const uint32_t v1 = s1 == slice ? m : ld_cg_u32(aux + 1 + s1);
+        f = min(v0, v1);
+    }
+    f = __reduce_min_sync(0xffffffffu, f);
+    if (lane == 0 && f) atomicMax(aux, f);
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-partition counters.  SMEM = true: CTA-private u32 words in shared memory (bucket-major, so the
-// index is one multiply-add), native ATOMS without a return value.  64-bit byte sums are kept as two
-// u32 words — Σ(len & 0xffff) and Σ(len >> 16) — that every warp drains into the global u64 sums with
-// an atomic exchange every FOLD_TILES of its tiles, which bounds what can accumulate in between (exact).
+// per-partition counters (src/metric.rs:74-100, inc_*).  Derived at read-back: key_non_null = Σ key buckets,
+// alive = Σ value buckets, total = key_non_null + key_null, tombstones = total − alive.
+//
+// SMEM = true: CTA-private u32 rows in shared memory (layout above), updated with RED.SHARED (no return
+// value, nothing to wait for), branch-free per record.  64-bit byte sums are kept as two u32 words —
+// Σ(len & 0xffff) and Σ(len >> 16) — that every warp checks every FOLD_TILES of its tiles and drains into
+// the global u64 sums with an atomic exchange before they can overflow (exact).
 // SMEM = false: straight 64-bit global atomics (P too large for shared memory).
-// src/metric.rs:74-100 (inc_*); derived at read-back:  key_non_null = Σ khist, alive = Σ vhist,
-// total = key_non_null + key_null, tombstones = total − alive.
 // ------------------------------------------------------------------------------------------------
 template <bool SMEM>
 struct Counters {
-    uint32_t *s;
+    uint32_t sbase;            // shared-window address of row 0
+    uint32_t *s;               // the same, as a generic pointer (flush / fold)
     unsigned long long *g;
     int P;
-    __device__ __forceinline__ void khist(int p, int b, uint32_t c) const {
-        if (SMEM) atomicAdd(&s[b * P + p], c);
-        else atomicAdd(&g[(size_t)p * NB + b], (unsigned long long)c);
+    // row r of partition p += c (uniform-row path, flush)
+    __device__ __forceinline__ void row_add(int r, int p, uint32_t c) const {
+        if (SMEM) red_shared_add(sbase + 4u * (uint32_t)(r * P + p), c);
+        else if (r < NB) atomicAdd(&g[(size_t)p * NB + r], (unsigned long long)c);                       // khist
+        else if (r == NB) atomicAdd(&g[(size_t)P * (2 * NB + 2) + p], (unsigned long long)c);           // knull
+        else if (r < ROW_V + NB) atomicAdd(&g[(size_t)(P + p) * NB + (r - ROW_V)], (unsigned long long)c);  // vhist
+        // r == ROW_V + NB (tombstones) is derived, nothing to store
     }
-    __device__ __forceinline__ void vhist(int p, int b, uint32_t c) const {
-        if (SMEM) atomicAdd(&s[(NB + b) * P + p], c);
-        else atomicAdd(&g[(size_t)(P + p) * NB + b], (unsigned long long)c);
-    }
-    __device__ __forceinline__ void sum(int which /*0 key, 1 value*/, int p, uint32_t v) const {
+    __device__ __forceinline__ void sum_add(int which /*0 key, 1 value*/, int p, uint32_t v) const {
         if (SMEM) {
-            atomicAdd(&s[(2 * NB + 2 * which) * P + p], v & 0xffffu);
-            if (v >> 16) atomicAdd(&s[(2 * NB + 2 * which + 1) * P + p], v >> 16);
-        } else atomicAdd(&g[(size_t)P * (2 * NB + which) + p], (unsigned long long)v);
+            const uint32_t a = sbase + 4u * (uint32_t)((ROW_KSUM + 2 * which) * P + p);
+            red_shared_add(a, v & 0xffffu);
+            if (v >> 16) red_shared_add(a + 4u * (uint32_t)P, v >> 16);
+        } else if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], (unsigned long long)v);
     }
-    __device__ __forceinline__ void knull(int p, uint32_t c) const {
-        if (SMEM) atomicAdd(&s[(2 * NB + 4) * P + p], c);
-        else atomicAdd(&g[(size_t)P * (2 * NB + 2) + p], (unsigned long long)c);
+    // one record, partition already validated; MessageMetrics::handle_message's increments (metric.rs:215-244)
+    __device__ __forceinline__ void record(int p, int kl, int vl) const {
+        const int kb = (int)bfind_u32((uint32_t)kl) + 1;   // 32 = null key (metric.rs:228), else its size bucket (:220)
+        const int vb = (int)bfind_u32((uint32_t)vl) + 1;   // 32 = tombstone (:243), else its size bucket (:239)
+        if (SMEM) {
+            const uint32_t P4 = 4u * (uint32_t)P, pa = sbase + 4u * (uint32_t)p;
+            red_shared_add(pa + (uint32_t)kb * P4, 1u);
+            red_shared_add(pa + (uint32_t)(ROW_V + vb) * P4, 1u);
+            const uint32_t ks = (uint32_t)max(kl, 0), vs = (uint32_t)max(vl, 0);
+            red_shared_add(pa + ROW_KSUM * P4, ks & 0xffffu);                 // metric.rs:223
+            if (ks >> 16) red_shared_add(pa + (ROW_KSUM + 1) * P4, ks >> 16);
+            red_shared_add(pa + ROW_VSUM * P4, vs & 0xffffu);                 // metric.rs:237
+            if (vs >> 16) red_shared_add(pa + (ROW_VSUM + 1) * P4, vs >> 16);
+        } else {
+            row_add(kb, p, 1u);
+            row_add(ROW_V + vb, p, 1u);
+            sum_add(0, p, (uint32_t)max(kl, 0));
+            sum_add(1, p, (uint32_t)max(vl, 0));
+        }
     }
     // One warp drains split sums that reached `threshold` into the global u64 sums; safe against concurrent
     // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp checks every FOLD_TILES of
     // its tiles, so between two checks of an entry each of the <= 32 warps adds fewer than 2*FOLD_TILES*128
     // values < 2^16: growth < 32 * 1024 * 65535 < 2^31, and a word that passed a check was < 2^30.
-    __device__ __forceinline__ void fold_sums(int lane, uint32_t threshold) const {
+    __device__ __noinline__ void fold_sums(int lane, uint32_t threshold) const {
         if (!SMEM) return;
         for (int i = lane; i < 2 * P; i += 32) {
             const int which = i >= P, p = which ? i - P : i;
-            uint32_t *lo = &s[(2 * NB + 2 * which) * P + p];
+            uint32_t *lo = &s[(ROW_KSUM + 2 * which) * P + p];
             if (*(volatile uint32_t *)lo >= threshold || *(volatile uint32_t *)(lo + P) >= threshold) {
                 const unsigned long long v = (unsigned long long)atomicExch(lo, 0u) +
                                              ((unsigned long long)atomicExch(lo + P, 0u) << 16);
@@ -276,60 +330,33 @@ struct Counters {
     }
 };
 
-__device__ __forceinline__ int len_bucket(int len) { return 32 - __clz(len); }  // len >= 0; clz(0) == 32
-
-// One row = 32 consecutive records, one per lane.  MessageMetrics::handle_message, metric.rs:206-253.
-template <bool SMEM, bool FULL>
-__device__ __forceinline__ void count_row(const Counters<SMEM> &C, bool valid, int p, int kl, int vl, int lane,
-                                          uint32_t &bad) {
+// A row of 32 records that all belong to one partition (the usual shape of a Kafka fetch): aggregate in the
+// warp, one reduction per distinct bucket and per sum instead of 32 same-address ones.
+template <bool SMEM>
+__device__ __noinline__ void count_row_uniform(const Counters<SMEM> C, int p0, int kl, int vl, int lane) {
     const unsigned full = 0xffffffffu;
-    const int p0 = __shfl_sync(full, p, 0);
-    const bool ok = (FULL || valid) && (unsigned)p < (unsigned)C.P;
-    const bool uni = __all_sync(full, ok && p == p0 && (kl | vl) < (1 << 26));
-    if (uni) {
-        // the whole row belongs to one partition (the usual shape of a Kafka fetch): aggregate in
-        // the warp, one atomic per distinct bucket and per sum
-        const int kb = kl < 0 ? NB : len_bucket(kl);
-        const int vb = vl < 0 ? NB : len_bucket(vl);
-        unsigned rem = full;
-        while (rem) {
-            const int leader = __ffs(rem) - 1;
-            const int b0 = __shfl_sync(full, kb, leader);
-            const unsigned m = __ballot_sync(full, kb == b0);
-            if (lane == leader) {
-                if (b0 == NB) C.knull(p0, __popc(m));   // metric.rs:228
-                else C.khist(p0, b0, __popc(m));        // metric.rs:220 (key_non_null = Σ buckets)
-            }
-            rem &= ~m;
-        }
-        rem = full;
-        while (rem) {
-            const int leader = __ffs(rem) - 1;
-            const int b0 = __shfl_sync(full, vb, leader);
-            const unsigned m = __ballot_sync(full, vb == b0);
-            if (lane == leader && b0 != NB) C.vhist(p0, b0, __popc(m));  // metric.rs:239
-            rem &= ~m;
-        }
-        const uint32_t ks = __reduce_add_sync(full, (uint32_t)max(kl, 0));
-        const uint32_t vs = __reduce_add_sync(full, (uint32_t)max(vl, 0));
-        if (lane == 0) {
-            if (ks) C.sum(0, p0, ks);  // metric.rs:223
-            if (vs) C.sum(1, p0, vs);  // metric.rs:237
-        }
-    } else if (FULL || valid) {
-        if (!ok) {
-            bad++;
-        } else {
-            if (kl < 0) C.knull(p, 1u);
-            else {
-                C.khist(p, len_bucket(kl), 1u);
-                C.sum(0, p, (uint32_t)kl);
-            }
-            if (vl >= 0) {
-                C.vhist(p, len_bucket(vl), 1u);
-                C.sum(1, p, (uint32_t)vl);
-            }
-        }
+    const int kb = (int)bfind_u32((uint32_t)kl) + 1, vb = (int)bfind_u32((uint32_t)vl) + 1;
+    unsigned rem = full;
+    while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const int b0 = __shfl_sync(full, kb, leader);
+        const unsigned m = __ballot_sync(full, kb == b0);
+        if (lane == leader) C.row_add(b0, p0, __popc(m));
+        rem &= ~m;
+    }
+    rem = full;
+    while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const int b0 = __shfl_sync(full, vb, leader);
+        const unsigned m = __ballot_sync(full, vb == b0);
+        if (lane == leader) C.row_add(ROW_V + b0, p0, __popc(m));
+        rem &= ~m;
+    }
+    const uint32_t ks = __reduce_add_sync(full, (uint32_t)max(kl, 0));   // each < 2^26: no overflow
+    const uint32_t vs = __reduce_add_sync(full, (uint32_t)max(vl, 0));
+    if (lane == 0) {
+        C.sum_add(0, p0, ks);
+        C.sum_add(1, p0, vs);
     }
 }
 
@@ -355,70 +382,76 @@ __device__ __noinline__ void wide_tile_hashes(const int32_t *key_len, int64_t n,
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused scan kernel.  HASH = false: counters + histograms + extrema only (20 B/record, no key
-// bytes touched — the reference without -c).  HASH = true: additionally FNV per key from staged
-// shared memory, alive-table stamps (-c) and/or the in-stream HLL sketch (20 + key bytes per record).
-// CAPTURE = true (tests only) also writes every record's hash to prm.hash_out.
+// the fused scan kernel.
+//   MODE_COUNTERS: counters + histograms + extrema only (20 B/record, no key bytes touched — the reference
+//                  without -c).
+//   MODE_HLL:      + FNV per key from staged shared memory + the in-stream HLL sketch (20 + key bytes).
+//   MODE_EXACT:    + FNV per key + alive-table stamps (the reference with -c).
+//   CAPTURE (tests only) also writes every record's hash to prm.hash_out.
 //
 // One persistent CTA per SM; every WARP is an autonomous worker: it walks its own 128-record tiles
 // (tile t belongs to global warp t % total_warps), stages each tile's packed key bytes with its own
 // bulk async copy (cp.async.bulk → UBLKCP) on its own pair of mbarriers, and never waits for another
 // warp — there is no __syncthreads in the loop, so the load phase of one warp overlaps the hash phase of
-// the others.  Only the per-partition counters are shared (shared-memory atomics).
+// the others.  Only the per-partition counters are shared (shared-memory reductions).
 // ------------------------------------------------------------------------------------------------
-template <bool HASH, bool SMEM, bool CAPTURE>
+template <int MODE, bool SMEM, bool CAPTURE>
 __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams prm) {
+    constexpr bool HASH = MODE != MODE_COUNTERS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int P = prm.P;
-    // layout: counters (SMEM) | per warp: mbar[2] + 112 B scratch | keybuf[2]
+    // layout: counter rows (SMEM) | per warp: mbar[2] + 112 B scratch | keybuf[2]
     uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
-    unsigned char *wsm = smem_raw + (SMEM ? smem_counter_bytes(P) : 0) + (size_t)warp * (HASH ? WARP_SMEM : 128);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(wsm);
-    unsigned char *keybuf = wsm + 128;
-    const Counters<SMEM> C{scnt, prm.sums, P};
+    const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : 128;
+    volatile uint32_t *s_floor = reinterpret_cast<volatile uint32_t *>(smem_raw + cta_bytes - 128);
+    unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * (HASH ? WARP_SMEM : 128);
+    const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
+    const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
+    const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P};
 
     if (SMEM) {
-        const int nw = (int)smem_counter_words(P);
+        const int nw = P * SMEM_ROWS;
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
     }
+    if (MODE == MODE_HLL && tid == 0) *s_floor = ld_cg_u32(prm.hll_floor);
     if (HASH && lane == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        mbar_init(mbar, 1);
+        mbar_init(mbar + 8, 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    // lane 0: start the bulk copy of a tile's packed key bytes into buffer b; returns the span descriptor
-    uint64_t nxt_g0 = 0;
-    uint32_t nxt_staged = 0, nxt_floor = 0;
-    auto issue = [&](int64_t tile, int b) {
+    // lane 0: start the bulk copy of a tile's packed key bytes into stage b.
+    // Returns the span descriptor: bit 0 staged, bits 1..4 = first key's offset inside its 16-byte line.
+    auto issue = [&](int64_t tile, int b) -> uint32_t {
         const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
         const uint64_t a0 = g0 & ~15ull;
         const uint64_t bytes = ((g1 - a0) + 15ull) & ~15ull;
-        const bool ok = prm.stage_ok && g1 > g0 && bytes <= (uint64_t)KEYBUF_COPY && a0 + bytes <= prm.key_readable;
-        nxt_g0 = g0;
-        nxt_staged = ok ? 1u : 0u;
-        nxt_floor = prm.hll_p ? ld_cg_u32(prm.hll_floor) : 0u;
+        const bool ok = g1 > g0 && bytes <= (uint64_t)KEYBUF_COPY && a0 + bytes <= prm.stage_limit;
+        uint32_t info = (ok ? 1u : 0u) | ((uint32_t)(g0 & 15ull) << 1);
         if (ok) {
-            mbar_arrive_expect_tx(&mbar[b], (uint32_t)bytes);
-            bulk_g2s(keybuf + (size_t)b * KEYBUF, prm.key_bytes + a0, (uint32_t)bytes, &mbar[b]);
+            mbar_arrive_expect_tx(mbar + 8u * b, (uint32_t)bytes);
+            bulk_g2s(keybuf + (uint32_t)b * KEYBUF, prm.key_bytes + a0, (uint32_t)bytes, mbar + 8u * b);
         }
+        return info;
     };
 
     long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
-    uint32_t phase = 0;  // bit b = parity to wait for on mbar[b]
+    uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
+    bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
+    uint32_t nxt_info = 0;
 
     const int64_t gstride = (int64_t)gridDim.x * nwarps;
     int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
-    if (HASH && lane == 0 && tile < prm.ntiles) issue(tile, 0);
+    if (HASH && lane == 0 && tile < prm.ntiles) nxt_info = issue(tile, 0);
 
     // the body of one tile; FULL = every record of the tile exists (no tail predicates)
-    auto body = [&](auto full_tag, int64_t tile, int buf, uint64_t g0, bool staged, uint32_t skip_mask) {
+    auto body = [&](auto full_tag, int64_t tile, int buf, uint32_t info, bool has_next) {
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- header columns: 4 rows of 32 consecutive records, fully coalesced ----
         const int64_t rbase = tile * TILE + lane;
@@ -435,40 +468,67 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 kl[k] = ld_stream_s32(prm.key_len + r);
                 vl[k] = ld_stream_s32(prm.value_len + r);
             } else {
-                p[k] = 0; ts[k] = 0; kl[k] = -1; vl[k] = -1;
+                p[k] = 0; ts[k] = INT64_MAX; kl[k] = -1; vl[k] = -1;
             }
         }
-
-        // ---- MessageMetrics::handle_message ----
+        // ---- MessageMetrics::handle_message (metric.rs:206-253) ----
+        bool inrange = true;
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) inrange = inrange && (unsigned)p[k] < (unsigned)P;
+        if (FULL && __all_sync(full, inrange)) {
+            bool any_uni = false;
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                bool uni = false;
+                if (try_uni) {
+                    const int p0 = __shfl_sync(full, p[k], 0);
+                    uni = __all_sync(full, p[k] == p0 && (kl[k] | vl[k]) < (1 << 26));
+                    if (uni) count_row_uniform<SMEM>(C, p0, kl[k], vl[k], lane);
+                    any_uni = any_uni || uni;
+                }
+                if (!uni) C.record(p[k], kl[k], vl[k]);
+            }
+            try_uni = any_uni;
+        } else {
+            // tail tile, or a record with a partition outside [0, P): per-record checks
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                if (valid[k]) {
+                    if ((unsigned)p[k] < (unsigned)P) C.record(p[k], kl[k], vl[k]);
+                    else bad++;
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
-            count_row<SMEM, FULL>(C, valid[k], p[k], kl[k], vl[k], lane, bad);
-            if (valid[k]) {
-                // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back:
-                // the raw extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps)
-                tmin = ts[k] < tmin ? ts[k] : tmin;
-                tmax = ts[k] > tmax ? ts[k] : tmax;
-            }
-            // metric.rs:249-251: size extrema, not for tombstones (branch-free; invalid rows have vl = -1)
+            // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back: the raw
+            // extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps)
+            tmin = ts[k] < tmin ? ts[k] : tmin;
+            const long long tm = (FULL || valid[k]) ? ts[k] : INT64_MIN;
+            tmax = tm > tmax ? tm : tmax;
+            // metric.rs:249-251: size extrema, not for tombstones (invalid rows carry vl = -1)
             const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
-            smin = min(smin, vl[k] >= 0 ? sz : 0xffffffffu);
-            smax = max(smax, vl[k] >= 0 ? sz : 0u);
+            if (vl[k] >= 0) {
+                smin = min(smin, sz);
+                smax = max(smax, sz);
+            }
         }
 
         if (HASH) {
             // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
             uint32_t off[ROWS];
             uint32_t h[ROWS];
-            bool fix16 = true, small = true;
+            // all keys null or exactly 16 bytes?  (kl ^ 16) & ~(kl >> 31) is 0 for both
+            uint32_t odd = 0;
+            bool small = true;
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                fix16 = fix16 && (kl[k] < 0 || kl[k] == 16);
+                odd |= ((uint32_t)kl[k] ^ 16u) & ~(uint32_t)(kl[k] >> 31);
                 small = small && kl[k] < (1 << 20);
             }
-            fix16 = __all_sync(full, fix16);
-            small = fix16 || __all_sync(full, small);
+            const bool fix16 = __all_sync(full, odd == 0);
             if (fix16) {
-                // every key of this tile is null or 16 bytes: offsets from ballots, no shuffle scan
+                // offsets from ballots, no shuffle scan
                 uint32_t before = 0;
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
@@ -476,34 +536,43 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                     off[k] = 16u * (before + __popc(m & lt_mask));
                     before += __popc(m);
                 }
-            } else if (small) {
+            } else {
+                small = __all_sync(full, small);
                 uint32_t c32 = 0;
+                if (small) {
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    const uint32_t v = (uint32_t)max(kl[k], 0);
-                    uint32_t inc = v;
+                    for (int k = 0; k < ROWS; k++) {
+                        const uint32_t v = (uint32_t)max(kl[k], 0);
+                        uint32_t inc = v;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(full, inc, d);
-                        if (lane >= d) inc += t;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t t = __shfl_up_sync(full, inc, d);
+                            if (lane >= d) inc += t;
+                        }
+                        off[k] = c32 + inc - v;
+                        c32 += __shfl_sync(full, inc, 31);
                     }
-                    off[k] = c32 + inc - v;
-                    c32 += __shfl_sync(full, inc, 31);
                 }
             }
-            const unsigned char *kb8 = keybuf + (size_t)buf * KEYBUF;
+            const uint32_t kb = keybuf + (uint32_t)buf * KEYBUF;
 
-            if (staged) {   // staged ⇒ the tile's keys total <= KEYBUF_COPY bytes ⇒ small
-                const uint32_t a0 = (uint32_t)(g0 & 15ull);
-                mbar_wait(&mbar[buf], (phase >> buf) & 1u);
+            if (info & 1u) {   // staged ⇒ the tile's keys total <= KEYBUF_COPY bytes ⇒ small
+                const uint32_t a0 = (info >> 1) & 15u;
+                mbar_wait(mbar + 8u * buf, (phase >> buf) & 1u);
                 phase ^= 1u << buf;
+#ifdef KTA_EXP_NO_FNV
+                if (fix16 && a0 == 0) {
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) h[k] = lds32(kb + off[k]);
+                } else
+#endif
                 if (fix16 && a0 == 0) {
                     // two independent FNV chains at a time per lane, one LDS.128 per key (null keys hash
-                    // garbage that is never used); the other 7 warps of the SM sub-partition supply the rest of the ILP
+                    // garbage that is never used); the other warps of the SM sub-partition supply the rest of the ILP
 #pragma unroll
                     for (int k = 0; k < ROWS; k += 2) {
-                        const uint4 qa = *reinterpret_cast<const uint4 *>(kb8 + off[k]);
-                        const uint4 qb = *reinterpret_cast<const uint4 *>(kb8 + off[k + 1]);
+                        const uint4 qa = lds128(kb + off[k]);
+                        const uint4 qb = lds128(kb + off[k + 1]);
                         uint32_t ha = FNV_BASIS, hb = FNV_BASIS;
                         ha = fnv_word(ha, qa.x); hb = fnv_word(hb, qb.x);
                         ha = fnv_word(ha, qa.y); hb = fnv_word(hb, qb.y);
@@ -513,80 +582,100 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                         h[k + 1] = hb;
                     }
                 } else {
-                    const uint32_t *kb32 = reinterpret_cast<const uint32_t *>(kb8);
 #pragma unroll
-                    for (int k = 0; k < ROWS; k++) h[k] = kl[k] >= 0 ? fnv_smem(kb32, a0 + off[k], kl[k]) : 0u;
+                    for (int k = 0; k < ROWS; k++) h[k] = kl[k] >= 0 ? fnv_smem(kb, a0 + off[k], kl[k]) : 0u;
                 }
-            } else if (small) {
+            } else if (fix16 || small) {
+                const uint64_t g0 = prm.key_tile_base[tile];
 #pragma unroll
                 for (int k = 0; k < ROWS; k++)
                     h[k] = (valid[k] && kl[k] >= 0) ? fnv_global(prm.key_bytes + g0 + off[k], kl[k]) : 0u;
             } else {
-                uint32_t *scratch = reinterpret_cast<uint32_t *>(keybuf + (size_t)buf * KEYBUF);  // not staged: free
-                wide_tile_hashes(prm.key_len, prm.n, prm.key_bytes + g0, tile, scratch, lane);
+                uint32_t *scratch = reinterpret_cast<uint32_t *>(wsm + 128 + (size_t)buf * KEYBUF);  // not staged: free
+                wide_tile_hashes(prm.key_len, prm.n, prm.key_bytes + prm.key_tile_base[tile], tile, scratch, lane);
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) h[k] = scratch[32 * k + lane];
             }
 
             // ---- LogCompactionInMemoryMetrics::handle_message, metric.rs:288-305 ----
+            if (CAPTURE) {
 #pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                const int64_t r = rbase + 32 * k;
-                const bool keyed = valid[k] && kl[k] >= 0;   // metric.rs:291 Some(k); None => {} (:302)
-                if (CAPTURE && valid[k]) prm.hash_out[r] = keyed ? h[k] : 0u;
-                if (keyed) {
-                    if (prm.exact) {
-                        // last-writer-wins per hash in seq order == BitSet insert/remove replayed in
-                        // order (metric.rs:295 mark_key_alive, :298 mark_key_dead)
+                for (int k = 0; k < ROWS; k++)
+                    if (valid[k]) prm.hash_out[rbase + 32 * k] = kl[k] >= 0 ? h[k] : 0u;
+            }
+            if (MODE == MODE_EXACT) {
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    if (valid[k] && kl[k] >= 0) {   // metric.rs:291 Some(k); None => {} (:302)
+                        // last-writer-wins per hash in seq order == BitSet insert/remove replayed in order
+                        // (metric.rs:295 mark_key_alive, :298 mark_key_dead)
+                        const int64_t r = rbase + 32 * k;
                         const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
                         const unsigned long long stamp = ((seq + 1ull) << 1) | (vl[k] >= 0 ? 1ull : 0ull);
                         atomicMax(prm.alive_table + h[k], stamp);
                         uint8_t *d = prm.alive_dirty + (h[k] >> DIRTY_SHIFT);
                         if (__ldca(d) == 0) *d = 1;
                     }
-                    if (prm.hll_p && vl[k] >= 0) hll_update(prm.hll, prm.hll_p, skip_mask, h[k]);
                 }
             }
+#ifndef KTA_EXP_NO_HLL
+            if (MODE == MODE_HLL) {
+                // the floor comes from the CTA's shared-memory copy: one global word read by every warp for every tile
+                // would make a single L2 line the bottleneck of the whole kernel (measured: +0.46 ms)
+                const uint32_t skip_mask = hll_skip_mask(prm.hll_p, *s_floor);
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    // in-stream sketch: every record with a key and a value (invalid rows carry kl = vl = -1)
+                    const uint32_t x = hll_mix(h[k]);
+                    if (((x & skip_mask) | (uint32_t)((kl[k] | vl[k]) >> 31)) == 0) hll_raise(prm.hll, prm.hll_p, x);
+                }
+            }
+#else
+            if (MODE == MODE_HLL) {   // experiment: keep the hashes alive without the sketch
+                if ((h[0] ^ h[1] ^ h[2] ^ h[3]) == 0x12345678u) prm.hll[0] = 1;
+            }
+#endif
         }
     };
 
     for (int it = 0; tile < prm.ntiles; tile += gstride, ++it) {
         const int buf = it & 1;
-        uint64_t g0 = 0;
-        bool staged = false;
-        uint32_t skip_mask = 0;
+        uint32_t info = 0;
         if (HASH) {
-            g0 = __shfl_sync(full, nxt_g0, 0);
-            staged = __shfl_sync(full, nxt_staged, 0) != 0;
-            if (prm.hll_p) skip_mask = hll_skip_mask(prm.hll_p, __shfl_sync(full, nxt_floor, 0));
-            __syncwarp();  // every lane is done reading buffer buf^1 (previous tile) before it is refilled
-            if (lane == 0 && tile + gstride < prm.ntiles) issue(tile + gstride, buf ^ 1);
+            info = __shfl_sync(full, nxt_info, 0);   // also: every lane is done with stage buf^1 before it is refilled
         }
-        if ((tile + 1) * TILE <= prm.n) body(std::true_type{}, tile, buf, g0, staged, skip_mask);
-        else body(std::false_type{}, tile, buf, g0, staged, skip_mask);
-        if (SMEM && (it & (FOLD_TILES - 1)) == FOLD_TILES - 1) C.fold_sums(lane, 1u << 30);
-        // warp 0 of every CTA re-derives the HLL floor at its tile 4, 8, 16, 32, ... (cheap, and early)
-        if (HASH && prm.hll_p && warp == 0 && it >= 4 && (it & (it - 1)) == 0)
-            hll_refresh_floor(prm.hll, prm.hll_p, prm.hll_floor, lane);
+        const bool has_next = tile + gstride < prm.ntiles;
+        if (HASH && has_next && lane == 0) nxt_info = issue(tile + gstride, buf ^ 1);
+        if ((tile + 1) * TILE <= prm.n) body(std::true_type{}, tile, buf, info, has_next);
+        else body(std::false_type{}, tile, buf, info, has_next);
+        if ((it & (FOLD_TILES - 1)) == FOLD_TILES - 1) {
+            if (SMEM) C.fold_sums(lane, 1u << 30);
+            try_uni = try_uni || (it & 15) == 15;   // re-probe now and then
+        }
+        // HLL floor upkeep: every 4th tile ONE warp of each CTA (the role rotates, so no warp falls behind)
+        // refreshes one slice — the 148 CTAs cover all 64 slices about every two tile-times — and republishes
+        // the floor to its CTA through shared memory
+        if (MODE == MODE_HLL && (it & 3) == 3 && ((it >> 2) & 31) == (warp & 31)) {
+            hll_refresh_slice(prm.hll, prm.hll_p, prm.hll_floor, (blockIdx.x + (uint32_t)(it >> 2) * 37u) & (HLL_SLICES - 1), lane);
+            if (lane == 0) *s_floor = ld_cg_u32(prm.hll_floor);
+        }
     }
 
     // ---- flush CTA-private state ----
     __syncthreads();
     if (SMEM) {
-        const int nh = 2 * NB * P;  // khist then vhist, bucket-major in shared memory, partition-major in global
+        // bucket rows → global [which][p][bucket]; row 32 → knull; row 65 (tombstones) is derived, not stored
+        const int nh = (ROW_V + NB) * P;
         for (int i = tid; i < nh; i += blockDim.x) {
             const uint32_t v = scnt[i];
             if (v) {
-                const int row = i / P, pp = i - row * P;           // row = which * NB + bucket
-                const int which = row >= NB, b = row - which * NB;
-                atomicAdd(&prm.sums[(size_t)(which * P + pp) * NB + b], (unsigned long long)v);
+                const int row = i / P, pp = i - row * P;
+                if (row < NB) atomicAdd(&prm.sums[(size_t)pp * NB + row], (unsigned long long)v);
+                else if (row == NB) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 2) + pp], (unsigned long long)v);
+                else atomicAdd(&prm.sums[(size_t)(P + pp) * NB + (row - ROW_V)], (unsigned long long)v);
             }
         }
         if (warp == 0) C.fold_sums(lane, 1u);
-        for (int i = tid; i < P; i += blockDim.x) {
-            const uint32_t kn = scnt[(2 * NB + 4) * P + i];
-            if (kn) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 2) + i], (unsigned long long)kn);
-        }
     }
     // extrema + bad-partition count: warp shuffle, then one lane per warp, then one thread per CTA
     long long smin64 = smin != 0xffffffffu ? (long long)smin : INT64_MAX;
@@ -689,7 +778,7 @@ constexpr int THREADS = 256;  // block size of the table / utility kernels below
 
 __global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned long long *table, const uint8_t *dirty,
                                                                 uint32_t npages, unsigned long long *alive_count,
-                                                                uint8_t *hll, int hll_p) {
+                                                                uint32_t *hll, int hll_p) {
     unsigned long long local = 0;
     for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
         if (!dirty[page]) continue;
@@ -698,7 +787,7 @@ __global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned l
             const unsigned long long v = pg[i];
             if (v & 1ull) {
                 local++;
-                if (hll_p) hll_update(hll, hll_p, 0u, (page << DIRTY_SHIFT) + (uint32_t)i);
+                if (hll_p) hll_raise(hll, hll_p, hll_mix((page << DIRTY_SHIFT) + (uint32_t)i));
             }
         }
     }
@@ -755,18 +844,17 @@ __global__ void __launch_bounds__(THREADS) alive_clear_kernel(unsigned long long
 }
 
 // state (re)initialisation: sums = 0, minmax = {+inf, -inf, u64 max, 0}, hll = 0, hll floor = 0
-__global__ void state_init_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint8_t *hll, size_t nhll,
+__global__ void state_init_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint32_t *hll, size_t nhll,
                                   uint32_t *hll_floor) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsums; i += stride) sums[i] = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nhll / 4; i += stride)
-        reinterpret_cast<uint32_t *>(hll)[i] = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nhll; i += stride) hll[i] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         minmax[0] = INT64_MAX;
         minmax[1] = INT64_MIN;
         reinterpret_cast<unsigned long long *>(minmax)[2] = ~0ull;
         reinterpret_cast<unsigned long long *>(minmax)[3] = 0ull;
-        *hll_floor = 0;
+        for (int i = 0; i <= HLL_SLICES; i++) hll_floor[i] = 0;
     }
 }
 
@@ -777,13 +865,13 @@ __global__ void fnv32_kernel(int64_t n, const int32_t *key_len, const uint64_t *
         out[i] = key_len[i] < 0 ? 0u : fnv_global(key_bytes + key_off[i], key_len[i]);
 }
 
-// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×(nhll/8) register words] ----
+// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×(nhll/2) register words] ----
 // Every rank writes its min/max scalars and HLL registers into its own slot and zeros elsewhere, so ONE
 // SUM all-reduce over u64 delivers every rank's values to every rank; the import folds them.
 __global__ void merge_export_kernel(const unsigned long long *sums, size_t nsums, const long long *minmax,
-                                    const uint8_t *hll, size_t nhll, int rank, int world, unsigned long long *buf) {
+                                    const uint32_t *hll, size_t nhll, int rank, int world, unsigned long long *buf) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nmm = (size_t)world * 4, hw = nhll / 8, total = nsums + nmm + (size_t)world * hw;
+    const size_t nmm = (size_t)world * 4, hw = nhll / 2, total = nsums + nmm + (size_t)world * hw;
     for (size_t i = t0; i < total; i += stride) {
         unsigned long long v = 0;
         if (i < nsums) v = sums[i];
@@ -798,23 +886,19 @@ __global__ void merge_export_kernel(const unsigned long long *sums, size_t nsums
     }
 }
 
-__global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint8_t *hll,
+__global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long long *minmax, uint32_t *hll,
                                     size_t nhll, uint32_t *hll_floor, int world, const unsigned long long *buf) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = t0; i < nsums; i += stride) sums[i] = buf[i];
     const unsigned long long *mm = buf + nsums;
-    const size_t hw = nhll / 8;
+    const size_t hw = nhll / 2;
     const unsigned long long *hb = mm + (size_t)world * 4;
     for (size_t i = t0; i < hw; i += stride) {
         unsigned long long m = 0;
         for (int r = 0; r < world; r++) {
             const unsigned long long v = hb[(size_t)r * hw + i];
-            unsigned long long o = 0;
-#pragma unroll
-            for (int b = 0; b < 64; b += 8) {
-                const unsigned long long x = (m >> b) & 0xff, y = (v >> b) & 0xff;
-                o |= (x > y ? x : y) << b;   // bytewise max
-            }
+            const unsigned long long lo = max(m & 0xffffffffull, v & 0xffffffffull), hi = max(m >> 32, v >> 32);
+            const unsigned long long o = lo | (hi << 32);   // max of each 32-bit register
             m = o;
         }
         reinterpret_cast<unsigned long long *>(hll)[i] = m;
@@ -832,7 +916,7 @@ __global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long
         minmax[1] = tmax;
         reinterpret_cast<unsigned long long *>(minmax)[2] = smin;
         reinterpret_cast<unsigned long long *>(minmax)[3] = smax;
-        *hll_floor = 0;
+        for (int i = 0; i <= HLL_SLICES; i++) hll_floor[i] = 0;
     }
 }
 

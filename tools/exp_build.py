@@ -1,0 +1,15 @@
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import glob
+from kafka_topic_analyzer_b200 import _native as N
+variants = {
+ 'base': [],
+ 'nohll': ['KTA_EXP_NO_HLL'],
+ 'nofnv': ['KTA_EXP_NO_FNV'],
+}
+for f in glob.glob(N.LIB_PATH.replace('.so','_exp_*.so')): os.remove(f)
+import concurrent.futures as cf
+def b(kv):
+    k,v=kv
+    N.build(force=True, defines=v, out=N.LIB_PATH.replace('.so','_exp_%s.so'%k)); return k
+with cf.ThreadPoolExecutor(8) as ex:
+    for k in ex.map(b, variants.items()): print('built',k)
