@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -274,7 +274,8 @@ def run_ours(a):
         "config": {"workload": workload_name(a, world), "partitions": P, "records_per_gpu": n,
                    "mean_key_bytes": topic.key_bytes_len / n, "l2": "inputs larger than L2"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "kta::scan_kernel<HASH=%s,SMEM=%s>" % (a.mode != "counters", P <= 512),
+                     "traffic": traffic,
+                     "kernel": "kta::scan_kernel<MODE_%s>" % {"fused": "HLL", "counters": "COUNTERS", "alive": "EXACT"}[a.mode],
                      "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
         "logical_topic_gb_s": value * (topic.key_bytes_len / n + a.value_mean) / 1e9,
@@ -310,6 +311,9 @@ def run_ours(a):
 
         e2e_step()
         barrier()
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
         e0.record(stream)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -317,6 +321,8 @@ def run_ours(a):
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
+        if rank == 0:
+            line["clocks_e2e"] = sampler2.stop()
         t = torch.tensor([max(e0.elapsed_time(e1) / 1e3, wall)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1,0 +1,178 @@
+// kafka-topic-analyzer (B200 build) — the reference's CLI surface (src/main.rs:32-67) over libkta_gpu.so.
+//
+//   -t/--topic TOPIC  -b/--bootstrap-server HOSTS  [--librdkafka k=v,...]  [-c/--count-alive-keys]
+//   --synthetic n=...,partitions=...,value_mean=...,run_len=...,distinct_keys=...,key_mode=...,seed=...,
+//               tombstone_per_10k=...,null_key_per_10k=...      (the in-memory topic of BASELINE.json configs)
+//   --feed push|batch|device   how records reach the handlers: kta_push per record (the reference's call shape),
+//                              kta_push_batch_host, or generated and scanned in HBM
+//
+// There is no librdkafka and no broker in this build: without --synthetic the program explains
+// that and exits, like the reference does when it cannot fetch metadata.  Everything numeric comes from the
+// GPU library; this file only feeds records and prints.
+#include <cuda_runtime_api.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/kta.h"
+#include "kta_report.hpp"
+
+static void die(const char *what) {
+    fprintf(stderr, "error: %s: %s\n", what, kta_last_error());
+    exit(1);
+}
+#define KTA(call) do { if ((call) != KTA_OK) die(#call); } while (0)
+
+int main(int argc, char **argv) {
+    std::string topic, bootstrap, librdkafka, synthetic, feed = "batch";
+    int count_alive_occurrences = 0, hll = 0;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&]() -> std::string { if (i + 1 >= argc) { fprintf(stderr, "error: %s needs a value\n", a.c_str()); exit(2); } return argv[++i]; };
+        if (a == "-t" || a == "--topic") topic = val();
+        else if (a == "-b" || a == "--bootstrap-server") bootstrap = val();
+        else if (a == "--librdkafka") librdkafka = val();
+        else if (a == "-c" || a == "--count-alive-keys") count_alive_occurrences++;
+        else if (a == "-cc") count_alive_occurrences += 2;
+        else if (a == "--synthetic") synthetic = val();
+        else if (a == "--feed") feed = val();
+        else if (a == "--hll") hll = atoi(val().c_str());
+        else if (a == "-V" || a == "--version") { puts("Kafka Topic Analyzer 0.4.1"); return 0; }  // main.rs:35
+        else if (a == "-h" || a == "--help") {
+            puts("Kafka Topic Analyzer 0.4.1\n\nUSAGE:\n    kafka-topic-analyzer [FLAGS] [OPTIONS] --bootstrap-server <BOOTSTRAP_SERVER> --topic <TOPIC>\n\n"
+                 "FLAGS:\n    -c, --count-alive-keys    Counts the effective number of alive keys in a log compacted topic\n\n"
+                 "OPTIONS:\n    -b, --bootstrap-server <BOOTSTRAP_SERVER>    Bootstrap server(s) to work with, comma separated\n"
+                 "        --librdkafka <LIBRDKAFKA>                Options to pass into the underlying librdkafka\n"
+                 "    -t, --topic <TOPIC>                          The topic to analyze\n"
+                 "        --synthetic <k=v,...>                    in-memory synthetic topic (this build has no Kafka client)\n"
+                 "        --feed <push|batch|device>               how records are handed to the metric handlers");
+            return 0;
+        } else { fprintf(stderr, "error: Found argument '%s' which wasn't expected\n", a.c_str()); return 2; }
+    }
+    if (topic.empty() || bootstrap.empty()) {
+        fprintf(stderr, "error: The following required arguments were not provided:\n    --bootstrap-server <BOOTSTRAP_SERVER>\n    --topic <TOPIC>\n");
+        return 2;
+    }
+    if (synthetic.empty()) {
+        fprintf(stderr, "Error fetching metadata: this build has no librdkafka client (no broker access); pass --synthetic n=...,partitions=...\n");
+        return 101;  // the reference panics here (src/kafka.rs:61)
+    }
+    const auto start_time = std::chrono::steady_clock::now();  // main.rs:69
+
+    std::map<std::string, std::string> kv;
+    for (size_t p = 0; p < synthetic.size();) {
+        size_t e = synthetic.find(',', p);
+        if (e == std::string::npos) e = synthetic.size();
+        const std::string item = synthetic.substr(p, e - p);
+        const size_t q = item.find('=');
+        if (q != std::string::npos) kv[item.substr(0, q)] = item.substr(q + 1);
+        p = e + 1;
+    }
+    auto geti = [&](const char *k, long long d) { return kv.count(k) ? atoll(kv[k].c_str()) : d; };
+    kta_synth_spec spec{};
+    spec.seed = (uint64_t)geti("seed", 0x4B544131);
+    spec.num_partitions = (int32_t)geti("partitions", 4);
+    spec.run_len = (int32_t)geti("run_len", 1);
+    spec.n_total = geti("n", 100000);
+    spec.n_total -= spec.n_total % ((int64_t)spec.num_partitions * spec.run_len);
+    spec.distinct_keys = (uint64_t)geti("distinct_keys", spec.n_total / 10 > spec.num_partitions ? spec.n_total / 10 : spec.num_partitions);
+    spec.key_mode = (int32_t)geti("key_mode", 0);
+    spec.value_mean = (int32_t)geti("value_mean", 256);
+    spec.null_key_per_10k = (int32_t)geti("null_key_per_10k", 100);
+    spec.tombstone_per_10k = (int32_t)geti("tombstone_per_10k", 500);
+    spec.ts_missing_per_10k = (int32_t)geti("ts_missing_per_10k", 0);
+    spec.empty_value_per_10k = (int32_t)geti("empty_value_per_10k", 0);
+    const int P = spec.num_partitions;
+    const int64_t n = spec.n_total;
+
+    // get_topic_offsets (src/kafka.rs:60-72): synthetic watermarks
+    std::vector<int64_t> start_offsets(P, 0), end_offsets(P, n / P);
+    if (n == 0) { fprintf(stderr, "Given topic has no content, no analysis possible. Exiting.\n"); return 254; }  // main.rs:98-101
+
+    kta_config cfg{};
+    cfg.struct_size = sizeof cfg;
+    cfg.device = -1;
+    cfg.num_partitions = P;
+    cfg.count_alive_keys = count_alive_occurrences == 1 ? 1 : 0;  // occurrences_of == 1, main.rs:77-80
+    cfg.hll_precision = hll;
+    cfg.now_s = INT64_MIN;
+    kta_handle *h = nullptr;
+    KTA(kta_create(&cfg, &h));
+
+    printf("Subscribing to %s\n", topic.c_str());          // src/kafka.rs:88
+    printf("Starting message consumption...\n");            // src/kafka.rs:91
+    const int64_t CH = 1 << 20;
+    if (feed == "device") {
+        const int64_t ntiles = (n + KTA_KEY_TILE - 1) / KTA_KEY_TILE;
+        int32_t *dp, *dk, *dv; int64_t *dt; uint8_t *dkb; uint64_t *dtb;
+        const int64_t cap = n * 40 + 64;
+        if (cudaMalloc((void **)&dp, n * 4) || cudaMalloc((void **)&dk, n * 4) || cudaMalloc((void **)&dv, n * 4) || cudaMalloc((void **)&dt, n * 8) ||
+            cudaMalloc((void **)&dkb, cap) || cudaMalloc((void **)&dtb, (ntiles + 1) * 8)) { fprintf(stderr, "cudaMalloc failed\n"); return 1; }
+        int64_t kbl = 0;
+        if (kta_synth_fill_device(&spec, -1, 0, 1, 0, n, dp, nullptr, dt, dk, dv, nullptr, dkb, cap, dtb, &kbl)) { fprintf(stderr, "synthetic fill failed\n"); return 1; }
+        kta_batch b{};
+        b.n = n; b.partition = dp; b.ts_ms = dt; b.key_len = dk; b.value_len = dv; b.key_bytes = dkb; b.key_bytes_len = kbl; b.key_tile_base = dtb;
+        KTA(kta_scan_batch_device(h, &b));
+    } else {
+        std::vector<int32_t> part(CH), kl(CH), vl(CH);
+        std::vector<int64_t> off(CH), ts(CH);
+        std::vector<uint8_t> kb((size_t)CH * 40 + 16);
+        for (int64_t s0 = 0; s0 < n; s0 += CH) {
+            const int64_t c = std::min(CH, n - s0);
+            int64_t kbl = 0;
+            if (kta_synth_fill_host(&spec, 0, 1, s0, c, part.data(), off.data(), ts.data(), kl.data(), vl.data(), nullptr,
+                                    kb.data(), (int64_t)kb.size(), &kbl)) { fprintf(stderr, "synthetic fill failed\n"); return 1; }
+            if (feed == "push") {
+                // the reference's shape: one handle_message per polled message (src/kafka.rs:107-109)
+                int64_t ko = 0;
+                for (int64_t i = 0; i < c; i++) {
+                    KTA(kta_push(h, part[i], off[i], ts[i], kl[i] > 0 ? kb.data() + ko : (kl[i] == 0 ? kb.data() : nullptr), kl[i], vl[i]));
+                    if (kl[i] > 0) ko += kl[i];
+                }
+            } else {
+                kta_batch b{};
+                b.n = c; b.seq_base = (uint64_t)s0; b.partition = part.data(); b.offset = off.data(); b.ts_ms = ts.data();
+                b.key_len = kl.data(); b.value_len = vl.data(); b.key_bytes = kb.data(); b.key_bytes_len = kbl;
+                KTA(kta_push_batch_host(h, &b));
+            }
+        }
+    }
+    KTA(kta_finalize(h));
+    const uint64_t duration_secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
+
+    kta_report::Summary s{};
+    s.topic = topic;
+    s.duration_secs = duration_secs;
+    KTA(kta_global(h, KTA_OVERALL_COUNT, &s.overall_count));
+    KTA(kta_timestamps(h, &s.earliest_s, &s.earliest_ns, &s.latest_s));
+    KTA(kta_global(h, KTA_LARGEST_MESSAGE, &s.largest_message));
+    KTA(kta_global(h, KTA_SMALLEST_MESSAGE, &s.smallest_message));
+    KTA(kta_global(h, KTA_OVERALL_SIZE, &s.overall_size));
+    s.has_alive_keys = cfg.count_alive_keys == 1;
+    if (s.has_alive_keys) KTA(kta_alive_keys(h, &s.alive_keys));
+    std::vector<kta_report::PartitionRow> rows;
+    for (int p = 0; p < P; p++) {  // partitions sorted ascending, main.rs:103-106
+        kta_report::PartitionRow r{};
+        r.partition = p; r.start_offset = start_offsets[p]; r.end_offset = end_offsets[p];
+        KTA(kta_counter(h, KTA_TOTAL, p, &r.total)); KTA(kta_counter(h, KTA_ALIVE, p, &r.alive));
+        KTA(kta_counter(h, KTA_TOMBSTONES, p, &r.tombstones)); KTA(kta_dirty_ratio(h, p, &r.dirty_ratio));
+        KTA(kta_counter(h, KTA_KEY_NULL, p, &r.key_null)); KTA(kta_counter(h, KTA_KEY_NON_NULL, p, &r.key_non_null));
+        KTA(kta_counter(h, KTA_KEY_SIZE_SUM, p, &r.key_size_sum)); KTA(kta_counter(h, KTA_VALUE_SIZE_SUM, p, &r.value_size_sum));
+        // the reference panics ("attempt to divide by zero") when sum > 0 && alive == 0 (metric.rs:132-157)
+        int rc = kta_avg(h, KTA_KEY_SIZE_AVG, p, &r.key_size_avg);
+        if (rc == KTA_OK) rc = kta_avg(h, KTA_VALUE_SIZE_AVG, p, &r.value_size_avg);
+        if (rc == KTA_OK) rc = kta_avg(h, KTA_MESSAGE_SIZE_AVG, p, &r.message_size_avg);
+        if (rc == KTA_ERR_DIV_BY_ZERO) { fprintf(stderr, "thread 'main' panicked at 'attempt to divide by zero', src/metric.rs\n"); return 101; }
+        if (rc != KTA_OK) die("kta_avg");
+        rows.push_back(r);
+    }
+    fputs(kta_report::render(s, rows).c_str(), stdout);
+    if (hll) { double e = 0; KTA(kta_alive_keys_hll(h, &e)); printf("| extension: HyperLogLog(p=%d) alive-key estimate: %.0f\n", hll, e); }
+    kta_destroy(h);
+    return 0;
+}

@@ -45,3 +45,50 @@ def allreduce_merge(engine: KtaEngine, group=None) -> None:
         for r in range(world):
             if r != rank and cl[r]:
                 engine.alive_import(h_all[r * cap:], s_all[r * cap:], int(cl[r]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Host-side statement of the merge-buffer layout (what merge_export_kernel / merge_import_kernel do on the
+# device, csrc/kta_kernels.cuh).  Used by the gloo CPU tests of the N>1 logic and usable for host-side merges.
+#   [ sums (nsums u64) | world × 4 extrema slots | world × (nhll/2) words, two u32 registers per word ]
+# Every rank fills only its own slots, so ONE SUM all-reduce hands every rank's values to every rank.
+# ---------------------------------------------------------------------------------------------------
+def merge_words(nsums: int, nhll: int, world: int) -> int:
+    return nsums + world * 4 + world * (nhll // 2)
+
+
+def pack_merge_buffer(sums, minmax, hll, rank: int, world: int):
+    """sums u64[nsums]; minmax = (min_ts i64, max_ts i64, min_size u64, max_size u64); hll u32[nhll]."""
+    import numpy as np
+    nsums, nhll = len(sums), len(hll)
+    buf = np.zeros(merge_words(nsums, nhll, world), dtype=np.uint64)
+    buf[:nsums] = np.asarray(sums, dtype=np.uint64)
+    mm = np.array([minmax[0], minmax[1]], dtype=np.int64).view(np.uint64)
+    buf[nsums + 4 * rank: nsums + 4 * rank + 2] = mm
+    buf[nsums + 4 * rank + 2] = np.uint64(minmax[2])
+    buf[nsums + 4 * rank + 3] = np.uint64(minmax[3])
+    if nhll:
+        hw = nhll // 2
+        regs = np.asarray(hll, dtype=np.uint32)
+        words = regs[0::2].astype(np.uint64) | (regs[1::2].astype(np.uint64) << np.uint64(32))
+        o = nsums + 4 * world + rank * hw
+        buf[o:o + hw] = words
+    return buf
+
+
+def fold_merge_buffer(buf, nsums: int, nhll: int, world: int):
+    """inverse of pack after the SUM all-reduce: returns (sums, (min_ts, max_ts, min_size, max_size), hll)."""
+    import numpy as np
+    sums = buf[:nsums].copy()
+    mm = buf[nsums:nsums + 4 * world].reshape(world, 4)
+    tmin = int(mm[:, 0].copy().view(np.int64).min())
+    tmax = int(mm[:, 1].copy().view(np.int64).max())
+    smin, smax = int(mm[:, 2].min()), int(mm[:, 3].max())
+    hll = np.zeros(nhll, dtype=np.uint32)
+    if nhll:
+        hw = nhll // 2
+        w = buf[nsums + 4 * world:].reshape(world, hw)
+        lo = (w & np.uint64(0xFFFFFFFF)).max(axis=0).astype(np.uint32)
+        hi = (w >> np.uint64(32)).max(axis=0).astype(np.uint32)
+        hll[0::2], hll[1::2] = lo, hi
+    return sums, (tmin, tmax, smin, smax), hll
