@@ -32,6 +32,8 @@ constexpr int WARP_SMEM = 128 + 2 * KEYBUF;  // per warp: 2 mbarriers (+ scratch
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
+constexpr int ALIVE_BUCKETS = 512;        // alive-table application order: 2^32 / 512 hash values = 64 MiB of table per bucket
+constexpr int ALIVE_BUCKET_SHIFT = 23;
 constexpr int FOLD_TILES = 4;             // every warp checks the CTA's 16-bit-split sums every 4 of its tiles
 
 // shared-memory counter rows (each row = P u32 words):
@@ -44,8 +46,10 @@ enum ScanMode { MODE_COUNTERS = 0, MODE_HLL = 1, MODE_EXACT = 2 };
 
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
-// counter rows, then one 128-byte CTA scratch line (word 0: the CTA's cached copy of the HLL floor)
-__host__ __device__ inline size_t smem_counter_bytes(int P) { return (((size_t)P * SMEM_ROWS * 4 + 127) & ~(size_t)127) + 128; }
+// counter rows, then the CTA scratch: one 128-byte line (word 0: the CTA's cached copy of the HLL floor) followed by
+// the per-CTA hash-bucket histogram of MODE_EXACT
+constexpr int CTA_SCRATCH = 128 + ALIVE_BUCKETS * 4;
+__host__ __device__ inline size_t smem_counter_bytes(int P) { return (((size_t)P * SMEM_ROWS * 4 + 127) & ~(size_t)127) + CTA_SCRATCH; }
 
 struct ScanParams {
     int64_t n;
@@ -66,8 +70,13 @@ struct ScanParams {
     uint32_t *hll;                   // [1 << hll_p] registers (one u32 each so that RED.MAX applies)
     uint32_t *hll_floor;             // [0] lower bound of every register (monotone; lets most records skip the
                                      // table), [1..HLL_SLICES] per-slice minima it is derived from
-    unsigned long long *alive_table; // [2^32]
+    unsigned long long *alive_table; // [2^32] stamps: epoch(16) | seq+1 (47) | alive(1)
     uint8_t *alive_dirty;            // [2^32 >> DIRTY_SHIFT]
+    unsigned long long *alive_count; // running number of alive entries of the current epoch (two's-complement deltas)
+    uint64_t epoch_tag;              // current epoch << 48
+    uint32_t *hash_col;              // MODE_EXACT, bucketed: per-record hash out [n] (NULL = stamp the table directly)
+    uint8_t *flag_col;               //   per-record flags out [n]: bit 1 keyed, bit 0 alive
+    uint32_t *bucket_hist;           //   [ALIVE_BUCKETS] records per hash bucket (global, accumulated)
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
 };
 
@@ -330,6 +339,25 @@ struct Counters {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// alive-key table (LogCompactionInMemoryMetrics, metric.rs:262-305).  table[hash] = the stamp of the LAST
+// record that carried this hash: epoch (16 bits) | seq + 1 (47 bits) | alive (1 bit); atomicMax makes
+// "last" mean highest seq regardless of execution order.  The epoch makes kta_reset O(1): stamps of an older
+// epoch lose against any new stamp and count as "never seen".  The number of alive entries (sum_all_alive,
+// metric.rs:282-284) is maintained incrementally from the value atomicMax returns — the chain of successful
+// updates of one entry telescopes to (final alive − initial alive) — so no pass over the 32 GiB table is needed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int alive_stamp(unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag, uint32_t hash,
+                                           uint64_t seq_plus_1, bool alive) {
+    const unsigned long long stamp = epoch_tag | (seq_plus_1 << 1) | (alive ? 1ull : 0ull);
+    const unsigned long long old = atomicMax(table + hash, stamp);
+    uint8_t *d = dirty + (hash >> DIRTY_SHIFT);
+    if (__ldca(d) == 0) *d = 1;
+    if (stamp <= old) return 0;   // a later record already spoke for this hash
+    const int was = ((old ^ epoch_tag) >> 48) == 0 ? (int)(old & 1ull) : 0;
+    return (int)alive - was;
+}
+
 // A row of 32 records that all belong to one partition (the usual shape of a Kafka fetch): aggregate in the
 // warp, one reduction per distinct bucket and per sum instead of 32 same-address ones.
 template <bool SMEM>
@@ -405,8 +433,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     const int P = prm.P;
     // layout: counter rows (SMEM) | per warp: mbar[2] + 112 B scratch | keybuf[2]
     uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
-    const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : 128;
-    volatile uint32_t *s_floor = reinterpret_cast<volatile uint32_t *>(smem_raw + cta_bytes - 128);
+    const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : CTA_SCRATCH;
+    volatile uint32_t *s_floor = reinterpret_cast<volatile uint32_t *>(smem_raw + cta_bytes - CTA_SCRATCH);
+    uint32_t *s_bucket = const_cast<uint32_t *>(s_floor) + 32;   // [ALIVE_BUCKETS], MODE_EXACT only
     unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * (HASH ? WARP_SMEM : 128);
     const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
@@ -417,6 +446,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
     }
     if (MODE == MODE_HLL && tid == 0) *s_floor = ld_cg_u32(prm.hll_floor);
+    if (MODE == MODE_EXACT)
+        for (int i = tid; i < ALIVE_BUCKETS; i += blockDim.x) s_bucket[i] = 0;
     if (HASH && lane == 0) {
         mbar_init(mbar, 1);
         mbar_init(mbar + 8, 1);
@@ -442,6 +473,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
+    int alive_delta = 0;      // MODE_EXACT, direct stamping: change of the alive-entry count caused by this lane
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     uint32_t nxt_info = 0;
@@ -604,17 +636,31 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                     if (valid[k]) prm.hash_out[rbase + 32 * k] = kl[k] >= 0 ? h[k] : 0u;
             }
             if (MODE == MODE_EXACT) {
+                // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
+                // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
+                // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
+                if (prm.hash_col) {
+                    // bucketed: hand (hash, flags) to the bucket pass, which applies the stamps to the table in
+                    // hash order so that each 64 MiB slice of the 32 GiB table is touched while it sits in L2
+                    const uint32_t sb = smem_u32(s_bucket);
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    if (valid[k] && kl[k] >= 0) {   // metric.rs:291 Some(k); None => {} (:302)
-                        // last-writer-wins per hash in seq order == BitSet insert/remove replayed in order
-                        // (metric.rs:295 mark_key_alive, :298 mark_key_dead)
-                        const int64_t r = rbase + 32 * k;
-                        const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
-                        const unsigned long long stamp = ((seq + 1ull) << 1) | (vl[k] >= 0 ? 1ull : 0ull);
-                        atomicMax(prm.alive_table + h[k], stamp);
-                        uint8_t *d = prm.alive_dirty + (h[k] >> DIRTY_SHIFT);
-                        if (__ldca(d) == 0) *d = 1;
+                    for (int k = 0; k < ROWS; k++) {
+                        if (valid[k]) {
+                            const int64_t r = rbase + 32 * k;
+                            prm.hash_col[r] = h[k];
+                            prm.flag_col[r] = (uint8_t)((kl[k] >= 0 ? 2 : 0) | (vl[k] >= 0 ? 1 : 0));
+                            if (kl[k] >= 0) red_shared_add(sb + 4u * (h[k] >> ALIVE_BUCKET_SHIFT), 1u);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {
+                        if (valid[k] && kl[k] >= 0) {
+                            const int64_t r = rbase + 32 * k;
+                            const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
+                            alive_delta += alive_stamp(prm.alive_table, prm.alive_dirty, prm.epoch_tag, h[k], seq + 1ull,
+                                                       vl[k] >= 0);
+                        }
                     }
                 }
             }
@@ -663,6 +709,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
 
     // ---- flush CTA-private state ----
     __syncthreads();
+    if (MODE == MODE_EXACT) {
+        if (prm.hash_col) {
+            for (int i = tid; i < ALIVE_BUCKETS; i += blockDim.x)
+                if (s_bucket[i]) atomicAdd(prm.bucket_hist + i, s_bucket[i]);
+        } else {
+            alive_delta = __reduce_add_sync(full, alive_delta);
+            if (lane == 0 && alive_delta) atomicAdd(prm.alive_count, (unsigned long long)(long long)alive_delta);
+        }
+    }
     if (SMEM) {
         // bucket rows → global [which][p][bucket]; row 32 → knull; row 65 (tombstones) is derived, not stored
         const int nh = (ROW_V + NB) * P;
@@ -769,78 +824,142 @@ __global__ void __launch_bounds__(1024) tile_base_scan_kernel(uint64_t *tile_bas
 }
 
 // ------------------------------------------------------------------------------------------------
-// alive-key table: resolve / export / import / clear.  Entry = ((seq+1) << 1) | alive of the last
-// record that carried this hash; 0 = never seen.  sum_all_alive (metric.rs:282-284) = #entries with
-// the alive bit set.
+// alive-key table: bucket pass (scan → offsets → scatter → apply), HLL over the alive set, export / import / clear
 // ------------------------------------------------------------------------------------------------
 constexpr int PAGE_ENTRIES = 1 << DIRTY_SHIFT;
 constexpr int THREADS = 256;  // block size of the table / utility kernels below
+constexpr int SCATTER_THREADS = 512, SCATTER_CHUNK = 8192;
 
-__global__ void __launch_bounds__(THREADS) alive_resolve_kernel(const unsigned long long *table, const uint8_t *dirty,
-                                                                uint32_t npages, unsigned long long *alive_count,
-                                                                uint32_t *hll, int hll_p) {
-    unsigned long long local = 0;
+// bucket[0..B): counts in, exclusive offsets out; bucket[B..2B): cursors (= offsets); bucket[2B]: total
+__global__ void __launch_bounds__(ALIVE_BUCKETS) bucket_offsets_kernel(uint32_t *bucket) {
+    __shared__ uint32_t wsum[ALIVE_BUCKETS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t v = bucket[tid];
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; w++) base += wsum[w];
+    const uint32_t excl = base + inc - v;
+    bucket[tid] = 0;                         // ready for the next batch's histogram
+    bucket[ALIVE_BUCKETS + tid] = excl;
+    if (tid == ALIVE_BUCKETS - 1) bucket[2 * ALIVE_BUCKETS] = excl + v;
+}
+
+// Move every keyed record's (hash, batch-relative stamp) into its hash bucket.  A CTA handles 8192 records at a
+// time: shared-memory histogram, ONE global reservation per bucket, then the scatter with shared-memory cursors.
+// entry = hash << 32 | (index_in_batch + 1) << 1 | alive
+__global__ void __launch_bounds__(SCATTER_THREADS) bucket_scatter_kernel(const uint32_t *hash_col, const uint8_t *flag_col,
+                                                                         int64_t n, uint32_t *bucket,
+                                                                         unsigned long long *entries) {
+    __shared__ uint32_t hist[ALIVE_BUCKETS], base[ALIVE_BUCKETS];
+    const int tid = threadIdx.x;
+    const int64_t nchunks = (n + SCATTER_CHUNK - 1) / SCATTER_CHUNK;
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        for (int i = tid; i < ALIVE_BUCKETS; i += SCATTER_THREADS) hist[i] = 0;
+        __syncthreads();
+        const int64_t r0 = chunk * SCATTER_CHUNK;
+#pragma unroll 4
+        for (int j = 0; j < SCATTER_CHUNK / SCATTER_THREADS; j++) {
+            const int64_t r = r0 + j * SCATTER_THREADS + tid;
+            if (r < n && (flag_col[r] & 2)) atomicAdd(&hist[hash_col[r] >> ALIVE_BUCKET_SHIFT], 1u);
+        }
+        __syncthreads();
+        for (int i = tid; i < ALIVE_BUCKETS; i += SCATTER_THREADS) {
+            const uint32_t c = hist[i];
+            base[i] = c ? atomicAdd(&bucket[ALIVE_BUCKETS + i], c) : 0u;
+            hist[i] = 0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < SCATTER_CHUNK / SCATTER_THREADS; j++) {
+            const int64_t r = r0 + j * SCATTER_THREADS + tid;
+            if (r < n) {
+                const uint32_t f = flag_col[r];
+                if (f & 2) {
+                    const uint32_t h = hash_col[r];
+                    const uint32_t b = h >> ALIVE_BUCKET_SHIFT;
+                    const uint32_t pos = base[b] + atomicAdd(&hist[b], 1u);
+                    entries[pos] = ((unsigned long long)h << 32) | ((unsigned long long)(r + 1) << 1) | (f & 1u);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Apply the bucketed stamps in hash order: at any moment the whole grid works inside one or two buckets, i.e.
+// inside 64-128 MiB of the table, which the 126 MB L2 absorbs; DRAM sees each touched sector about once.
+__global__ void __launch_bounds__(THREADS) bucket_apply_kernel(const unsigned long long *entries, const uint32_t *bucket,
+                                                               unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag,
+                                                               uint64_t seq_base, unsigned long long *alive_count) {
+    const uint32_t total = bucket[2 * ALIVE_BUCKETS];
+    int delta = 0;
+    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < total; i += gridDim.x * THREADS) {
+        const unsigned long long e = entries[i];
+        const uint32_t rel = (uint32_t)e;
+        delta += alive_stamp(table, dirty, epoch_tag, (uint32_t)(e >> 32), seq_base + (rel >> 1), (rel & 1u) != 0);
+    }
+    delta = __reduce_add_sync(0xffffffffu, delta);
+    if ((threadIdx.x & 31) == 0 && delta) atomicAdd(alive_count, (unsigned long long)(long long)delta);
+}
+
+// EXTENSION: HyperLogLog over the resolved alive set (only when an HLL precision was asked for together with -c)
+__global__ void __launch_bounds__(THREADS) alive_hll_kernel(const unsigned long long *table, const uint8_t *dirty,
+                                                            uint32_t npages, uint64_t epoch_tag, uint32_t *hll, int hll_p) {
     for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
         if (!dirty[page]) continue;
         const unsigned long long *pg = table + ((size_t)page << DIRTY_SHIFT);
         for (int i = threadIdx.x; i < PAGE_ENTRIES; i += THREADS) {
             const unsigned long long v = pg[i];
-            if (v & 1ull) {
-                local++;
-                if (hll_p) hll_raise(hll, hll_p, hll_mix((page << DIRTY_SHIFT) + (uint32_t)i));
-            }
+            if ((v & 1ull) && ((v ^ epoch_tag) >> 48) == 0) hll_raise(hll, hll_p, hll_mix((page << DIRTY_SHIFT) + (uint32_t)i));
         }
     }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(alive_count, local);
 }
 
-// mode 0: count non-zero entries; mode 1: append them as (hash, stamp)
+// mode 0: count current-epoch entries; mode 1: append them as (hash, stamp without epoch)
 __global__ void __launch_bounds__(THREADS) alive_export_kernel(const unsigned long long *table, const uint8_t *dirty,
-                                                               uint32_t npages, int mode, unsigned long long *counter,
-                                                               uint32_t *out_hash, unsigned long long *out_stamp,
-                                                               unsigned long long cap) {
+                                                               uint32_t npages, uint64_t epoch_tag, int mode,
+                                                               unsigned long long *counter, uint32_t *out_hash,
+                                                               unsigned long long *out_stamp, unsigned long long cap) {
     const int lane = threadIdx.x & 31;
     for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
         if (!dirty[page]) continue;
         const unsigned long long *pg = table + ((size_t)page << DIRTY_SHIFT);
         for (int i = threadIdx.x; i < PAGE_ENTRIES; i += THREADS) {
             const unsigned long long v = pg[i];
-            const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+            const bool live = v != 0 && ((v ^ epoch_tag) >> 48) == 0;
+            const unsigned m = __ballot_sync(0xffffffffu, live);
             if (!m) continue;
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (mode == 1 && v != 0) {
+            if (mode == 1 && live) {
                 const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
                 if (slot < cap) {
                     out_hash[slot] = (page << DIRTY_SHIFT) + (uint32_t)i;
-                    out_stamp[slot] = v;
+                    out_stamp[slot] = v & 0x0000ffffffffffffull;
                 }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(THREADS) alive_import_kernel(unsigned long long *table, uint8_t *dirty,
+__global__ void __launch_bounds__(THREADS) alive_import_kernel(unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag,
                                                                const uint32_t *hash, const unsigned long long *stamp,
-                                                               int64_t count) {
+                                                               int64_t count, unsigned long long *alive_count) {
+    int delta = 0;
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < count; i += (int64_t)gridDim.x * THREADS) {
-        const uint32_t h = hash[i];
-        atomicMax(table + h, stamp[i]);
-        dirty[h >> DIRTY_SHIFT] = 1;
+        const unsigned long long st = stamp[i];
+        delta += alive_stamp(table, dirty, epoch_tag, hash[i], st >> 1, (st & 1ull) != 0);
     }
-}
-
-__global__ void __launch_bounds__(THREADS) alive_clear_kernel(unsigned long long *table, uint8_t *dirty, uint32_t npages) {
-    for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
-        if (!dirty[page]) continue;  // uniform per CTA
-        ulonglong2 *pg = reinterpret_cast<ulonglong2 *>(table + ((size_t)page << DIRTY_SHIFT));
-        for (int i = threadIdx.x; i < PAGE_ENTRIES / 2; i += THREADS) pg[i] = make_ulonglong2(0ull, 0ull);
-        __syncthreads();
-        if (threadIdx.x == 0) dirty[page] = 0;
-    }
+    delta = __reduce_add_sync(0xffffffffu, delta);
+    if ((threadIdx.x & 31) == 0 && delta) atomicAdd(alive_count, (unsigned long long)(long long)delta);
 }
 
 // state (re)initialisation: sums = 0, minmax = {+inf, -inf, u64 max, 0}, hll = 0, hll floor = 0
