@@ -92,11 +92,6 @@ struct kta_handle {
     uint8_t *d_alive_dirty = nullptr;
     unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export counter, [2..] hll floor + slice minima (u32)
     uint32_t epoch = 1;                      // alive-table epoch (stamps carry it in their top 16 bits)
-    uint32_t *d_hash_col = nullptr;          // bucket pass scratch: per-record hash,
-    uint8_t *d_flag_col = nullptr;           //   per-record keyed/alive flags,
-    unsigned long long *d_entries = nullptr; //   bucketed (hash, stamp) entries,
-    uint32_t *d_bucket = nullptr;            //   [0,B) histogram/offsets, [B,2B) cursors, [2B] total
-    int64_t bucket_cap = 0;                  //   records the scratch can hold
     uint32_t *d_hash_out = nullptr;          // test hook
     uint64_t *d_tb_scratch = nullptr;        // key_tile_base scratch for device batches
     int64_t tb_scratch_tiles = 0;
@@ -192,7 +187,6 @@ static int state_reset_device(kta_handle *h) {
         }
         CU(cudaMemsetAsync(h->d_alive_dirty, 0, (size_t)1 << (32 - DIRTY_SHIFT), h->stream));
         CU(cudaMemsetAsync(h->d_scalar, 0, 16, h->stream));
-        CU(cudaMemsetAsync(h->d_bucket, 0, (2 * ALIVE_BUCKETS + 1) * 4, h->stream));
     }
     return KTA_OK;
 }
@@ -213,7 +207,6 @@ extern "C" int kta_destroy(kta_handle *h) {
     for (auto &c : h->chunks) free_chunk(c);
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
     cudaFree(h->d_alive_dirty); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
-    cudaFree(h->d_hash_col); cudaFree(h->d_flag_col); cudaFree(h->d_entries); cudaFree(h->d_bucket);
     for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -265,7 +258,6 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
         CU(cudaMalloc(&h->d_alive_dirty, (size_t)1 << (32 - DIRTY_SHIFT)));
         CU(cudaMemsetAsync(h->d_alive_table, 0, ((size_t)1 << 32) * 8, h->stream));
         CU(cudaMemsetAsync(h->d_alive_dirty, 0, (size_t)1 << (32 - DIRTY_SHIFT), h->stream));
-        CU(cudaMalloc(&h->d_bucket, (2 * ALIVE_BUCKETS + 1) * 4));
         h->epoch = 0;   // state_reset_device below moves to epoch 1
     }
     h->smem_optin = prop.sharedMemPerBlockOptin;
@@ -335,22 +327,6 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
     prm.alive_count = h->d_scalar;
     prm.epoch_tag = (uint64_t)h->epoch << 48;
     prm.hash_out = h->d_hash_out;
-    // -c: stamps go through the hash-bucket pass unless the batch carries explicit sequence numbers
-    const bool bucketed = exact && !prm.seq && prm.n < ((int64_t)1 << 31);
-    if (bucketed) {
-        if (prm.n > h->bucket_cap) {
-            CU(cudaStreamSynchronize(h->stream));   // earlier passes may still read the old scratch
-            cudaFree(h->d_hash_col); cudaFree(h->d_flag_col); cudaFree(h->d_entries);
-            h->d_hash_col = nullptr; h->d_flag_col = nullptr; h->d_entries = nullptr; h->bucket_cap = 0;
-            CU(cudaMalloc(&h->d_hash_col, (size_t)prm.n * 4));
-            CU(cudaMalloc(&h->d_flag_col, (size_t)prm.n));
-            CU(cudaMalloc(&h->d_entries, (size_t)prm.n * 8));
-            h->bucket_cap = prm.n;
-        }
-        prm.hash_col = h->d_hash_col;
-        prm.flag_col = h->d_flag_col;
-        prm.bucket_hist = h->d_bucket;
-    }
     if (mode != MODE_COUNTERS) {
         if (!prm.key_tile_base) return fail(KTA_ERR_INVALID, "internal: key_tile_base missing");
         if (!prm.key_bytes && key_readable > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL but keys are required");
@@ -377,17 +353,6 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
     else launch_variant<false>(variant, grid, threads, sm, h->stream, prm);
     CU(cudaGetLastError());
     h->launches++;
-    if (bucketed) {
-        bucket_offsets_kernel<<<1, ALIVE_BUCKETS, 0, h->stream>>>(h->d_bucket);
-        const int64_t nchunks = (prm.n + SCATTER_CHUNK - 1) / SCATTER_CHUNK;
-        bucket_scatter_kernel<<<(int)std::min<int64_t>(nchunks, (int64_t)h->sm_count * 4), SCATTER_THREADS, 0, h->stream>>>(
-            h->d_hash_col, h->d_flag_col, prm.n, h->d_bucket, h->d_entries);
-        bucket_apply_kernel<<<h->sm_count * 8, THREADS, 0, h->stream>>>(h->d_entries, h->d_bucket, h->d_alive_table,
-                                                                       h->d_alive_dirty, prm.epoch_tag, prm.seq_base,
-                                                                       h->d_scalar);
-        CU(cudaGetLastError());
-        h->launches += 3;
-    }
     if (h->timing) CU(cudaEventRecord(e1, h->stream));
     h->records += (uint64_t)prm.n;
     h->finalized = false;

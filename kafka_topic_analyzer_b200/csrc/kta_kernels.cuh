@@ -32,8 +32,6 @@ constexpr int WARP_SMEM = 128 + 2 * KEYBUF;  // per warp: 2 mbarriers (+ scratch
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
-constexpr int ALIVE_BUCKETS = 512;        // alive-table application order: 2^32 / 512 hash values = 64 MiB of table per bucket
-constexpr int ALIVE_BUCKET_SHIFT = 23;
 constexpr int FOLD_TILES = 4;             // every warp checks the CTA's 16-bit-split sums every 4 of its tiles
 
 // shared-memory counter rows (each row = P u32 words):
@@ -46,9 +44,8 @@ enum ScanMode { MODE_COUNTERS = 0, MODE_HLL = 1, MODE_EXACT = 2 };
 
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
-// counter rows, then the CTA scratch: one 128-byte line (word 0: the CTA's cached copy of the HLL floor) followed by
-// the per-CTA hash-bucket histogram of MODE_EXACT
-constexpr int CTA_SCRATCH = 128 + ALIVE_BUCKETS * 4;
+// counter rows, then the CTA scratch: one 128-byte line (word 0: the CTA's cached copy of the HLL floor)
+constexpr int CTA_SCRATCH = 128;
 __host__ __device__ inline size_t smem_counter_bytes(int P) { return (((size_t)P * SMEM_ROWS * 4 + 127) & ~(size_t)127) + CTA_SCRATCH; }
 
 struct ScanParams {
@@ -74,9 +71,6 @@ struct ScanParams {
     uint8_t *alive_dirty;            // [2^32 >> DIRTY_SHIFT]
     unsigned long long *alive_count; // running number of alive entries of the current epoch (two's-complement deltas)
     uint64_t epoch_tag;              // current epoch << 48
-    uint32_t *hash_col;              // MODE_EXACT, bucketed: per-record hash out [n] (NULL = stamp the table directly)
-    uint8_t *flag_col;               //   per-record flags out [n]: bit 1 keyed, bit 0 alive
-    uint32_t *bucket_hist;           //   [ALIVE_BUCKETS] records per hash bucket (global, accumulated)
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
 };
 
@@ -350,6 +344,11 @@ struct Counters {
 __device__ __forceinline__ int alive_stamp(unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag, uint32_t hash,
                                            uint64_t seq_plus_1, bool alive) {
     const unsigned long long stamp = epoch_tag | (seq_plus_1 << 1) | (alive ? 1ull : 0ull);
+    // Entries only grow, so a plain (possibly stale, never too large) read is a safe filter: a record that is not
+    // the newest for its hash stops here with one 32-byte sector read instead of an atomic read-modify-write.
+    // The scan walks each batch from its newest tile to its oldest, so for a key written k times about (k-1)/k
+    // of its records take this exit.
+    if (__ldcg(table + hash) >= stamp) return 0;
     const unsigned long long old = atomicMax(table + hash, stamp);
     uint8_t *d = dirty + (hash >> DIRTY_SHIFT);
     if (__ldca(d) == 0) *d = 1;
@@ -435,7 +434,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
     const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : CTA_SCRATCH;
     volatile uint32_t *s_floor = reinterpret_cast<volatile uint32_t *>(smem_raw + cta_bytes - CTA_SCRATCH);
-    uint32_t *s_bucket = const_cast<uint32_t *>(s_floor) + 32;   // [ALIVE_BUCKETS], MODE_EXACT only
     unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * (HASH ? WARP_SMEM : 128);
     const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
@@ -446,8 +444,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
     }
     if (MODE == MODE_HLL && tid == 0) *s_floor = ld_cg_u32(prm.hll_floor);
-    if (MODE == MODE_EXACT)
-        for (int i = tid; i < ALIVE_BUCKETS; i += blockDim.x) s_bucket[i] = 0;
     if (HASH && lane == 0) {
         mbar_init(mbar, 1);
         mbar_init(mbar + 8, 1);
@@ -478,9 +474,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     uint32_t nxt_info = 0;
 
+    // MODE_EXACT walks the batch from its newest tile to its oldest (see alive_stamp); the other modes ascend
+    auto phys = [&](int64_t t) { return MODE == MODE_EXACT ? prm.ntiles - 1 - t : t; };
     const int64_t gstride = (int64_t)gridDim.x * nwarps;
     int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
-    if (HASH && lane == 0 && tile < prm.ntiles) nxt_info = issue(tile, 0);
+    if (HASH && lane == 0 && tile < prm.ntiles) nxt_info = issue(phys(tile), 0);
 
     // the body of one tile; FULL = every record of the tile exists (no tail predicates)
     auto body = [&](auto full_tag, int64_t tile, int buf, uint32_t info, bool has_next) {
@@ -639,28 +637,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
                 // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
                 // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
-                if (prm.hash_col) {
-                    // bucketed: hand (hash, flags) to the bucket pass, which applies the stamps to the table in
-                    // hash order so that each 64 MiB slice of the 32 GiB table is touched while it sits in L2
-                    const uint32_t sb = smem_u32(s_bucket);
 #pragma unroll
-                    for (int k = 0; k < ROWS; k++) {
-                        if (valid[k]) {
-                            const int64_t r = rbase + 32 * k;
-                            prm.hash_col[r] = h[k];
-                            prm.flag_col[r] = (uint8_t)((kl[k] >= 0 ? 2 : 0) | (vl[k] >= 0 ? 1 : 0));
-                            if (kl[k] >= 0) red_shared_add(sb + 4u * (h[k] >> ALIVE_BUCKET_SHIFT), 1u);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < ROWS; k++) {
-                        if (valid[k] && kl[k] >= 0) {
-                            const int64_t r = rbase + 32 * k;
-                            const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
-                            alive_delta += alive_stamp(prm.alive_table, prm.alive_dirty, prm.epoch_tag, h[k], seq + 1ull,
-                                                       vl[k] >= 0);
-                        }
+                for (int k = 0; k < ROWS; k++) {
+                    if (valid[k] && kl[k] >= 0) {
+                        const int64_t r = rbase + 32 * k;
+                        const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
+                        alive_delta += alive_stamp(prm.alive_table, prm.alive_dirty, prm.epoch_tag, h[k], seq + 1ull,
+                                                   vl[k] >= 0);
                     }
                 }
             }
@@ -691,9 +674,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             info = __shfl_sync(full, nxt_info, 0);   // also: every lane is done with stage buf^1 before it is refilled
         }
         const bool has_next = tile + gstride < prm.ntiles;
-        if (HASH && has_next && lane == 0) nxt_info = issue(tile + gstride, buf ^ 1);
-        if ((tile + 1) * TILE <= prm.n) body(std::true_type{}, tile, buf, info, has_next);
-        else body(std::false_type{}, tile, buf, info, has_next);
+        if (HASH && has_next && lane == 0) nxt_info = issue(phys(tile + gstride), buf ^ 1);
+        const int64_t pt = phys(tile);
+        if ((pt + 1) * TILE <= prm.n) body(std::true_type{}, pt, buf, info, has_next);
+        else body(std::false_type{}, pt, buf, info, has_next);
         if ((it & (FOLD_TILES - 1)) == FOLD_TILES - 1) {
             if (SMEM) C.fold_sums(lane, 1u << 30);
             try_uni = try_uni || (it & 15) == 15;   // re-probe now and then
@@ -710,13 +694,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     // ---- flush CTA-private state ----
     __syncthreads();
     if (MODE == MODE_EXACT) {
-        if (prm.hash_col) {
-            for (int i = tid; i < ALIVE_BUCKETS; i += blockDim.x)
-                if (s_bucket[i]) atomicAdd(prm.bucket_hist + i, s_bucket[i]);
-        } else {
-            alive_delta = __reduce_add_sync(full, alive_delta);
-            if (lane == 0 && alive_delta) atomicAdd(prm.alive_count, (unsigned long long)(long long)alive_delta);
-        }
+        alive_delta = __reduce_add_sync(full, alive_delta);
+        if (lane == 0 && alive_delta) atomicAdd(prm.alive_count, (unsigned long long)(long long)alive_delta);
     }
     if (SMEM) {
         // bucket rows → global [which][p][bucket]; row 32 → knull; row 65 (tombstones) is derived, not stored
@@ -824,91 +803,10 @@ __global__ void __launch_bounds__(1024) tile_base_scan_kernel(uint64_t *tile_bas
 }
 
 // ------------------------------------------------------------------------------------------------
-// alive-key table: bucket pass (scan → offsets → scatter → apply), HLL over the alive set, export / import / clear
+// alive-key table: HLL over the alive set, export / import
 // ------------------------------------------------------------------------------------------------
 constexpr int PAGE_ENTRIES = 1 << DIRTY_SHIFT;
 constexpr int THREADS = 256;  // block size of the table / utility kernels below
-constexpr int SCATTER_THREADS = 512, SCATTER_CHUNK = 8192;
-
-// bucket[0..B): counts in, exclusive offsets out; bucket[B..2B): cursors (= offsets); bucket[2B]: total
-__global__ void __launch_bounds__(ALIVE_BUCKETS) bucket_offsets_kernel(uint32_t *bucket) {
-    __shared__ uint32_t wsum[ALIVE_BUCKETS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t v = bucket[tid];
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int w = 0; w < warp; w++) base += wsum[w];
-    const uint32_t excl = base + inc - v;
-    bucket[tid] = 0;                         // ready for the next batch's histogram
-    bucket[ALIVE_BUCKETS + tid] = excl;
-    if (tid == ALIVE_BUCKETS - 1) bucket[2 * ALIVE_BUCKETS] = excl + v;
-}
-
-// Move every keyed record's (hash, batch-relative stamp) into its hash bucket.  A CTA handles 8192 records at a
-// time: shared-memory histogram, ONE global reservation per bucket, then the scatter with shared-memory cursors.
-// entry = hash << 32 | (index_in_batch + 1) << 1 | alive
-__global__ void __launch_bounds__(SCATTER_THREADS) bucket_scatter_kernel(const uint32_t *hash_col, const uint8_t *flag_col,
-                                                                         int64_t n, uint32_t *bucket,
-                                                                         unsigned long long *entries) {
-    __shared__ uint32_t hist[ALIVE_BUCKETS], base[ALIVE_BUCKETS];
-    const int tid = threadIdx.x;
-    const int64_t nchunks = (n + SCATTER_CHUNK - 1) / SCATTER_CHUNK;
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        for (int i = tid; i < ALIVE_BUCKETS; i += SCATTER_THREADS) hist[i] = 0;
-        __syncthreads();
-        const int64_t r0 = chunk * SCATTER_CHUNK;
-#pragma unroll 4
-        for (int j = 0; j < SCATTER_CHUNK / SCATTER_THREADS; j++) {
-            const int64_t r = r0 + j * SCATTER_THREADS + tid;
-            if (r < n && (flag_col[r] & 2)) atomicAdd(&hist[hash_col[r] >> ALIVE_BUCKET_SHIFT], 1u);
-        }
-        __syncthreads();
-        for (int i = tid; i < ALIVE_BUCKETS; i += SCATTER_THREADS) {
-            const uint32_t c = hist[i];
-            base[i] = c ? atomicAdd(&bucket[ALIVE_BUCKETS + i], c) : 0u;
-            hist[i] = 0;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < SCATTER_CHUNK / SCATTER_THREADS; j++) {
-            const int64_t r = r0 + j * SCATTER_THREADS + tid;
-            if (r < n) {
-                const uint32_t f = flag_col[r];
-                if (f & 2) {
-                    const uint32_t h = hash_col[r];
-                    const uint32_t b = h >> ALIVE_BUCKET_SHIFT;
-                    const uint32_t pos = base[b] + atomicAdd(&hist[b], 1u);
-                    entries[pos] = ((unsigned long long)h << 32) | ((unsigned long long)(r + 1) << 1) | (f & 1u);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Apply the bucketed stamps in hash order: at any moment the whole grid works inside one or two buckets, i.e.
-// inside 64-128 MiB of the table, which the 126 MB L2 absorbs; DRAM sees each touched sector about once.
-__global__ void __launch_bounds__(THREADS) bucket_apply_kernel(const unsigned long long *entries, const uint32_t *bucket,
-                                                               unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag,
-                                                               uint64_t seq_base, unsigned long long *alive_count) {
-    const uint32_t total = bucket[2 * ALIVE_BUCKETS];
-    int delta = 0;
-    for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < total; i += gridDim.x * THREADS) {
-        const unsigned long long e = entries[i];
-        const uint32_t rel = (uint32_t)e;
-        delta += alive_stamp(table, dirty, epoch_tag, (uint32_t)(e >> 32), seq_base + (rel >> 1), (rel & 1u) != 0);
-    }
-    delta = __reduce_add_sync(0xffffffffu, delta);
-    if ((threadIdx.x & 31) == 0 && delta) atomicAdd(alive_count, (unsigned long long)(long long)delta);
-}
-
 // EXTENSION: HyperLogLog over the resolved alive set (only when an HLL precision was asked for together with -c)
 __global__ void __launch_bounds__(THREADS) alive_hll_kernel(const unsigned long long *table, const uint8_t *dirty,
                                                             uint32_t npages, uint64_t epoch_tag, uint32_t *hll, int hll_p) {
@@ -954,7 +852,8 @@ __global__ void __launch_bounds__(THREADS) alive_import_kernel(unsigned long lon
                                                                const uint32_t *hash, const unsigned long long *stamp,
                                                                int64_t count, unsigned long long *alive_count) {
     int delta = 0;
-    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < count; i += (int64_t)gridDim.x * THREADS) {
+    const int64_t stride = (int64_t)gridDim.x * THREADS;
+    for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < count; i += stride) {
         const unsigned long long st = stamp[i];
         delta += alive_stamp(table, dirty, epoch_tag, hash[i], st >> 1, (st & 1ull) != 0);
     }
