@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--run-len", type=int, default=1)
     ap.add_argument("--distinct-keys", type=int, default=10_000_000)
     ap.add_argument("--hll", type=int, default=14)
+    ap.add_argument("--key-mode", type=int, default=0, help="0 = 16-byte binary keys, 1 = ASCII key-<id>, 2 = variable 0..40 B")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -49,9 +50,9 @@ def parse():
 
 
 def workload_name(a, world):
-    return ("C1 %d partitions, %.0e msgs/GPU x %d GPU, %d B mean value, 16 B keys, mode=%s "
+    return ("C1 %d partitions, %.0e msgs/GPU x %d GPU, %d B mean value, %s keys, mode=%s "
             "(counters+histograms%s), run_len=%d; inputs %.1f GB/GPU > L2, no flush needed" %
-            (a.partitions, a.n, world, a.value_mean, a.mode,
+            (a.partitions, a.n, world, a.value_mean, {0: "16 B", 1: "ASCII key-<id>", 2: "variable 0..40 B"}[a.key_mode], a.mode,
              {"fused": "+FNV32+HLL p%d" % a.hll, "counters": "", "alive": "+FNV32+exact alive-key table"}[a.mode],
              a.run_len, a.n * 36 / 1e9))
 
@@ -204,7 +205,8 @@ def run_ours(a):
     # ---- the rank's shard of the topic, generated in HBM ----
     P = a.partitions
     n_total = a.n * world
-    spec = synth.make_spec(n_total, P, run_len=a.run_len, distinct_keys=a.distinct_keys * world, value_mean=a.value_mean)
+    spec = synth.make_spec(n_total, P, run_len=a.run_len, distinct_keys=a.distinct_keys * world, value_mean=a.value_mean,
+                           key_mode=a.key_mode)
     exact = a.mode == "alive"
     topic = synth.DeviceTopic(spec, rank=rank, world=world, device=local, with_seq=(exact and world > 1))
     n = topic.n

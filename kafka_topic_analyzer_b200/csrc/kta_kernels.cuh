@@ -27,7 +27,7 @@ constexpr int TILE = KTA_KEY_TILE;        // records per warp tile (128)
 constexpr int ROWS = TILE / 32;           // records per lane per tile
 constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
 constexpr int KEYBUF_COPY = TILE * 18;    // max staged key bytes per tile (18 B/record average)
-constexpr int KEYBUF = KEYBUF_COPY + 64;  // + slack for the (harmless) over-read of the last words
+constexpr int KEYBUF = KEYBUF_COPY + 32;  // + slack for the (harmless, <= 23 byte) over-read of the last words
 constexpr int WARP_SMEM = 128 + 2 * KEYBUF;  // per warp: 2 mbarriers (+ scratch) and a double-buffered key stage
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
@@ -77,7 +77,13 @@ struct ScanParams {
 // ------------------------------------------------------------------------------------------------
 // small PTX wrappers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-window address of a generic pointer; volatile so that it is computed once and kept, not rematerialised
+// (S2UR + ULEA) in front of every shared-memory reduction
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+    return a;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -109,6 +115,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
 // shared-memory reductions on 32-bit shared-window addresses (no generic→shared conversion in the loop)
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// [addr] += v unless v == 0, as ONE predicated instruction (no branch, no reconvergence bookkeeping)
+__device__ __forceinline__ void red_shared_add_nz(uint32_t addr, uint32_t v) {
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], %1; }" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -145,9 +155,6 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {  // L2-cohere
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ void red_global_max(uint32_t *p, uint32_t v) {  // fire-and-forget, never stalls the warp
     asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -292,28 +299,41 @@ struct Counters {
         if (SMEM) {
             const uint32_t a = sbase + 4u * (uint32_t)((ROW_KSUM + 2 * which) * P + p);
             red_shared_add(a, v & 0xffffu);
-            if (v >> 16) red_shared_add(a + 4u * (uint32_t)P, v >> 16);
+            red_shared_add_nz(a + 4u * (uint32_t)P, v >> 16);
         } else if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], (unsigned long long)v);
     }
-    // one record, partition already validated; MessageMetrics::handle_message's increments (metric.rs:215-244)
-    __device__ __forceinline__ void record(int p, int kl, int vl) const {
+    // one record, partition already validated; MessageMetrics::handle_message's increments (metric.rs:215-244).
+    // buckets(): the two counting increments.  Lanes that hit the same counter are merged by the hardware
+    // (ATOMS.POPC.INC), so rows of one partition cost no more than scattered rows.
+    __device__ __forceinline__ void buckets(int p, int kl, int vl) const {
         const int kb = (int)bfind_u32((uint32_t)kl) + 1;   // 32 = null key (metric.rs:228), else its size bucket (:220)
         const int vb = (int)bfind_u32((uint32_t)vl) + 1;   // 32 = tombstone (:243), else its size bucket (:239)
         if (SMEM) {
             const uint32_t P4 = 4u * (uint32_t)P, pa = sbase + 4u * (uint32_t)p;
             red_shared_add(pa + (uint32_t)kb * P4, 1u);
             red_shared_add(pa + (uint32_t)(ROW_V + vb) * P4, 1u);
-            const uint32_t ks = (uint32_t)max(kl, 0), vs = (uint32_t)max(vl, 0);
-            red_shared_add(pa + ROW_KSUM * P4, ks & 0xffffu);                 // metric.rs:223
-            if (ks >> 16) red_shared_add(pa + (ROW_KSUM + 1) * P4, ks >> 16);
-            red_shared_add(pa + ROW_VSUM * P4, vs & 0xffffu);                 // metric.rs:237
-            if (vs >> 16) red_shared_add(pa + (ROW_VSUM + 1) * P4, vs >> 16);
         } else {
             row_add(kb, p, 1u);
             row_add(ROW_V + vb, p, 1u);
+        }
+    }
+    // sums(): the two byte sums (metric.rs:223, :237)
+    __device__ __forceinline__ void sums(int p, int kl, int vl) const {
+        if (SMEM) {
+            const uint32_t P4 = 4u * (uint32_t)P, pa = sbase + 4u * (uint32_t)p;
+            const uint32_t ks = (uint32_t)max(kl, 0), vs = (uint32_t)max(vl, 0);
+            red_shared_add(pa + ROW_KSUM * P4, ks & 0xffffu);
+            red_shared_add_nz(pa + (ROW_KSUM + 1) * P4, ks >> 16);
+            red_shared_add(pa + ROW_VSUM * P4, vs & 0xffffu);
+            red_shared_add_nz(pa + (ROW_VSUM + 1) * P4, vs >> 16);
+        } else {
             sum_add(0, p, (uint32_t)max(kl, 0));
             sum_add(1, p, (uint32_t)max(vl, 0));
         }
+    }
+    __device__ __forceinline__ void record(int p, int kl, int vl) const {
+        buckets(p, kl, vl);
+        sums(p, kl, vl);
     }
     // One warp drains split sums that reached `threshold` into the global u64 sums; safe against concurrent
     // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp checks every FOLD_TILES of
@@ -355,36 +375,6 @@ __device__ __forceinline__ int alive_stamp(unsigned long long *table, uint8_t *d
     if (stamp <= old) return 0;   // a later record already spoke for this hash
     const int was = ((old ^ epoch_tag) >> 48) == 0 ? (int)(old & 1ull) : 0;
     return (int)alive - was;
-}
-
-// A row of 32 records that all belong to one partition (the usual shape of a Kafka fetch): aggregate in the
-// warp, one reduction per distinct bucket and per sum instead of 32 same-address ones.
-template <bool SMEM>
-__device__ __noinline__ void count_row_uniform(const Counters<SMEM> C, int p0, int kl, int vl, int lane) {
-    const unsigned full = 0xffffffffu;
-    const int kb = (int)bfind_u32((uint32_t)kl) + 1, vb = (int)bfind_u32((uint32_t)vl) + 1;
-    unsigned rem = full;
-    while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int b0 = __shfl_sync(full, kb, leader);
-        const unsigned m = __ballot_sync(full, kb == b0);
-        if (lane == leader) C.row_add(b0, p0, __popc(m));
-        rem &= ~m;
-    }
-    rem = full;
-    while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int b0 = __shfl_sync(full, vb, leader);
-        const unsigned m = __ballot_sync(full, vb == b0);
-        if (lane == leader) C.row_add(ROW_V + b0, p0, __popc(m));
-        rem &= ~m;
-    }
-    const uint32_t ks = __reduce_add_sync(full, (uint32_t)max(kl, 0));   // each < 2^26: no overflow
-    const uint32_t vs = __reduce_add_sync(full, (uint32_t)max(vl, 0));
-    if (lane == 0) {
-        C.sum_add(0, p0, ks);
-        C.sum_add(1, p0, vs);
-    }
 }
 
 // rare path: a tile with a key of >= 1 MiB — 64-bit offsets, keys read straight from global memory.
@@ -506,19 +496,31 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
 #pragma unroll
         for (int k = 0; k < ROWS; k++) inrange = inrange && (unsigned)p[k] < (unsigned)P;
         if (FULL && __all_sync(full, inrange)) {
-            bool any_uni = false;
+            if (try_uni) {
+                // run-structured input (a Kafka fetch delivers long runs of one partition): the byte sums of a row that
+                // lies inside one run are reduced in the warp (2 REDUX) and added once, instead of 32 same-address adds
+                bool any_uni = false;
 #pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                bool uni = false;
-                if (try_uni) {
+                for (int k = 0; k < ROWS; k++) {
+                    C.buckets(p[k], kl[k], vl[k]);
                     const int p0 = __shfl_sync(full, p[k], 0);
-                    uni = __all_sync(full, p[k] == p0 && (kl[k] | vl[k]) < (1 << 26));
-                    if (uni) count_row_uniform<SMEM>(C, p0, kl[k], vl[k], lane);
-                    any_uni = any_uni || uni;
+                    if (__all_sync(full, p[k] == p0 && (kl[k] | vl[k]) < (1 << 26))) {
+                        const uint32_t ks = __reduce_add_sync(full, (uint32_t)max(kl[k], 0));   // each < 2^26: no overflow
+                        const uint32_t vs = __reduce_add_sync(full, (uint32_t)max(vl[k], 0));
+                        if (lane == 0) {
+                            C.sum_add(0, p0, ks);
+                            C.sum_add(1, p0, vs);
+                        }
+                        any_uni = true;
+                    } else {
+                        C.sums(p[k], kl[k], vl[k]);
+                    }
                 }
-                if (!uni) C.record(p[k], kl[k], vl[k]);
+                try_uni = any_uni;
+            } else {
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) C.record(p[k], kl[k], vl[k]);
             }
-            try_uni = any_uni;
         } else {
             // tail tile, or a record with a partition outside [0, P): per-record checks
 #pragma unroll
@@ -568,8 +570,28 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 }
             } else {
                 small = __all_sync(full, small);
-                uint32_t c32 = 0;
-                if (small) {
+                static_assert(ROWS == 4, "the packed scan below handles exactly four rows");
+                uint32_t mxl = 0;
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) mxl = max(mxl, (uint32_t)max(kl[k], 0));
+                if (__all_sync(full, mxl < 2048u)) {
+                    // short keys (every row sums to < 2^16): scan two rows per 32-bit word, 10 shuffles instead of 20
+                    const uint32_t v0 = (uint32_t)max(kl[0], 0), v1 = (uint32_t)max(kl[1], 0);
+                    const uint32_t v2 = (uint32_t)max(kl[2], 0), v3 = (uint32_t)max(kl[3], 0);
+                    uint32_t a = v0 | (v1 << 16), b = v2 | (v3 << 16);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t ta = __shfl_up_sync(full, a, d), tb = __shfl_up_sync(full, b, d);
+                        if (lane >= d) { a += ta; b += tb; }
+                    }
+                    const uint32_t ea = __shfl_sync(full, a, 31), eb = __shfl_sync(full, b, 31);
+                    const uint32_t t0 = ea & 0xffffu, t1 = ea >> 16, t2 = eb & 0xffffu;
+                    off[0] = (a & 0xffffu) - v0;
+                    off[1] = t0 + (a >> 16) - v1;
+                    off[2] = t0 + t1 + (b & 0xffffu) - v2;
+                    off[3] = t0 + t1 + t2 + (b >> 16) - v3;
+                } else if (small) {
+                    uint32_t c32 = 0;
 #pragma unroll
                     for (int k = 0; k < ROWS; k++) {
                         const uint32_t v = (uint32_t)max(kl[k], 0);
