@@ -107,6 +107,8 @@ int main(int argc, char **argv) {
     printf("Subscribing to %s\n", topic.c_str());          // src/kafka.rs:88
     printf("Starting message consumption...\n");            // src/kafka.rs:91
     const int64_t CH = 1 << 20;
+    double feed_s = 0;   // time spent inside the library's entry points only (not in the synthetic generator)
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     if (feed == "device") {
         const int64_t ntiles = (n + KTA_KEY_TILE - 1) / KTA_KEY_TILE;
         int32_t *dp, *dk, *dv; int64_t *dt; uint8_t *dkb; uint64_t *dtb;
@@ -117,7 +119,10 @@ int main(int argc, char **argv) {
         if (kta_synth_fill_device(&spec, -1, 0, 1, 0, n, dp, nullptr, dt, dk, dv, nullptr, dkb, cap, dtb, &kbl)) { fprintf(stderr, "synthetic fill failed\n"); return 1; }
         kta_batch b{};
         b.n = n; b.partition = dp; b.ts_ms = dt; b.key_len = dk; b.value_len = dv; b.key_bytes = dkb; b.key_bytes_len = kbl; b.key_tile_base = dtb;
+        const double t0 = now();
         KTA(kta_scan_batch_device(h, &b));
+        KTA(kta_sync(h));
+        feed_s += now() - t0;
     } else {
         std::vector<int32_t> part(CH), kl(CH), vl(CH);
         std::vector<int64_t> off(CH), ts(CH);
@@ -127,6 +132,7 @@ int main(int argc, char **argv) {
             int64_t kbl = 0;
             if (kta_synth_fill_host(&spec, 0, 1, s0, c, part.data(), off.data(), ts.data(), kl.data(), vl.data(), nullptr,
                                     kb.data(), (int64_t)kb.size(), &kbl)) { fprintf(stderr, "synthetic fill failed\n"); return 1; }
+            const double t0 = now();
             if (feed == "push") {
                 // the reference's shape: one handle_message per polled message (src/kafka.rs:107-109)
                 int64_t ko = 0;
@@ -140,9 +146,16 @@ int main(int argc, char **argv) {
                 b.key_len = kl.data(); b.value_len = vl.data(); b.key_bytes = kb.data(); b.key_bytes_len = kbl;
                 KTA(kta_push_batch_host(h, &b));
             }
+            feed_s += now() - t0;
         }
     }
-    KTA(kta_finalize(h));
+    {
+        const double t0 = now();
+        KTA(kta_finalize(h));
+        feed_s += now() - t0;
+    }
+    fprintf(stderr, "[kta] feed=%s: %lld records through the handlers in %.4f s = %.3e msg/s (generator excluded)\n", feed.c_str(),
+            (long long)n, feed_s, feed_s > 0 ? (double)n / feed_s : 0.0);
     const uint64_t duration_secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
 
     kta_report::Summary s{};

@@ -920,8 +920,13 @@ extern "C" int kta_merge_export_device(kta_handle *h, int32_t rank, int32_t worl
                                                            world, reinterpret_cast<unsigned long long *>(dev_buf));
     h->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));  // the collective runs on the caller's stream
-    return collect_timing(h);
+    // With its own stream the handle must finish before the caller's collective may read the buffer.  On an
+    // adopted stream (kta_set_stream) the caller's collective is ordered behind this kernel by the stream itself.
+    if (h->own_stream) {
+        CU(cudaStreamSynchronize(h->stream));
+        return collect_timing(h);
+    }
+    return KTA_OK;
 }
 
 extern "C" int kta_merge_import_device(kta_handle *h, int32_t world, const uint64_t *dev_buf) {
@@ -934,7 +939,7 @@ extern "C" int kta_merge_import_device(kta_handle *h, int32_t world, const uint6
     h->launches++;
     CU(cudaGetLastError());
     h->finalized = false;
-    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) CU(cudaStreamSynchronize(h->stream));
     return KTA_OK;
 }
 

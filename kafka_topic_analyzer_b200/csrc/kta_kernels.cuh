@@ -550,22 +550,28 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
             uint32_t off[ROWS];
             uint32_t h[ROWS];
-            // all keys null or exactly 16 bytes?  (kl ^ 16) & ~(kl >> 31) is 0 for both
-            uint32_t odd = 0;
+            // do all keys of this tile that are not null have ONE length L?  (kl ^ L) & ~(kl >> 31) is 0 for null and L
+            int lmax = kl[0];
             bool small = true;
 #pragma unroll
+            for (int k = 1; k < ROWS; k++) lmax = max(lmax, kl[k]);
+            const int L = __reduce_max_sync(full, lmax);   // -1 when every key is null
+            uint32_t odd = 0;
+#pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                odd |= ((uint32_t)kl[k] ^ 16u) & ~(uint32_t)(kl[k] >> 31);
+                odd |= ((uint32_t)kl[k] ^ (uint32_t)L) & ~(uint32_t)(kl[k] >> 31);
                 small = small && kl[k] < (1 << 20);
             }
-            const bool fix16 = __all_sync(full, odd == 0);
-            if (fix16) {
-                // offsets from ballots, no shuffle scan
+            const bool fixL = __all_sync(full, odd == 0) && L < (1 << 16);
+            const bool fix16 = fixL && L == 16;
+            if (fixL) {
+                // fixed-width keys (the common case: ids, hashes, UUIDs): offsets from ballots, no shuffle scan
                 uint32_t before = 0;
+                const uint32_t Lu = (uint32_t)max(L, 0);
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
                     const unsigned m = __ballot_sync(full, kl[k] >= 0);
-                    off[k] = 16u * (before + __popc(m & lt_mask));
+                    off[k] = Lu * (before + __popc(m & lt_mask));
                     before += __popc(m);
                 }
             } else {
@@ -637,7 +643,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
 #pragma unroll
                     for (int k = 0; k < ROWS; k++) h[k] = kl[k] >= 0 ? fnv_smem(kb, a0 + off[k], kl[k]) : 0u;
                 }
-            } else if (fix16 || small) {
+            } else if (fixL || small) {
                 const uint64_t g0 = prm.key_tile_base[tile];
 #pragma unroll
                 for (int k = 0; k < ROWS; k++)

@@ -21,9 +21,12 @@ def allreduce_merge(engine: KtaEngine, group=None) -> None:
     dev = torch.device("cuda", torch.cuda.current_device())
     words = engine.merge_words(world)
     buf = torch.empty(words, dtype=torch.int64, device=dev)   # u64 payload; SUM is bit-identical on i64
+    # When the engine runs on torch's current stream (engine.set_stream) the three steps are ordered by that
+    # stream alone — export kernel, NCCL all-reduce, import kernel — with no host synchronisation in between.
     engine.merge_export(rank, world, buf)
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    torch.cuda.current_stream().synchronize()
+    if not engine.shares_caller_stream:
+        torch.cuda.current_stream().synchronize()
     engine.merge_import(world, buf)
     if engine.count_alive_keys:
         n_local = engine.alive_export_count()

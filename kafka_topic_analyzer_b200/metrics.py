@@ -72,6 +72,7 @@ class KtaEngine:
         self.num_partitions = num_partitions
         self.count_alive_keys = bool(count_alive_keys)
         self.hll_precision = hll_precision
+        self.shares_caller_stream = False   # True after set_stream(): work is ordered by the caller's stream
         self.message_metrics = MessageMetrics(self)
         self.log_compaction_metrics = LogCompactionInMemoryMetrics(self) if count_alive_keys else None
 
@@ -211,6 +212,7 @@ class KtaEngine:
     def set_stream(self, cuda_stream: int) -> None:
         """Run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
         check(lib().kta_set_stream(self._h, cuda_stream))
+        self.shares_caller_stream = True
 
     def merge_words(self, world: int) -> int:
         return lib().kta_merge_words(self._h, world)

@@ -121,6 +121,24 @@ def test_random_ragged_batches(seed):
         assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10))
 
 
+@pytest.mark.parametrize("L", [1, 9, 16, 17, 40])
+def test_fixed_width_keys(L):
+    """Fixed-width keys of any length take the ballot-offset path (16-byte aligned ones the LDS.128 path)."""
+    from kafka_topic_analyzer_b200.synth import HostTopic, tile_base_from_key_len
+    rng = np.random.default_rng(L)
+    n = 20_000
+    kl = np.where(rng.random(n) < 0.03, -1, L).astype(np.int32)
+    pool = rng.integers(0, 256, size=(500, L), dtype=np.uint8)
+    kb = pool[rng.integers(0, 500, size=int((kl >= 0).sum()))].reshape(-1)
+    t = HostTopic(rng.integers(0, 5, size=n).astype(np.int32), np.zeros(n, dtype=np.int64),
+                  (1_600_000_000_000 + np.arange(n)).astype(np.int64), kl, rng.integers(-1, 300, size=n).astype(np.int32),
+                  np.arange(n, dtype=np.uint64), kb, tile_base_from_key_len(kl))
+    o = oracle_for(t, count_alive_keys=True, now=NOW)
+    with KtaEngine(5, count_alive_keys=True, hll_precision=9, now=NOW) as e:
+        scan_device(e, t)
+        assert_parity(e, o, 5, check_alive=True, hll_regs=o.hll_alive_regs(9))
+
+
 def test_hash_capture_matches_oracle_per_record():
     """Every per-record hash computed inside the fused kernel (bulk-copy staged path, all alignments)."""
     import torch
