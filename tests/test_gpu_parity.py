@@ -191,6 +191,28 @@ def test_edge_cases():
         assert e.message_metrics.overall_count() == 0 and e.alive_keys() == 0
 
 
+def test_reset_forgets_the_alive_table_in_o1():
+    """kta_reset starts a new epoch instead of wiping 32 GiB: stamps of the previous topic must not leak."""
+    sa = synth.make_spec(8 * 4000, 8, distinct_keys=800, tombstone_per_10k=1000, key_mode=1)
+    sb = synth.make_spec(8 * 3000, 8, distinct_keys=800, tombstone_per_10k=6000, key_mode=1, seed=77)   # same key space
+    ta, tb = synth.fill_host(sa), synth.fill_host(sb)
+    with KtaEngine(8, count_alive_keys=True, hll_precision=10, now=NOW) as e:
+        for t in (ta, tb, ta):
+            e.reset()
+            scan_device(e, t)
+            o = oracle_for(t, count_alive_keys=True, now=NOW)
+            assert_parity(e, o, 8, check_alive=True, hll_regs=o.hll_alive_regs(10))
+        # and without a reset the second topic continues the first (seq keeps counting)
+        e.reset()
+        e.push_batch_host(ta.partition, ta.ts_ms, ta.key_len, ta.value_len, ta.key_bytes, ta.key_tile_base, seq_base=0)
+        e.push_batch_host(tb.partition, tb.ts_ms, tb.key_len, tb.value_len, tb.key_bytes, tb.key_tile_base, seq_base=ta.n)
+        e.finalize()
+        o = Oracle(count_alive_keys=True, now=NOW)
+        o.handle_batch(ta.partition, ta.ts_ms, ta.key_len, ta.value_len, ta.key_bytes)
+        o.handle_batch(tb.partition, tb.ts_ms, tb.key_len, tb.value_len, tb.key_bytes)
+        assert_parity(e, o, 8, check_alive=True, hll_regs=o.hll_alive_regs(10))
+
+
 def test_partition_out_of_range_is_an_error():
     with KtaEngine(2, now=NOW) as e:
         e.push(2, 0, 0, b"k", 1)
