@@ -182,6 +182,18 @@ int kta_alive_export_device(kta_handle *h, uint32_t *dev_hash, uint64_t *dev_sta
 int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, const uint64_t *dev_stamp,
                             int64_t count);
 
+/* ---- Kafka log segments: the step before the handlers ----
+ * A segment is the concatenation of RecordBatch v2 (magic 2) batches of ONE partition — what a broker stores in
+ * <topic>-<partition>/NNN.log and returns in a fetch response.  The library decodes it on the GPU into the SoA
+ * columns above (what librdkafka's parser + BorrowedMessage accessors do per message, src/kafka.rs:93,
+ * src/metric.rs:208-209,218,233) and scans it.  Control batches are skipped, LogAppendTime batches use
+ * maxTimestamp, CRCs are not verified (librdkafka default check.crcs=false), compressed batches are rejected. */
+/* raw bytes already in device memory; batch_off[nbatches] = byte offset of every batch header (device memory) */
+int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
+                                const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out);
+/* raw bytes in host memory (e.g. an mmap of a .log file); returns when `bytes` may be reused */
+int kta_push_log_segment_host(kta_handle *h, int32_t partition, const uint8_t *bytes, int64_t len, int64_t *records_out);
+
 /* ---- introspection for benchmarks ---- */
 /* kernels launched by this handle since create/reset, and device time of the scan kernels (ms,
  * CUDA events on the handle's stream; only collected when enabled) */

@@ -3,6 +3,8 @@
 //   -t/--topic TOPIC  -b/--bootstrap-server HOSTS  [--librdkafka k=v,...]  [-c/--count-alive-keys]
 //   --synthetic n=...,partitions=...,value_mean=...,run_len=...,distinct_keys=...,key_mode=...,seed=...,
 //               tombstone_per_10k=...,null_key_per_10k=...      (the in-memory topic of BASELINE.json configs)
+//   --log-dir DIR              read Kafka log segments from DIR/<topic>-<partition>/*.log (a broker's data directory)
+//                              and decode them on the GPU (uncompressed RecordBatch v2)
 //   --feed push|batch|device   how records reach the handlers: kta_push per record (the reference's call shape),
 //                              kta_push_batch_host, or generated and scanned in HBM
 //
@@ -11,7 +13,12 @@
 // GPU library; this file only feeds records and prints.
 #include <cuda_runtime_api.h>
 
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <algorithm>
 #include <chrono>
+#include <fstream>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,8 +35,92 @@ static void die(const char *what) {
 }
 #define KTA(call) do { if ((call) != KTA_OK) die(#call); } while (0)
 
+
+// ---- --log-dir: a broker's data directory instead of a live cluster ------------------------------------------------
+static bool read_file(const std::string &path, std::vector<uint8_t> &out) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) return false;
+    const std::streamsize n = f.tellg();
+    f.seekg(0);
+    out.resize((size_t)n);
+    return n == 0 || (bool)f.read(reinterpret_cast<char *>(out.data()), n);
+}
+
+static int print_report(kta_handle *h, const std::string &topic, int P, const std::vector<int64_t> &start_offsets,
+                        const std::vector<int64_t> &end_offsets, bool alive, int hll, uint64_t duration_secs);
+
+static int analyze_log_dir(const std::string &topic, const std::string &dir, bool alive, int hll,
+                           std::chrono::steady_clock::time_point start_time) {
+    // get_topic_offsets (src/kafka.rs:60-72) from the files: partitions = <topic>-<n> directories, low watermark =
+    // first batch's baseOffset, high watermark = last batch's baseOffset + lastOffsetDelta + 1
+    std::map<int, std::vector<std::string>> segs;
+    DIR *d = opendir(dir.c_str());
+    if (!d) { fprintf(stderr, "Error fetching metadata: cannot open %s\n", dir.c_str()); return 101; }
+    while (dirent *e = readdir(d)) {
+        const std::string name = e->d_name;
+        if (name.size() <= topic.size() + 1 || name.compare(0, topic.size() + 1, topic + "-") != 0) continue;
+        const std::string num = name.substr(topic.size() + 1);
+        if (num.empty() || num.find_first_not_of("0123456789") != std::string::npos) continue;
+        const int p = atoi(num.c_str());
+        DIR *pd = opendir((dir + "/" + name).c_str());
+        if (!pd) continue;
+        std::vector<std::string> files;
+        while (dirent *fe = readdir(pd)) {
+            const std::string fn = fe->d_name;
+            if (fn.size() > 4 && fn.substr(fn.size() - 4) == ".log") files.push_back(dir + "/" + name + "/" + fn);
+        }
+        closedir(pd);
+        std::sort(files.begin(), files.end());
+        segs[p] = files;
+    }
+    closedir(d);
+    if (segs.empty()) { fprintf(stderr, "Topic not found!\n"); return 101; }  // src/kafka.rs:62
+    const int P = segs.rbegin()->first + 1;
+    std::vector<int64_t> start_offsets(P, 0), end_offsets(P, 0);
+    kta_config cfg{};
+    cfg.struct_size = sizeof cfg;
+    cfg.device = -1;
+    cfg.num_partitions = P;
+    cfg.count_alive_keys = alive ? 1 : 0;
+    cfg.hll_precision = hll;
+    cfg.now_s = INT64_MIN;
+    kta_handle *h = nullptr;
+    KTA(kta_create(&cfg, &h));
+    printf("Subscribing to %s\n", topic.c_str());
+    printf("Starting message consumption...\n");
+    std::vector<uint8_t> buf;
+    auto be64 = [](const uint8_t *p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | p[i]; return (int64_t)v; };
+    auto be32 = [](const uint8_t *p) { return (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]); };
+    int64_t total = 0;
+    for (auto &kv : segs) {
+        bool first = true;
+        for (const auto &path : kv.second) {
+            if (!read_file(path, buf)) { fprintf(stderr, "cannot read %s\n", path.c_str()); return 1; }
+            for (int64_t pos = 0; pos + 61 <= (int64_t)buf.size();) {
+                const int64_t bl = be32(buf.data() + pos + 8);
+                if (bl < 49 || pos + 12 + bl > (int64_t)buf.size()) break;
+                if (first) { start_offsets[kv.first] = be64(buf.data() + pos); first = false; }
+                end_offsets[kv.first] = be64(buf.data() + pos) + be32(buf.data() + pos + 23) + 1;
+                pos += 12 + bl;
+            }
+            int64_t nrec = 0;
+            KTA(kta_push_log_segment_host(h, kv.first, buf.data(), (int64_t)buf.size(), &nrec));
+            total += nrec;
+        }
+    }
+    if (std::all_of(end_offsets.begin(), end_offsets.end(), [](int64_t v) { return v == 0; })) {
+        fprintf(stderr, "Given topic has no content, no analysis possible. Exiting.\n");  // main.rs:98-101
+        return 254;
+    }
+    KTA(kta_finalize(h));
+    const uint64_t secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
+    const int rc = print_report(h, topic, P, start_offsets, end_offsets, alive, hll, secs);
+    kta_destroy(h);
+    return rc;
+}
+
 int main(int argc, char **argv) {
-    std::string topic, bootstrap, librdkafka, synthetic, feed = "batch";
+    std::string topic, bootstrap, librdkafka, synthetic, log_dir, feed = "batch";
     int count_alive_occurrences = 0, hll = 0;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -40,6 +131,7 @@ int main(int argc, char **argv) {
         else if (a == "-c" || a == "--count-alive-keys") count_alive_occurrences++;
         else if (a == "-cc") count_alive_occurrences += 2;
         else if (a == "--synthetic") synthetic = val();
+        else if (a == "--log-dir") log_dir = val();
         else if (a == "--feed") feed = val();
         else if (a == "--hll") hll = atoi(val().c_str());
         else if (a == "-V" || a == "--version") { puts("Kafka Topic Analyzer 0.4.1"); return 0; }  // main.rs:35
@@ -58,11 +150,12 @@ int main(int argc, char **argv) {
         fprintf(stderr, "error: The following required arguments were not provided:\n    --bootstrap-server <BOOTSTRAP_SERVER>\n    --topic <TOPIC>\n");
         return 2;
     }
-    if (synthetic.empty()) {
-        fprintf(stderr, "Error fetching metadata: this build has no librdkafka client (no broker access); pass --synthetic n=...,partitions=...\n");
+    if (synthetic.empty() && log_dir.empty()) {
+        fprintf(stderr, "Error fetching metadata: this build has no librdkafka client (no broker access); pass --log-dir DIR or --synthetic n=...,partitions=...\n");
         return 101;  // the reference panics here (src/kafka.rs:61)
     }
     const auto start_time = std::chrono::steady_clock::now();  // main.rs:69
+    if (!log_dir.empty()) return analyze_log_dir(topic, log_dir, count_alive_occurrences == 1, hll, start_time);
 
     std::map<std::string, std::string> kv;
     for (size_t p = 0; p < synthetic.size();) {
@@ -158,6 +251,13 @@ int main(int argc, char **argv) {
             (long long)n, feed_s, feed_s > 0 ? (double)n / feed_s : 0.0);
     const uint64_t duration_secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
 
+    const int rc = print_report(h, topic, P, start_offsets, end_offsets, cfg.count_alive_keys == 1, hll, duration_secs);
+    kta_destroy(h);
+    return rc;
+}
+
+static int print_report(kta_handle *h, const std::string &topic, int P, const std::vector<int64_t> &start_offsets,
+                        const std::vector<int64_t> &end_offsets, bool alive, int hll, uint64_t duration_secs) {
     kta_report::Summary s{};
     s.topic = topic;
     s.duration_secs = duration_secs;
@@ -166,7 +266,7 @@ int main(int argc, char **argv) {
     KTA(kta_global(h, KTA_LARGEST_MESSAGE, &s.largest_message));
     KTA(kta_global(h, KTA_SMALLEST_MESSAGE, &s.smallest_message));
     KTA(kta_global(h, KTA_OVERALL_SIZE, &s.overall_size));
-    s.has_alive_keys = cfg.count_alive_keys == 1;
+    s.has_alive_keys = alive;
     if (s.has_alive_keys) KTA(kta_alive_keys(h, &s.alive_keys));
     std::vector<kta_report::PartitionRow> rows;
     for (int p = 0; p < P; p++) {  // partitions sorted ascending, main.rs:103-106
@@ -186,6 +286,5 @@ int main(int argc, char **argv) {
     }
     fputs(kta_report::render(s, rows).c_str(), stdout);
     if (hll) { double e = 0; KTA(kta_alive_keys_hll(h, &e)); printf("| extension: HyperLogLog(p=%d) alive-key estimate: %.0f\n", hll, e); }
-    kta_destroy(h);
     return 0;
 }

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kta_kernels.cuh"
+#include "kta_logdecode.cuh"
 #include "kta_synth.h"
 
 using namespace kta;
@@ -95,6 +96,13 @@ struct kta_handle {
     uint32_t *d_hash_out = nullptr;          // test hook
     uint64_t *d_tb_scratch = nullptr;        // key_tile_base scratch for device batches
     int64_t tb_scratch_tiles = 0;
+    // RecordBatch decoder scratch (kta_scan_log_segment_device / kta_push_log_segment_host)
+    uint8_t *d_log_bytes = nullptr; int64_t log_bytes_cap = 0;       // raw segment staged from the host
+    uint64_t *d_log_off = nullptr;                                    // batch offsets staged from the host
+    LogBatchInfo *d_log_info = nullptr; uint64_t *d_log_cnt = nullptr, *d_log_kb = nullptr; int64_t log_batch_cap = 0;
+    int32_t *d_dec_part = nullptr, *d_dec_klen = nullptr, *d_dec_vlen = nullptr; int64_t *d_dec_ts = nullptr; int64_t dec_rec_cap = 0;
+    uint8_t *d_dec_keys = nullptr; int64_t dec_key_cap = 0;
+    uint32_t *d_log_err = nullptr;
     size_t nsums = 0, nhll = 0;
     // landing ring
     Chunk chunks[NCHUNK];
@@ -207,6 +215,9 @@ extern "C" int kta_destroy(kta_handle *h) {
     for (auto &c : h->chunks) free_chunk(c);
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
     cudaFree(h->d_alive_dirty); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
+    cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt); cudaFree(h->d_log_kb);
+    cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys);
+    cudaFree(h->d_log_err);
     for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
@@ -416,6 +427,132 @@ extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
     if ((rc = launch_scan(h, prm, b->key_bytes_len))) return rc;
     h->next_seq = std::max<uint64_t>(h->next_seq, b->seq_base + (uint64_t)b->n);
     return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kafka RecordBatch v2 segments → SoA → scan (kernels in kta_logdecode.cuh)
+// ------------------------------------------------------------------------------------------------
+static int ring_flush(kta_handle *h);
+
+template <typename T>
+static int grow(T *&ptr, int64_t &cap, int64_t need, cudaStream_t s) {
+    if (need <= cap) return KTA_OK;
+    CU(cudaStreamSynchronize(s));   // queued work may still read the old buffer
+    cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    const int64_t n = need + need / 4 + 64;
+    CU(cudaMalloc(&ptr, (size_t)n * sizeof(T)));
+    cap = n;
+    return KTA_OK;
+}
+
+extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
+                                           const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
+    if (!h || len < 0 || nbatches < 0 || (nbatches && (!dev_bytes || !dev_batch_off))) return fail(KTA_ERR_INVALID, "bad argument");
+    if (records_out) *records_out = 0;
+    if (nbatches == 0) return KTA_OK;
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;   // keep seq order with records pushed earlier
+    cudaStream_t s = h->stream;
+    if (nbatches + 1 > h->log_batch_cap) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(h->d_log_info); cudaFree(h->d_log_cnt); cudaFree(h->d_log_kb);
+        h->d_log_info = nullptr; h->d_log_cnt = nullptr; h->d_log_kb = nullptr; h->log_batch_cap = 0;
+        const int64_t n = nbatches + nbatches / 4 + 64;
+        CU(cudaMalloc(&h->d_log_info, (size_t)n * sizeof(LogBatchInfo)));
+        CU(cudaMalloc(&h->d_log_cnt, (size_t)n * 8));
+        CU(cudaMalloc(&h->d_log_kb, (size_t)n * 8));
+        h->log_batch_cap = n;
+    }
+    if (!h->d_log_err) CU(cudaMalloc(&h->d_log_err, 4));
+    CU(cudaMemsetAsync(h->d_log_err, 0, 4, s));
+    const int grid = (int)std::min<int64_t>((nbatches + 127) / 128, (int64_t)h->sm_count * 16);
+    log_header_kernel<<<grid, 128, 0, s>>>(dev_bytes, len, dev_batch_off, nbatches, partition, h->d_log_info, h->d_log_cnt,
+                                            h->d_log_err);
+    tile_base_scan_kernel<<<1, 1024, 0, s>>>(h->d_log_cnt, nbatches);   // inclusive scan of [1..nbatches] in place
+    CU(cudaGetLastError());
+    h->launches += 2;
+    uint64_t nrec = 0;
+    uint32_t err = 0;
+    CU(cudaMemcpyAsync(&nrec, h->d_log_cnt + nbatches, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&err, h->d_log_err, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (err & LOGB_COMPRESSED) return fail(KTA_ERR_INVALID, "compressed record batches are not supported (no decompressor on this path)");
+    if (err) return fail(KTA_ERR_INVALID, "malformed record batch header in partition %d", partition);
+    if (nrec == 0) return KTA_OK;
+    if ((int64_t)nrec > h->dec_rec_cap) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts);
+        h->d_dec_part = h->d_dec_klen = h->d_dec_vlen = nullptr; h->d_dec_ts = nullptr; h->dec_rec_cap = 0;
+        const int64_t n = (int64_t)nrec + (int64_t)nrec / 4 + 1024;
+        CU(cudaMalloc(&h->d_dec_part, (size_t)n * 4));
+        CU(cudaMalloc(&h->d_dec_klen, (size_t)n * 4));
+        CU(cudaMalloc(&h->d_dec_vlen, (size_t)n * 4));
+        CU(cudaMalloc(&h->d_dec_ts, (size_t)n * 8));
+        h->dec_rec_cap = n;
+    }
+    log_decode_kernel<0><<<grid, 128, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, h->d_dec_part, nullptr, h->d_dec_ts,
+                                              h->d_dec_klen, h->d_dec_vlen, h->d_log_kb, nullptr, h->d_log_err);
+    tile_base_scan_kernel<<<1, 1024, 0, s>>>(h->d_log_kb, nbatches);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    uint64_t nkey = 0;
+    CU(cudaMemcpyAsync(&nkey, h->d_log_kb + nbatches, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&err, h->d_log_err, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (err) return fail(KTA_ERR_INVALID, "malformed record inside a batch of partition %d", partition);
+    const bool hash = h->need_hash || h->d_hash_out;
+    if (hash) {
+        if ((rc = grow(h->d_dec_keys, h->dec_key_cap, (int64_t)nkey + 64, s))) return rc;
+        log_decode_kernel<1><<<grid, 128, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, nullptr, nullptr, nullptr, nullptr,
+                                                  nullptr, h->d_log_kb, h->d_dec_keys, h->d_log_err);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    kta_batch b{};
+    b.n = (int64_t)nrec;
+    b.seq_base = h->next_seq;
+    b.partition = h->d_dec_part;
+    b.ts_ms = h->d_dec_ts;
+    b.key_len = h->d_dec_klen;
+    b.value_len = h->d_dec_vlen;
+    b.key_bytes = hash ? h->d_dec_keys : nullptr;
+    b.key_bytes_len = hash ? (int64_t)nkey : 0;
+    if ((rc = kta_scan_batch_device(h, &b))) return rc;
+    if (records_out) *records_out = (int64_t)nrec;
+    return KTA_OK;
+}
+
+extern "C" int kta_push_log_segment_host(kta_handle *h, int32_t partition, const uint8_t *bytes, int64_t len,
+                                         int64_t *records_out) {
+    if (!h || len < 0 || (len && !bytes)) return fail(KTA_ERR_INVALID, "bad argument");
+    if (records_out) *records_out = 0;
+    // hop from batch header to batch header on the host (12 + batchLength bytes each); a truncated tail is ignored,
+    // as a consumer would ignore a partially fetched batch
+    std::vector<uint64_t> offs;
+    int64_t pos = 0;
+    while (pos + LOG_HEADER_BYTES <= len) {
+        const uint8_t *p = bytes + pos;
+        const int64_t bl = (int64_t)(int32_t)(((uint32_t)p[8] << 24) | ((uint32_t)p[9] << 16) | ((uint32_t)p[10] << 8) | p[11]);
+        if (bl < LOG_HEADER_BYTES - 12 || pos + 12 + bl > len) break;
+        offs.push_back((uint64_t)pos);
+        pos += 12 + bl;
+    }
+    if (offs.empty()) return KTA_OK;
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    cudaStream_t s = h->stream;
+    if ((rc = grow(h->d_log_bytes, h->log_bytes_cap, pos + 64, s))) return rc;
+    cudaFree(h->d_log_off);
+    h->d_log_off = nullptr;
+    CU(cudaMalloc(&h->d_log_off, offs.size() * 8));
+    CU(cudaMemcpyAsync(h->d_log_bytes, bytes, (size_t)pos, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_log_off, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, s));
+    if ((rc = kta_scan_log_segment_device(h, partition, h->d_log_bytes, pos, h->d_log_off, (int64_t)offs.size(), records_out))) return rc;
+    CU(cudaStreamSynchronize(s));   // the caller may reuse `bytes`, and the scratch may be reused by the next segment
+    return collect_timing(h);
 }
 
 // ------------------------------------------------------------------------------------------------

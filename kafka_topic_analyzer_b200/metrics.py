@@ -141,6 +141,14 @@ class KtaEngine:
         self._keep.append((partition, ts_ms, key_len, value_len, key_bytes, key_tile_base, seq))
         check(lib().kta_scan_batch_device(self._h, C.byref(b)))
 
+    def push_log_segment(self, partition: int, data) -> int:
+        """Decode + scan one Kafka log segment (RecordBatch v2 bytes of one partition, host memory).  Returns the
+        number of records delivered to the handlers."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        n = C.c_int64()
+        check(lib().kta_push_log_segment_host(self._h, partition, buf.ctypes.data, buf.size, C.byref(n)))
+        return n.value
+
     def sync(self) -> None:
         check(lib().kta_sync(self._h))
         self._keep = []

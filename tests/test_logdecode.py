@@ -1,0 +1,145 @@
+"""Kafka RecordBatch v2 log segments decoded on the GPU and scanned, against the CPU oracle fed
+with the same records (what librdkafka would have delivered message by message)."""
+import numpy as np
+import pytest
+
+from kafka_topic_analyzer_b200 import KtaEngine, KtaError, synth
+from oracle_lib import Oracle
+from parity import assert_parity
+import kafka_codec as kc
+
+NOW = (4102444800, 123456789)
+
+
+def test_codec_varints_roundtrip():
+    for n in (0, 1, -1, 63, 64, -64, -65, 300, -300, 2**31 - 1, -2**31, 2**40, -2**40):
+        b = kc.varint(n)
+        u, shift = 0, 0
+        for x in b:
+            u |= (x & 0x7F) << shift
+            shift += 7
+        assert ((u >> 1) ^ -(u & 1)) == n
+    assert kc.varint(-1) == b"\x01" and kc.varint(0) == b"\x00" and kc.varint(1) == b"\x02"
+
+
+def _partition_lists(t):
+    """per-partition record lists (ts, key, value_len) in offset order, from a HostTopic"""
+    kl = t.key_len
+    koff = np.concatenate([[0], np.cumsum(np.maximum(kl, 0))])
+    per = {}
+    for i in range(t.n):
+        key = None if kl[i] < 0 else t.key_bytes[koff[i]:koff[i] + kl[i]].tobytes()
+        vl = None if t.value_len[i] < 0 else int(t.value_len[i])
+        per.setdefault(int(t.partition[i]), []).append((int(t.ts_ms[i]), key, vl))
+    return per
+
+
+def _oracle_over(per, **kw):
+    o = Oracle(now=NOW, **kw)
+    for p in sorted(per):
+        for ts, key, vl in per[p]:
+            o.handle_message(p, None if ts == -1 else ts, key, vl)
+    return o
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key_mode,exact", [(0, True), (2, True), (1, False)])
+def test_segments_decode_and_scan(key_mode, exact):
+    rng = np.random.default_rng(3 + key_mode)
+    P = 6
+    spec = synth.make_spec(P * 1500, P, key_mode=key_mode, distinct_keys=600, tombstone_per_10k=2000, null_key_per_10k=400,
+                           ts_missing_per_10k=300, empty_value_per_10k=200, value_mean=40)
+    per = _partition_lists(synth.fill_host(spec))
+    o = _oracle_over(per, count_alive_keys=exact, track_stream=not exact)
+    with KtaEngine(P, count_alive_keys=exact, hll_precision=10, now=NOW) as e:
+        total = 0
+        for p in sorted(per):
+            seg = kc.encode_partition(per[p], rng)
+            total += e.push_log_segment(p, seg + b"\x00" * 17)      # + a truncated tail, as in a partial fetch
+        e.finalize()
+        assert total == spec.n_total
+        assert_parity(e, o, P, check_alive=exact, hll_regs=o.hll_alive_regs(10) if exact else o.hll_stream_regs(10))
+
+
+@pytest.mark.gpu
+def test_log_append_time_control_batches_and_big_fields():
+    rng = np.random.default_rng(9)
+    big_key = bytes(rng.integers(0, 256, size=70_000, dtype=np.uint8))
+    recs = [(1_700_000_000_123, b"a", 10), (1_700_000_000_456, None, None), (1_700_000_001_000, b"", 0),
+            (1_700_000_002_000, big_key, 300_000), (1_600_000_000_000, b"a", None)]
+    seg = kc.encode_batch(0, 1_700_000_000_000, [(i, r[0] - 1_700_000_000_000, r[1], r[2]) for i, r in enumerate(recs)])
+    # a control batch (transaction marker) is never delivered to the application
+    seg += kc.encode_batch(5, 1_700_000_003_000, [(0, 0, b"\x00\x00\x00\x01", 6)], attributes=0x20)
+    # LogAppendTime: every record carries the batch's maxTimestamp
+    seg += kc.encode_batch(6, 1_500_000_000_000, [(0, 5, b"b", 1), (1, 9, b"c", 2)], attributes=0x08, max_ts=1_800_000_000_999)
+    o = Oracle(count_alive_keys=True, now=NOW)
+    for ts, key, vl in recs:
+        o.handle_message(2, ts, key, vl)
+    o.handle_message(2, 1_800_000_000_999, b"b", 1)
+    o.handle_message(2, 1_800_000_000_999, b"c", 2)
+    with KtaEngine(4, count_alive_keys=True, now=NOW) as e:
+        assert e.push_log_segment(2, seg) == 7
+        e.finalize()
+        assert_parity(e, o, 4, check_alive=True)
+        assert e.message_metrics.latest_message() == 1_800_000_000
+
+
+@pytest.mark.gpu
+def test_compressed_and_malformed_batches_are_rejected():
+    good = kc.encode_batch(0, 1000, [(0, 0, b"k", 1)])
+    with KtaEngine(1, now=NOW) as e:
+        with pytest.raises(KtaError):
+            e.push_log_segment(0, kc.encode_batch(0, 1000, [(0, 0, b"k", 1)], attributes=0x01))   # gzip
+        bad = bytearray(good)
+        bad[16] = 1                                                                              # magic 1
+        with pytest.raises(KtaError):
+            e.push_log_segment(0, bytes(bad))
+        bad = bytearray(good)
+        bad[61] = 0x7F                                                                           # record length beyond the batch
+        with pytest.raises(KtaError):
+            e.push_log_segment(0, bytes(bad))
+        assert e.push_log_segment(0, good[:30]) == 0                                             # only a truncated header
+
+
+@pytest.mark.gpu
+def test_cli_log_dir(tmp_path):
+    """The C++ CLI over a broker-style data directory: <topic>-<partition>/<base offset>.log, two segments per
+    partition, -c.  The printed table must equal the oracle over the same records."""
+    import os
+    import subprocess
+    from test_report import CLI_DIR, _build
+    _build()
+    rng = np.random.default_rng(21)
+    P = 3
+    spec = synth.make_spec(P * 2000, P, key_mode=1, distinct_keys=300, tombstone_per_10k=3000, value_mean=30)
+    per = _partition_lists(synth.fill_host(spec))
+    for p, recs in per.items():
+        d = tmp_path / ("orders-%d" % p)
+        d.mkdir()
+        half = len(recs) // 2
+        (d / "00000000000000000000.log").write_bytes(kc.encode_partition(recs[:half], rng))
+        second = bytearray()
+        # second segment continues the offsets
+        i = half
+        while i < len(recs):
+            chunk = recs[i:i + 25]
+            second += kc.encode_batch(i, chunk[0][0], [(j, r[0] - chunk[0][0], r[1], r[2]) for j, r in enumerate(chunk)])
+            i += len(chunk)
+        (d / ("%020d.log" % half)).write_bytes(bytes(second))
+        (d / "00000000000000000000.index").write_bytes(b"\x00" * 8)   # ignored
+    (tmp_path / "other-0").mkdir()
+    r = subprocess.run([os.path.join(CLI_DIR, "kafka-topic-analyzer"), "-t", "orders", "-b", "unused:9092", "-c", "--log-dir",
+                        str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    o = _oracle_over(per, count_alive_keys=True)
+    lines = r.stdout.splitlines()
+    assert "Alive keys: %d" % o.scalar("sum_all_alive") in lines
+    assert "Topic Size: %d bytes" % o.scalar("overall_size") in lines
+    rows = [l for l in lines if l.startswith("| ") and l[2].isdigit()]
+    assert len(rows) == P
+    for l in rows:
+        c = [x.strip() for x in l.strip("|").split("|")]
+        p = int(c[0])
+        assert (int(c[1]), int(c[2])) == (0, len(per[p]))                     # start / end offsets from the batch headers
+        assert [int(c[3]), int(c[4]), int(c[5])] == [o.counter("total", p), o.counter("alive", p), o.counter("tombstones", p)]
+        assert [int(c[10]), int(c[11])] == [o.counter("key_size_sum", p), o.counter("value_size_sum", p)]
