@@ -241,6 +241,11 @@ int kta_synth_fill_device(const kta_synth_spec *s, int32_t device, int32_t rank,
                           uint8_t *key_bytes, int64_t key_bytes_cap, uint64_t *key_tile_base,
                           int64_t *key_bytes_len);
 
+/* The same topic as a broker stores it: records [start, start+count) (offset order) of one partition as an
+ * uncompressed RecordBatch v2 log segment, `batch_records` records per batch (feeds kta_push_log_segment_host). */
+int kta_synth_encode_segment_host(const kta_synth_spec *s, int32_t partition, int64_t start, int64_t count,
+                                  int32_t batch_records, uint8_t *out, int64_t cap, int64_t *len);
+
 #ifdef __cplusplus
 }
 #endif

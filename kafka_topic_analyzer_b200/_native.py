@@ -127,6 +127,8 @@ SYMBOLS = {
                                       _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "kta_synth_fill_device": (C.c_int, [C.POINTER(SynthSpec), C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                         _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "kta_synth_encode_segment_host": (C.c_int, [C.POINTER(SynthSpec), C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64,
+                                                C.POINTER(C.c_int64)]),
     # test hook, not part of kta.h's stable surface
     "kta_set_hash_capture": (C.c_int, [_P, _P]),
 }

@@ -90,6 +90,21 @@ def fill_host(spec: SynthSpec, rank: int = 0, world: int = 1, start: int = 0, co
     return HostTopic(part, off, ts, kl, vl, seq, kb, tile_base_from_key_len(kl))
 
 
+def encode_segment(spec: SynthSpec, partition: int, start: int = 0, count: Optional[int] = None, batch_records: int = 500) -> np.ndarray:
+    """One partition of the synthetic topic as an uncompressed RecordBatch v2 log segment (host bytes)."""
+    if count is None:
+        count = spec.n_total // spec.num_partitions - start
+    n = C.c_int64()
+    rc = lib().kta_synth_encode_segment_host(C.byref(spec), partition, start, count, batch_records, None, 0, C.byref(n))
+    if rc != 0:
+        raise KtaError(rc, "kta_synth_encode_segment_host failed")
+    out = np.empty(n.value, dtype=np.uint8)
+    rc = lib().kta_synth_encode_segment_host(C.byref(spec), partition, start, count, batch_records, out.ctypes.data, out.size, C.byref(n))
+    if rc != 0:
+        raise KtaError(rc, "kta_synth_encode_segment_host failed")
+    return out
+
+
 class DeviceTopic:
     """SoA columns of one shard of the synthetic topic, generated directly in HBM (torch owns the memory)."""
 

@@ -143,3 +143,61 @@ def test_cli_log_dir(tmp_path):
         assert (int(c[1]), int(c[2])) == (0, len(per[p]))                     # start / end offsets from the batch headers
         assert [int(c[3]), int(c[4]), int(c[5])] == [o.counter("total", p), o.counter("alive", p), o.counter("tombstones", p)]
         assert [int(c[10]), int(c[11])] == [o.counter("key_size_sum", p), o.counter("value_size_sum", p)]
+
+
+def _py_decode(seg):
+    """tiny pure-Python RecordBatch v2 reader (test infra) → list of (offset, ts, key, value_len)"""
+    import struct
+    def uv(b, p):
+        u, sh = 0, 0
+        while True:
+            x = b[p]; p += 1
+            u |= (x & 0x7F) << sh; sh += 7
+            if not x & 0x80:
+                return (u >> 1) ^ -(u & 1), p
+    out, pos, b = [], 0, bytes(seg)
+    while pos + 61 <= len(b):
+        base_off, bl = struct.unpack(">qi", b[pos:pos + 12])
+        base_ts, = struct.unpack(">q", b[pos + 27:pos + 35])
+        cnt, = struct.unpack(">i", b[pos + 57:pos + 61])
+        p = pos + 61
+        for _ in range(cnt):
+            ln, p = uv(b, p); end = p + ln
+            p += 1
+            tsd, p = uv(b, p); od, p = uv(b, p)
+            kl, p = uv(b, p); key = None if kl < 0 else b[p:p + kl]; p += max(kl, 0)
+            vl, p = uv(b, p)
+            out.append((base_off + od, -1 if base_ts == -1 else base_ts + tsd, key, None if vl < 0 else vl))
+            p = end
+        pos += 12 + bl
+    return out
+
+
+def test_cpp_segment_encoder_matches_the_topic():
+    """kta_synth_encode_segment_host (the broker-format face of the synthetic topic) against fill_host."""
+    P = 8
+    spec = synth.make_spec(P * 700, P, key_mode=2, distinct_keys=400, tombstone_per_10k=1500, null_key_per_10k=500)
+    for p in (0, 5):
+        got = _py_decode(synth.encode_segment(spec, p, batch_records=33))
+        t = synth.fill_host(spec, rank=p, world=P)              # partition p's records in offset order
+        koff = np.concatenate([[0], np.cumsum(np.maximum(t.key_len, 0))])
+        assert len(got) == t.n
+        for i, (off, ts, key, vl) in enumerate(got):
+            assert off == t.offset[i] and ts == t.ts_ms[i]
+            assert key == (None if t.key_len[i] < 0 else t.key_bytes[koff[i]:koff[i] + t.key_len[i]].tobytes())
+            assert vl == (None if t.value_len[i] < 0 else t.value_len[i])
+
+
+@pytest.mark.gpu
+def test_synthetic_topic_as_log_segments_full_path():
+    """configs[0]-sized topic stored broker-style (one segment per partition), decoded + scanned on the GPU with -c."""
+    P = 4
+    spec = synth.make_spec(100_000, P, distinct_keys=5000, tombstone_per_10k=1500)
+    o = Oracle(count_alive_keys=True, now=NOW)
+    with KtaEngine(P, count_alive_keys=True, hll_precision=11, now=NOW) as e:
+        for p in range(P):
+            t = synth.fill_host(spec, rank=p, world=P)
+            o.handle_batch(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes)
+            assert e.push_log_segment(p, synth.encode_segment(spec, p, batch_records=200)) == t.n
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(11))
