@@ -493,7 +493,8 @@ extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, con
         CU(cudaMalloc(&h->d_dec_ts, (size_t)n * 8));
         h->dec_rec_cap = n;
     }
-    log_decode_kernel<0><<<grid, 128, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, h->d_dec_part, nullptr, h->d_dec_ts,
+    const int dgrid = (int)std::min<int64_t>((nbatches + 3) / 4, (int64_t)h->sm_count * 16);   // one warp per batch
+    log_decode_kernel<0><<<dgrid, LOG_DECODE_THREADS, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, h->d_dec_part, nullptr, h->d_dec_ts,
                                               h->d_dec_klen, h->d_dec_vlen, h->d_log_kb, nullptr, h->d_log_err);
     tile_base_scan_kernel<<<1, 1024, 0, s>>>(h->d_log_kb, nbatches);
     CU(cudaGetLastError());
@@ -506,7 +507,7 @@ extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, con
     const bool hash = h->need_hash || h->d_hash_out;
     if (hash) {
         if ((rc = grow(h->d_dec_keys, h->dec_key_cap, (int64_t)nkey + 64, s))) return rc;
-        log_decode_kernel<1><<<grid, 128, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, nullptr, nullptr, nullptr, nullptr,
+        log_decode_kernel<1><<<dgrid, LOG_DECODE_THREADS, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, nullptr, nullptr, nullptr, nullptr,
                                                   nullptr, h->d_log_kb, h->d_dec_keys, h->d_log_err);
         CU(cudaGetLastError());
         h->launches++;

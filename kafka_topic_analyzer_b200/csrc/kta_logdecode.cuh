@@ -98,60 +98,102 @@ __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const ui
     if (blockIdx.x == 0 && threadIdx.x == 0) rec_count[0] = 0;
 }
 
-// thread per batch walks its records.  PASS 0: header columns + key-byte total of the batch; PASS 1: copy the keys.
+// One WARP per batch.  Records are length-prefixed, so finding where record i starts is a serial chain — lane 0
+// hops through 32 record-length varints at a time (touching one or two bytes per record) and publishes the 32
+// start positions; then the 32 lanes parse their records in parallel and write the columns coalesced.
+// PASS 0: header columns + key-byte total of the batch; PASS 1: copy the keys (packed, in record order).
+constexpr int LOG_DECODE_THREADS = 128;
+
 template <int PASS>
-__global__ void log_decode_kernel(const uint8_t *bytes, const LogBatchInfo *info, int64_t nbatches, const uint64_t *rec_base,
-                                  int32_t *partition, int64_t *offset, int64_t *ts_ms, int32_t *key_len, int32_t *value_len,
-                                  uint64_t *key_total /*[nbatches+1], PASS 0 out, PASS 1 in as exclusive bases*/,
-                                  uint8_t *key_out, uint32_t *error_flags) {
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbatches; b += (int64_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(LOG_DECODE_THREADS) log_decode_kernel(
+    const uint8_t *bytes, const LogBatchInfo *info, int64_t nbatches, const uint64_t *rec_base, int32_t *partition,
+    int64_t *offset, int64_t *ts_ms, int32_t *key_len, int32_t *value_len,
+    uint64_t *key_total /*[nbatches+1], PASS 0 out, PASS 1 in as exclusive bases*/, uint8_t *key_out, uint32_t *error_flags) {
+    __shared__ uint32_t s_start[LOG_DECODE_THREADS / 32][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = gw; b < nbatches; b += gs) {
         const LogBatchInfo bi = info[b];
         uint64_t kbytes = 0;
         if (bi.flags == LOGB_OK && bi.records > 0) {
-            const uint8_t *p = bytes + bi.off + LOG_HEADER_BYTES;
-            const uint8_t *end = bytes + bi.off + bi.len;
-            uint64_t r = rec_base[b];
+            const uint8_t *base = bytes + bi.off;
+            const uint8_t *end = base + bi.len;
+            uint32_t pos = LOG_HEADER_BYTES;          // offset of the next record inside the batch
+            const uint64_t r0 = rec_base[b];
             uint64_t kdst = PASS == 1 ? key_total[b] : 0;
             bool ok = true;
-            for (int32_t i = 0; i < bi.records && ok; i++, r++) {
-                uint64_t u;
-                int n = uvarint(p, end, u);
-                const int64_t rec_len = unzigzag(u);
-                ok = n > 0 && rec_len >= 0 && p + n + rec_len <= end;
+            for (int32_t i0 = 0; i0 < bi.records && ok; i0 += 32) {
+                const int cnt = min(32, bi.records - i0);
+                if (lane == 0) {
+                    for (int j = 0; j < cnt; j++) {
+                        s_start[wib][j] = pos;
+                        uint64_t u;
+                        const int n = uvarint(base + pos, end, u);
+                        const int64_t rec_len = unzigzag(u);
+                        if (n <= 0 || rec_len < 0 || (uint64_t)pos + n + rec_len > bi.len) { ok = false; break; }
+                        pos += (uint32_t)n + (uint32_t)rec_len;
+                    }
+                    s_start[wib][32] = ok ? pos : 0xffffffffu;
+                }
+                __syncwarp();
+                pos = s_start[wib][32];
+                ok = pos != 0xffffffffu;
                 if (!ok) break;
-                const uint8_t *q = p + n, *rec_end = q + rec_len;
-                p = rec_end;
-                q += 1;  // record attributes (unused)
-                n = uvarint(q, rec_end, u); ok = ok && n > 0; q += n;
-                const int64_t ts_delta = unzigzag(u);
-                n = uvarint(q, rec_end, u); ok = ok && n > 0; q += n;
-                const int64_t off_delta = unzigzag(u);
-                n = uvarint(q, rec_end, u); ok = ok && n > 0; q += n;
-                const int64_t klen = unzigzag(u);
-                ok = ok && klen >= -1 && klen <= 0x7fffffff && (klen <= 0 || q + klen <= rec_end);
+                int64_t klen = -1, vlen = -1, ts_delta = 0, off_delta = 0;
+                const uint8_t *key = nullptr;
+                bool lane_ok = true;
+                if (lane < cnt) {
+                    const uint8_t *q = base + s_start[wib][lane];
+                    const uint8_t *rec_end = lane + 1 < cnt ? base + s_start[wib][lane + 1] : base + pos;
+                    uint64_t u;
+                    int n = uvarint(q, rec_end, u); q += n;            // record length (validated by lane 0)
+                    q += 1;                                             // record attributes (unused)
+                    n = uvarint(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
+                    ts_delta = unzigzag(u);
+                    n = uvarint(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
+                    off_delta = unzigzag(u);
+                    n = uvarint(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
+                    klen = unzigzag(u);
+                    lane_ok = lane_ok && klen >= -1 && klen <= 0x7fffffff && (klen <= 0 || q + klen <= rec_end);
+                    key = q;
+                    if (lane_ok && klen > 0) q += klen;
+                    n = lane_ok ? uvarint(q, rec_end, u) : 0; lane_ok = lane_ok && n > 0; q += n;
+                    vlen = unzigzag(u);
+                    lane_ok = lane_ok && vlen >= -1 && vlen <= 0x7fffffff && (vlen <= 0 || q + vlen <= rec_end);
+                }
+                __syncwarp();   // every lane has read its start before lane 0 overwrites them
+                ok = __all_sync(full, lane_ok);
                 if (!ok) break;
-                const uint8_t *key = q;
-                if (klen > 0) q += klen;
-                n = uvarint(q, rec_end, u); ok = ok && n > 0; q += n;
-                const int64_t vlen = unzigzag(u);
-                ok = ok && vlen >= -1 && vlen <= 0x7fffffff && (vlen <= 0 || q + vlen <= rec_end);
-                if (!ok) break;
+                const uint64_t kl = (lane < cnt && klen > 0) ? (uint64_t)klen : 0;
                 if (PASS == 0) {
-                    const int64_t t = bi.log_append_time ? bi.max_ts : (bi.base_ts == -1 ? -1 : bi.base_ts + ts_delta);
-                    partition[r] = bi.partition;
-                    if (offset) offset[r] = bi.base_offset + off_delta;
-                    ts_ms[r] = t;
-                    key_len[r] = (int32_t)klen;
-                    value_len[r] = (int32_t)vlen;
-                    if (klen > 0) kbytes += (uint64_t)klen;
-                } else if (klen > 0) {
-                    for (int64_t j = 0; j < klen; j++) key_out[kdst + j] = __ldg(key + j);
-                    kdst += (uint64_t)klen;
+                    if (lane < cnt) {
+                        const uint64_t r = r0 + (uint64_t)i0 + lane;
+                        partition[r] = bi.partition;
+                        if (offset) offset[r] = bi.base_offset + off_delta;
+                        ts_ms[r] = bi.log_append_time ? bi.max_ts : (bi.base_ts == -1 ? -1 : bi.base_ts + ts_delta);
+                        key_len[r] = (int32_t)klen;
+                        value_len[r] = (int32_t)vlen;
+                    }
+                    uint64_t t = kl;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(full, t, d);
+                    kbytes += t;
+                } else {
+                    uint64_t inc = kl;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint64_t t = __shfl_up_sync(full, inc, d);
+                        if (lane >= d) inc += t;
+                    }
+                    const uint64_t dst = kdst + inc - kl;
+                    for (uint64_t j = 0; j < kl; j++) key_out[dst + j] = __ldg(key + j);
+                    kdst += __shfl_sync(full, inc, 31);
                 }
             }
-            if (!ok) atomicOr(error_flags, (uint32_t)LOGB_BAD);
+            if (!ok && lane == 0) atomicOr(error_flags, (uint32_t)LOGB_BAD);
         }
-        if (PASS == 0) key_total[b + 1] = kbytes;
+        if (PASS == 0 && lane == 0) key_total[b + 1] = kbytes;
     }
     if (PASS == 0 && blockIdx.x == 0 && threadIdx.x == 0) key_total[0] = 0;
 }

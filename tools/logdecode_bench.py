@@ -8,11 +8,12 @@ from kafka_topic_analyzer_b200 import synth
 from kafka_topic_analyzer_b200._native import lib, check
 
 P, N, VM = 16, 8_000_000, int(sys.argv[1]) if len(sys.argv) > 1 else 256
+BR = int(sys.argv[2]) if len(sys.argv) > 2 else 56   # ~16 KB batches (the producer default batch.size) at 256 B values
 spec = synth.make_spec(N, P, value_mean=VM, distinct_keys=1_000_000)
 segs, offs = [], []
 t0 = time.time()
 for p in range(P):
-    s = synth.encode_segment(spec, p, batch_records=500)
+    s = synth.encode_segment(spec, p, batch_records=BR)
     # batch offsets by hopping headers on the host
     o, pos = [], 0
     while pos + 61 <= s.size:
