@@ -121,8 +121,6 @@ struct kta_handle {
     // occupancy-derived grids
     bool smem_counters = true;               // per-partition counters fit in shared memory
     size_t smem_optin = 0;
-    int threads_scan[5] = {0, 0, 0, 0, 0};   // [0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture]
-    size_t smem_scan[5] = {0, 0, 0, 0, 0};
     // stats / timing
     uint64_t launches = 0, records = 0;
     bool timing = false;
@@ -137,26 +135,39 @@ static int set_device(const kta_handle *h) {
     return KTA_OK;
 }
 
-static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads) {
-    return (smem ? smem_counter_bytes(P) : 128) + (size_t)(threads / 32) * (hash ? WARP_SMEM : 128);
+static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf) {
+    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf);
 }
 
-// one persistent CTA per SM; as many autonomous warps as the shared-memory budget allows.
+// Launch shape for one scan: key-stage bytes from the batch's mean key length, then as many warps as fit.
+static void scan_shape(const kta_handle *h, bool hash, int64_t n, int64_t key_bytes, int &threads, int &keybuf, size_t &smem) {
+    keybuf = KEYBUF_MIN;
+    if (hash && n > 0) {
+        const int64_t per_tile = (key_bytes * TILE + n - 1) / n;           // mean key bytes per 128-record tile
+        int64_t want = per_tile + per_tile / 4 + 64 + KEYBUF_SLACK;       // 25 % headroom for ragged tiles
+        want = (want + 127) / 128 * 128;
+        keybuf = (int)std::min<int64_t>(std::max<int64_t>(want, KEYBUF_MIN), KEYBUF_MAX);
+        keybuf = (keybuf + 15) / 16 * 16;
+    }
+    const int P = h->cfg.num_partitions;
+    for (threads = MAX_THREADS;; threads -= 128) {
+        smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf);
+        if (smem <= h->smem_optin || threads <= 256) break;
+    }
+    if (smem > h->smem_optin) {   // still too big with 8 warps: fall back to the smallest stage (long keys go through global)
+        keybuf = KEYBUF_MIN;
+        for (threads = MAX_THREADS;; threads -= 128) {
+            smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf);
+            if (smem <= h->smem_optin || threads <= 128) break;
+        }
+    }
+}
+
+// one persistent CTA per SM; every variant may use the whole opt-in shared memory (the shape is chosen per launch).
 // variant index: 0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture
 template <int MODE, bool SMEM, bool CAPTURE>
 static int prepare_variant(kta_handle *h) {
-    const int v = MODE + (CAPTURE ? 2 : 0);
-    const bool hash = MODE != MODE_COUNTERS;
-    int threads = MAX_THREADS;
-    size_t smem = 0;
-    for (;; threads -= 128) {
-        smem = scan_smem_bytes(hash, SMEM, h->cfg.num_partitions, threads);
-        if (smem <= h->smem_optin || threads <= 128) break;
-    }
-    if (smem > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", smem);
-    CU(cudaFuncSetAttribute(scan_kernel<MODE, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->threads_scan[v] = threads;
-    h->smem_scan[v] = smem;
+    CU(cudaFuncSetAttribute(scan_kernel<MODE, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
     return KTA_OK;
 }
 
@@ -273,7 +284,7 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     }
     h->smem_optin = prop.sharedMemPerBlockOptin;
     // counters in shared memory as long as at least 8 warps still fit beside them
-    h->smem_counters = smem_counter_bytes(P) + 8 * (size_t)WARP_SMEM <= h->smem_optin;
+    h->smem_counters = smem_counter_bytes(P) + 8 * warp_smem_bytes(true, KEYBUF_MIN) <= h->smem_optin;
     int rc;
     if ((rc = h->smem_counters ? prepare_all<true>(h) : prepare_all<false>(h))) return rc;
     if ((rc = state_reset_device(h))) return rc;
@@ -316,7 +327,7 @@ extern "C" int kta_set_stream(kta_handle *h, void *stream) {
 // ------------------------------------------------------------------------------------------------
 // scan launch
 // ------------------------------------------------------------------------------------------------
-static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
+static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes) {
     if (prm.n <= 0) return KTA_OK;
     const int P = h->cfg.num_partitions;
     const bool exact = h->cfg.count_alive_keys == 1;
@@ -344,9 +355,12 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable) {
         prm.stage_limit = (((uintptr_t)prm.key_bytes & 15u) == 0) ? (uint64_t)key_readable : 0;
     }
     const int variant = mode + (capture ? 2 : 0);
-    const int threads = h->threads_scan[variant];
+    int threads = 0, keybuf = 0;
+    size_t sm = 0;
+    scan_shape(h, mode != MODE_COUNTERS, prm.n, key_bytes, threads, keybuf, sm);
+    if (sm > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", sm);
+    prm.keybuf = keybuf;
     const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
-    const size_t sm = h->smem_scan[variant];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         if (h->ev_used == h->ev_pool.size()) {
@@ -424,7 +438,7 @@ extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
         if ((rc = derive_tile_base(h, b->key_len, b->n, h->d_tb_scratch))) return rc;
         prm.key_tile_base = h->d_tb_scratch;
     }
-    if ((rc = launch_scan(h, prm, b->key_bytes_len))) return rc;
+    if ((rc = launch_scan(h, prm, b->key_bytes_len, b->key_bytes_len))) return rc;
     h->next_seq = std::max<uint64_t>(h->next_seq, b->seq_base + (uint64_t)b->n);
     return KTA_OK;
 }
@@ -619,7 +633,7 @@ static int ring_flush(kta_handle *h) {
     prm.key_bytes = c.d_keys;
     prm.key_tile_base = c.d_tile_base;
     int rc;
-    if ((rc = launch_scan(h, prm, (kb + 15) & ~(int64_t)15))) return rc;
+    if ((rc = launch_scan(h, prm, (kb + 15) & ~(int64_t)15, kb))) return rc;
     CU(cudaEventRecord(c.free_ev, s));
     h->cur = (h->cur + 1) % NCHUNK;
     h->cur_n = 0;
@@ -744,7 +758,7 @@ extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
         prm.key_len = c.d_klen;
         prm.value_len = c.d_vlen;
         prm.seq = (b->seq && h->cfg.count_alive_keys == 1) ? c.d_seq : nullptr;
-        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull)))) return rc;
+        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull), (int64_t)(k1 - k0)))) return rc;
         CU(cudaEventRecord(c.free_ev, s));
         h->cur = (h->cur + 1) % NCHUNK;
         koff = k1;

@@ -26,9 +26,12 @@ constexpr int MAX_THREADS = KTA_SCAN_THREADS;  // one persistent CTA per SM, up 
 constexpr int TILE = KTA_KEY_TILE;        // records per warp tile (128)
 constexpr int ROWS = TILE / 32;           // records per lane per tile
 constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
-constexpr int KEYBUF_COPY = TILE * 18;    // max staged key bytes per tile (18 B/record average)
-constexpr int KEYBUF = KEYBUF_COPY + 32;  // + slack for the (harmless, <= 23 byte) over-read of the last words
-constexpr int WARP_SMEM = 128 + 2 * KEYBUF;  // per warp: 2 mbarriers (+ scratch) and a double-buffered key stage
+// Per warp: 128 bytes (2 mbarriers + scratch) and a double-buffered key stage.  The stage size is chosen per launch
+// from the batch's mean key length (ScanParams::keybuf): 18 B/record for the 16-byte-key benchmark, up to 128 B/record
+// for long keys, trading warps per SM for stage bytes when shared memory runs out.  A stage has 32 bytes of slack for
+// the (harmless, <= 23 byte) over-read of the last words.
+constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_SLACK = 32;
+__host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf) { return hash ? 128 + 2 * (size_t)keybuf : 128; }
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
@@ -62,6 +65,8 @@ struct ScanParams {
     int32_t P;
     int32_t hll_p;                   // HLL index bits (MODE_HLL)
     uint64_t stage_limit;            // bytes readable from key_bytes by 16-byte bulk copies; 0 = staging not allowed
+    int32_t keybuf;                  // bytes of one key stage (multiple of 16, incl. KEYBUF_SLACK)
+    int32_t pad0;
     unsigned long long *sums;        // [sums_words(P)]
     long long *minmax;               // [0] min raw ts_ms, [1] max raw ts_ms, [2] min size, [3] max size (as u64)
     uint32_t *hll;                   // [1 << hll_p] registers (one u32 each so that RED.MAX applies)
@@ -424,7 +429,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
     const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : CTA_SCRATCH;
     volatile uint32_t *s_floor = reinterpret_cast<volatile uint32_t *>(smem_raw + cta_bytes - CTA_SCRATCH);
-    unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * (HASH ? WARP_SMEM : 128);
+    const uint32_t KEYBUF = (uint32_t)prm.keybuf;
+    const size_t warp_bytes = warp_smem_bytes(HASH, prm.keybuf);
+    unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * warp_bytes;
     const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
     const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P};
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
         const uint64_t a0 = g0 & ~15ull;
         const uint64_t bytes = ((g1 - a0) + 15ull) & ~15ull;
-        const bool ok = g1 > g0 && bytes <= (uint64_t)KEYBUF_COPY && a0 + bytes <= prm.stage_limit;
+        const bool ok = g1 > g0 && bytes + KEYBUF_SLACK <= (uint64_t)KEYBUF && a0 + bytes <= prm.stage_limit;
         uint32_t info = (ok ? 1u : 0u) | ((uint32_t)(g0 & 15ull) << 1);
         if (ok) {
             mbar_arrive_expect_tx(mbar + 8u * b, (uint32_t)bytes);
@@ -614,7 +621,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             }
             const uint32_t kb = keybuf + (uint32_t)buf * KEYBUF;
 
-            if (info & 1u) {   // staged ⇒ the tile's keys total <= KEYBUF_COPY bytes ⇒ small
+            if (info & 1u) {   // staged ⇒ the tile's keys fit one stage (<= 16 KiB) ⇒ small
                 const uint32_t a0 = (info >> 1) & 15u;
                 mbar_wait(mbar + 8u * buf, (phase >> buf) & 1u);
                 phase ^= 1u << buf;
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < nwarps; w++) {
-            const long long *rw = reinterpret_cast<const long long *>(wsm + (size_t)w * (HASH ? WARP_SMEM : 128) + 64);
+            const long long *rw = reinterpret_cast<const long long *>(wsm + (size_t)w * warp_bytes + 64);
             tmin = rw[0] < tmin ? rw[0] : tmin;
             tmax = rw[1] > tmax ? rw[1] : tmax;
             smin64 = rw[2] < smin64 ? rw[2] : smin64;

@@ -121,7 +121,7 @@ def test_random_ragged_batches(seed):
         assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10))
 
 
-@pytest.mark.parametrize("L", [1, 9, 16, 17, 40])
+@pytest.mark.parametrize("L", [1, 9, 16, 17, 40, 100, 200])
 def test_fixed_width_keys(L):
     """Fixed-width keys of any length take the ballot-offset path (16-byte aligned ones the LDS.128 path)."""
     from kafka_topic_analyzer_b200.synth import HostTopic, tile_base_from_key_len
