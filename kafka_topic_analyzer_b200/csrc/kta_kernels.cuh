@@ -35,7 +35,7 @@ __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf) { retur
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
-constexpr int FOLD_TILES = 4;             // every warp checks the CTA's 16-bit-split sums every 4 of its tiles
+constexpr int FOLD_TILES = 64;            // the CTA's 16-bit-split sums are checked once per 64 tiles finished CTA-wide
 
 // shared-memory counter rows (each row = P u32 words):
 //   0..31 key-size buckets, 32 null keys | 33..64 value-size buckets, 65 tombstones |
@@ -47,7 +47,8 @@ enum ScanMode { MODE_COUNTERS = 0, MODE_HLL = 1, MODE_EXACT = 2 };
 
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
-// counter rows, then the CTA scratch: one 128-byte line (word 0: the CTA's cached copy of the HLL floor)
+// counter rows, then the CTA scratch: one 128-byte line (word 0: the CTA's cached copy of the HLL floor, word 1:
+// tiles finished CTA-wide)
 constexpr int CTA_SCRATCH = 128;
 __host__ __device__ inline size_t smem_counter_bytes(int P) { return (((size_t)P * SMEM_ROWS * 4 + 127) & ~(size_t)127) + CTA_SCRATCH; }
 
@@ -341,9 +342,11 @@ struct Counters {
         sums(p, kl, vl);
     }
     // One warp drains split sums that reached `threshold` into the global u64 sums; safe against concurrent
-    // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp checks every FOLD_TILES of
-    // its tiles, so between two checks of an entry each of the <= 32 warps adds fewer than 2*FOLD_TILES*128
-    // values < 2^16: growth < 32 * 1024 * 65535 < 2^31, and a word that passed a check was < 2^30.
+    // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp takes a ticket from a CTA-wide
+    // counter when it finishes a tile (after that tile's adds), and the warp that draws ticket 63 mod 64 runs the
+    // check.  Adds that reach a word between two consecutive examinations of it belong to tiles ticketed after the
+    // first check and no later than 31 tickets after the second (one tile in flight per other warp): at most 95
+    // tiles x 128 records x (2^16 - 1) < 2^30 — and a word that passed a check was < 2^30, so it stays < 2^31.
     __device__ __noinline__ void fold_sums(int lane, uint32_t threshold) const {
         if (!SMEM) return;
         for (int i = lane; i < 2 * P; i += 32) {
@@ -440,7 +443,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         const int nw = P * SMEM_ROWS;
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
     }
-    if (MODE == MODE_HLL && tid == 0) *s_floor = ld_cg_u32(prm.hll_floor);
+    if (tid == 0) {
+        s_floor[0] = MODE == MODE_HLL ? ld_cg_u32(prm.hll_floor) : 0u;
+        s_floor[1] = 0;   // CTA-wide count of finished tiles (fold tickets)
+    }
     if (HASH && lane == 0) {
         mbar_init(mbar, 1);
         mbar_init(mbar + 8, 1);
@@ -713,10 +719,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         const int64_t pt = phys(tile);
         if ((pt + 1) * TILE <= prm.n) body(std::true_type{}, pt, buf, info, has_next);
         else body(std::false_type{}, pt, buf, info, has_next);
-        if ((it & (FOLD_TILES - 1)) == FOLD_TILES - 1) {
-            if (SMEM) C.fold_sums(lane, 1u << 30);
-            try_uni = try_uni || (it & 15) == 15;   // re-probe now and then
+        if (SMEM) {
+            uint32_t ticket = 0;
+            if (lane == 0) ticket = atomicAdd(const_cast<uint32_t *>(s_floor) + 1, 1u);
+            if ((__shfl_sync(full, ticket, 0) & (FOLD_TILES - 1)) == FOLD_TILES - 1) C.fold_sums(lane, 1u << 30);
         }
+        try_uni = try_uni || (it & 15) == 15;   // re-probe for run-structured input now and then
         // HLL floor upkeep: every 4th tile ONE warp of each CTA (the role rotates, so no warp falls behind)
         // refreshes one slice — the 148 CTAs cover all 64 slices about every two tile-times — and republishes
         // the floor to its CTA through shared memory

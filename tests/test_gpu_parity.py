@@ -213,6 +213,26 @@ def test_reset_forgets_the_alive_table_in_o1():
         assert_parity(e, o, 8, check_alive=True, hll_regs=o.hll_alive_regs(10))
 
 
+def test_byte_sums_survive_u32_wraparound():
+    """16 M records of one partition with key_len 0x1ffff and value_len 0xffff: every CTA adds far more than 2^32 to
+    its 16-bit-split shared-memory sums, so the result is only exact if the fold logic drains them in time."""
+    import torch
+    n = 16_000_000
+    part = torch.zeros(n, dtype=torch.int32, device="cuda")
+    part[n // 2:] = 1
+    ts = torch.full((n,), 1_600_000_000_000, dtype=torch.int64, device="cuda")
+    kl = torch.full((n,), 0x1FFFF, dtype=torch.int32, device="cuda")
+    vl = torch.full((n,), 0xFFFF, dtype=torch.int32, device="cuda")
+    with KtaEngine(2, now=NOW) as e:
+        e.scan_batch_device(part, ts, kl, vl)
+        e.finalize()
+        mm = e.message_metrics
+        for p in (0, 1):
+            assert mm.total(p) == n // 2 and mm.key_size_sum(p) == (n // 2) * 0x1FFFF and mm.value_size_sum(p) == (n // 2) * 0xFFFF
+        assert mm.overall_size() == n * (0x1FFFF + 0xFFFF)
+        assert mm.largest_message() == 0x1FFFF + 0xFFFF == mm.smallest_message()
+
+
 def test_partition_out_of_range_is_an_error():
     with KtaEngine(2, now=NOW) as e:
         e.push(2, 0, 0, b"k", 1)
