@@ -253,6 +253,21 @@ def run_ours(a):
     ms, kern_avg_ms = t.tolist()
     value = n_total * a.steps / (ms / 1e3)
 
+    merge_ms = None
+    if world > 1:
+        # the merge alone (export kernel + ONE NCCL all-reduce + import kernel), 20 back-to-back calls
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for _ in range(20):
+            allreduce_merge(eng)
+        m1.record(stream)
+        barrier()
+        mt = torch.tensor([m0.elapsed_time(m1) / 20], dtype=torch.float64, device=dev)
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        merge_ms = mt.item()
+        step()   # leave the engine holding one clean, merged pass again
+
     # sanity: the result of the last step is the whole topic
     mm = eng.message_metrics
     assert mm.overall_count() == n_total, (mm.overall_count(), n_total)
@@ -283,6 +298,8 @@ def run_ours(a):
         "logical_topic_gb_s": value * (topic.key_bytes_len / n + a.value_mean) / 1e9,
         "gpu_launches": launches, "clocks": clocks,
     }
+    if merge_ms is not None:
+        line["merge_ms"] = merge_ms
 
     if rank == 0 and world == 1 and not a.no_extra:
         line["extra_modes"] = extra_modes(a, topic, kta, torch, dev, peak)

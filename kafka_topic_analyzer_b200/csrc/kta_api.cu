@@ -1060,7 +1060,7 @@ extern "C" int kta_set_hash_capture(kta_handle *h, uint32_t *dev_out) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int64_t kta_merge_words(const kta_handle *h, int32_t world) {
     if (!h || world < 1) return -1;
-    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * (h->nhll / 2));
+    return (int64_t)(h->nsums + (size_t)world * 4 + (size_t)world * (h->nhll / 8));
 }
 
 extern "C" int kta_merge_export_device(kta_handle *h, int32_t rank, int32_t world, uint64_t *dev_buf) {

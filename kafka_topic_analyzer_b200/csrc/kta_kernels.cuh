@@ -926,13 +926,13 @@ __global__ void fnv32_kernel(int64_t n, const int32_t *key_len, const uint64_t *
         out[i] = key_len[i] < 0 ? 0u : fnv_global(key_bytes + key_off[i], key_len[i]);
 }
 
-// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×(nhll/2) register words] ----
-// Every rank writes its min/max scalars and HLL registers into its own slot and zeros elsewhere, so ONE
-// SUM all-reduce over u64 delivers every rank's values to every rank; the import folds them.
+// ---- multi-GPU merge buffer (see kta.h): [sums | G×4 minmax slots | G×(nhll/8) register words] ----
+// Every rank writes its min/max scalars and HLL registers (one byte each, eight per word) into its own slot and
+// zeros elsewhere, so ONE SUM all-reduce over u64 delivers every rank's values to every rank; the import folds them.
 __global__ void merge_export_kernel(const unsigned long long *sums, size_t nsums, const long long *minmax,
                                     const uint32_t *hll, size_t nhll, int rank, int world, unsigned long long *buf) {
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nmm = (size_t)world * 4, hw = nhll / 2, total = nsums + nmm + (size_t)world * hw;
+    const size_t nmm = (size_t)world * 4, hw = nhll / 8, total = nsums + nmm + (size_t)world * hw;
     for (size_t i = t0; i < total; i += stride) {
         unsigned long long v = 0;
         if (i < nsums) v = sums[i];
@@ -941,7 +941,11 @@ __global__ void merge_export_kernel(const unsigned long long *sums, size_t nsums
             if ((int)(j / 4) == rank) v = (unsigned long long)minmax[j % 4];
         } else {
             const size_t j = i - nsums - nmm;
-            if ((int)(j / hw) == rank) v = reinterpret_cast<const unsigned long long *>(hll)[j % hw];
+            if ((int)(j / hw) == rank) {
+                const uint32_t *r = hll + (j % hw) * 8;
+#pragma unroll
+                for (int k = 0; k < 8; k++) v |= (unsigned long long)(r[k] & 0xffu) << (8 * k);
+            }
         }
         buf[i] = v;
     }
@@ -952,17 +956,12 @@ __global__ void merge_import_kernel(unsigned long long *sums, size_t nsums, long
     const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = t0; i < nsums; i += stride) sums[i] = buf[i];
     const unsigned long long *mm = buf + nsums;
-    const size_t hw = nhll / 2;
+    const size_t hw = nhll / 8;
     const unsigned long long *hb = mm + (size_t)world * 4;
-    for (size_t i = t0; i < hw; i += stride) {
-        unsigned long long m = 0;
-        for (int r = 0; r < world; r++) {
-            const unsigned long long v = hb[(size_t)r * hw + i];
-            const unsigned long long lo = max(m & 0xffffffffull, v & 0xffffffffull), hi = max(m >> 32, v >> 32);
-            const unsigned long long o = lo | (hi << 32);   // max of each 32-bit register
-            m = o;
-        }
-        reinterpret_cast<unsigned long long *>(hll)[i] = m;
+    for (size_t i = t0; i < nhll; i += stride) {
+        uint32_t m = 0;
+        for (int r = 0; r < world; r++) m = max(m, (uint32_t)(hb[(size_t)r * hw + i / 8] >> (8 * (i % 8))) & 0xffu);
+        hll[i] = m;
     }
     if (t0 == 0) {
         long long tmin = INT64_MAX, tmax = INT64_MIN;

@@ -53,11 +53,11 @@ def allreduce_merge(engine: KtaEngine, group=None) -> None:
 # ---------------------------------------------------------------------------------------------------
 # Host-side statement of the merge-buffer layout (what merge_export_kernel / merge_import_kernel do on the
 # device, csrc/kta_kernels.cuh).  Used by the gloo CPU tests of the N>1 logic and usable for host-side merges.
-#   [ sums (nsums u64) | world × 4 extrema slots | world × (nhll/2) words, two u32 registers per word ]
+#   [ sums (nsums u64) | world × 4 extrema slots | world × (nhll/8) words, eight one-byte registers per word ]
 # Every rank fills only its own slots, so ONE SUM all-reduce hands every rank's values to every rank.
 # ---------------------------------------------------------------------------------------------------
 def merge_words(nsums: int, nhll: int, world: int) -> int:
-    return nsums + world * 4 + world * (nhll // 2)
+    return nsums + world * 4 + world * (nhll // 8)
 
 
 def pack_merge_buffer(sums, minmax, hll, rank: int, world: int):
@@ -71,11 +71,10 @@ def pack_merge_buffer(sums, minmax, hll, rank: int, world: int):
     buf[nsums + 4 * rank + 2] = np.uint64(minmax[2])
     buf[nsums + 4 * rank + 3] = np.uint64(minmax[3])
     if nhll:
-        hw = nhll // 2
-        regs = np.asarray(hll, dtype=np.uint32)
-        words = regs[0::2].astype(np.uint64) | (regs[1::2].astype(np.uint64) << np.uint64(32))
+        hw = nhll // 8
+        regs = np.asarray(hll, dtype=np.uint8)
         o = nsums + 4 * world + rank * hw
-        buf[o:o + hw] = words
+        buf[o:o + hw] = regs.view(np.uint64) if regs.flags["C_CONTIGUOUS"] else np.ascontiguousarray(regs).view(np.uint64)
     return buf
 
 
@@ -89,9 +88,7 @@ def fold_merge_buffer(buf, nsums: int, nhll: int, world: int):
     smin, smax = int(mm[:, 2].min()), int(mm[:, 3].max())
     hll = np.zeros(nhll, dtype=np.uint32)
     if nhll:
-        hw = nhll // 2
-        w = buf[nsums + 4 * world:].reshape(world, hw)
-        lo = (w & np.uint64(0xFFFFFFFF)).max(axis=0).astype(np.uint32)
-        hi = (w >> np.uint64(32)).max(axis=0).astype(np.uint32)
-        hll[0::2], hll[1::2] = lo, hi
+        hw = nhll // 8
+        w = np.ascontiguousarray(buf[nsums + 4 * world:nsums + 4 * world + world * hw]).view(np.uint8).reshape(world, nhll)
+        hll[:] = w.max(axis=0)
     return sums, (tmin, tmax, smin, smax), hll
