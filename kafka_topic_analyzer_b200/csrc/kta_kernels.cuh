@@ -229,12 +229,23 @@ __device__ __forceinline__ uint32_t fnv_global(const uint8_t *key, int len) {
 // rho <= floor  ⇔  the top `floor` bits below the index bits are not all zero  ⇔  (x & skip_mask) != 0.
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t hll_mix(uint32_t h) {
+#ifdef __CUDA_ARCH__
+    // same function; the three right shifts ride the FMA pipe (mul.hi by 2^(32-s)) because the integer ALU pipe is
+    // the busiest pipe of the fused kernel
+    h ^= shr_fma(h, 1u << 16);
+    h *= 0x85ebca6bu;
+    h ^= shr_fma(h, 1u << 19);
+    h *= 0xc2b2ae35u;
+    h ^= shr_fma(h, 1u << 16);
+    return h;
+#else
     h ^= h >> 16;
     h *= 0x85ebca6bu;
     h ^= h >> 13;
     h *= 0xc2b2ae35u;
     h ^= h >> 16;
     return h;
+#endif
 }
 
 __device__ __forceinline__ uint32_t hll_skip_mask(int p, uint32_t floor) {

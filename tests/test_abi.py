@@ -72,3 +72,21 @@ def test_sass_has_bulk_copy_and_no_legacy_paths():
         pytest.skip("cuobjdump unavailable")
     assert "UBLKCP" in r.stdout and "SYNCS" in r.stdout and "ATOMS" in r.stdout
     assert "sm_100a" in r.stdout
+
+
+def test_abi_rejects_bad_arguments_without_cuda():
+    """Argument validation happens before any CUDA call, so it is checkable here (and never aborts the host)."""
+    L = lib()
+    h = C.c_void_p()
+    cfg = _native.Config()
+    cfg.struct_size = 12                      # wrong size: an ABI mismatch must be refused, not misread
+    assert L.kta_create(C.byref(cfg), C.byref(h)) == _native.ERR_INVALID and not h
+    assert b"struct_size" in L.kta_last_error()
+    assert L.kta_create(None, C.byref(h)) == _native.ERR_INVALID
+    out = C.c_uint64()
+    assert L.kta_counter(None, 0, 0, C.byref(out)) == _native.ERR_INVALID
+    assert L.kta_push(None, 0, 0, 0, None, -1, -1) == _native.ERR_INVALID
+    assert L.kta_destroy(None) == 0
+    assert L.kta_merge_words(None, 2) == -1
+    spec = _native.SynthSpec()
+    assert L.kta_synth_shard_records(C.byref(spec), 0, 1) == -1      # zero partitions
