@@ -739,7 +739,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         // HLL floor upkeep: every 4th tile ONE warp of each CTA (the role rotates, so no warp falls behind)
         // refreshes one slice — the 148 CTAs cover all 64 slices about every two tile-times — and republishes
         // the floor to its CTA through shared memory
-        if (MODE == MODE_HLL && (it & 3) == 3 && ((it >> 2) & 31) == (warp & 31)) {
+        // (plus two early refreshes after the first and second tile, so that a cold sketch stops taking every record)
+        if (MODE == MODE_HLL && (((it & 3) == 3 && ((it >> 2) & 31) == (warp & 31)) || (it < 2 && warp == it + 1))) {
             hll_refresh_slice(prm.hll, prm.hll_p, prm.hll_floor, (blockIdx.x + (uint32_t)(it >> 2) * 37u) & (HLL_SLICES - 1), lane);
             if (lane == 0) *s_floor = ld_cg_u32(prm.hll_floor);
         }
