@@ -193,6 +193,9 @@ int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t 
                                 const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out);
 /* raw bytes in host memory (e.g. an mmap of a .log file); returns when `bytes` may be reused */
 int kta_push_log_segment_host(kta_handle *h, int32_t partition, const uint8_t *bytes, int64_t len, int64_t *records_out);
+/* several segments (any partitions) in one go: one staging copy per segment, ONE decode and ONE scan for all of them */
+int kta_push_log_segments_host(kta_handle *h, int32_t nsegs, const int32_t *partitions, const uint8_t *const *bytes,
+                               const int64_t *lens, int64_t *records_out);
 
 /* ---- introspection for benchmarks ---- */
 /* kernels launched by this handle since create/reset, and device time of the scan kernels (ms,

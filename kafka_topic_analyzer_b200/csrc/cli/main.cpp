@@ -88,13 +88,26 @@ static int analyze_log_dir(const std::string &topic, const std::string &dir, boo
     KTA(kta_create(&cfg, &h));
     printf("Subscribing to %s\n", topic.c_str());
     printf("Starting message consumption...\n");
-    std::vector<uint8_t> buf;
     auto be64 = [](const uint8_t *p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | p[i]; return (int64_t)v; };
     auto be32 = [](const uint8_t *p) { return (int32_t)(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]); };
-    int64_t total = 0;
+    // segments are handed over in groups of up to 512 MiB: one staging copy each, one GPU decode + scan per group
+    std::vector<std::vector<uint8_t>> bufs;
+    std::vector<int32_t> parts;
+    int64_t total = 0, pending = 0;
+    auto flush = [&]() {
+        if (bufs.empty()) return;
+        std::vector<const uint8_t *> ptrs;
+        std::vector<int64_t> lens;
+        for (auto &b : bufs) { ptrs.push_back(b.data()); lens.push_back((int64_t)b.size()); }
+        int64_t nrec = 0;
+        KTA(kta_push_log_segments_host(h, (int32_t)bufs.size(), parts.data(), ptrs.data(), lens.data(), &nrec));
+        total += nrec;
+        bufs.clear(); parts.clear(); pending = 0;
+    };
     for (auto &kv : segs) {
         bool first = true;
         for (const auto &path : kv.second) {
+            std::vector<uint8_t> buf;
             if (!read_file(path, buf)) { fprintf(stderr, "cannot read %s\n", path.c_str()); return 1; }
             for (int64_t pos = 0; pos + 61 <= (int64_t)buf.size();) {
                 const int64_t bl = be32(buf.data() + pos + 8);
@@ -103,11 +116,13 @@ static int analyze_log_dir(const std::string &topic, const std::string &dir, boo
                 end_offsets[kv.first] = be64(buf.data() + pos) + be32(buf.data() + pos + 23) + 1;
                 pos += 12 + bl;
             }
-            int64_t nrec = 0;
-            KTA(kta_push_log_segment_host(h, kv.first, buf.data(), (int64_t)buf.size(), &nrec));
-            total += nrec;
+            pending += (int64_t)buf.size();
+            parts.push_back(kv.first);
+            bufs.push_back(std::move(buf));
+            if (pending >= ((int64_t)512 << 20)) flush();
         }
     }
+    flush();
     if (std::all_of(end_offsets.begin(), end_offsets.end(), [](int64_t v) { return v == 0; })) {
         fprintf(stderr, "Given topic has no content, no analysis possible. Exiting.\n");  // main.rs:98-101
         return 254;

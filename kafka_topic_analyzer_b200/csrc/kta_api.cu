@@ -461,8 +461,8 @@ static int grow(T *&ptr, int64_t &cap, int64_t need, cudaStream_t s) {
     return KTA_OK;
 }
 
-extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
-                                           const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
+static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev_batch_partition, const uint8_t *dev_bytes,
+                            int64_t len, const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
     if (!h || len < 0 || nbatches < 0 || (nbatches && (!dev_bytes || !dev_batch_off))) return fail(KTA_ERR_INVALID, "bad argument");
     if (records_out) *records_out = 0;
     if (nbatches == 0) return KTA_OK;
@@ -483,8 +483,8 @@ extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, con
     if (!h->d_log_err) CU(cudaMalloc(&h->d_log_err, 4));
     CU(cudaMemsetAsync(h->d_log_err, 0, 4, s));
     const int grid = (int)std::min<int64_t>((nbatches + 127) / 128, (int64_t)h->sm_count * 16);
-    log_header_kernel<<<grid, 128, 0, s>>>(dev_bytes, len, dev_batch_off, nbatches, partition, h->d_log_info, h->d_log_cnt,
-                                            h->d_log_err);
+    log_header_kernel<<<grid, 128, 0, s>>>(dev_bytes, len, dev_batch_off, nbatches, partition, dev_batch_partition, h->d_log_info,
+                                            h->d_log_cnt, h->d_log_err);
     tile_base_scan_kernel<<<1, 1024, 0, s>>>(h->d_log_cnt, nbatches);   // inclusive scan of [1..nbatches] in place
     CU(cudaGetLastError());
     h->launches += 2;
@@ -540,34 +540,60 @@ extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, con
     return KTA_OK;
 }
 
-extern "C" int kta_push_log_segment_host(kta_handle *h, int32_t partition, const uint8_t *bytes, int64_t len,
-                                         int64_t *records_out) {
-    if (!h || len < 0 || (len && !bytes)) return fail(KTA_ERR_INVALID, "bad argument");
+extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
+                                           const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
+    return scan_log_batches(h, partition, nullptr, dev_bytes, len, dev_batch_off, nbatches, records_out);
+}
+
+extern "C" int kta_push_log_segments_host(kta_handle *h, int32_t nsegs, const int32_t *partitions, const uint8_t *const *bytes,
+                                          const int64_t *lens, int64_t *records_out) {
+    if (!h || nsegs < 0 || (nsegs && (!partitions || !bytes || !lens))) return fail(KTA_ERR_INVALID, "bad argument");
     if (records_out) *records_out = 0;
     // hop from batch header to batch header on the host (12 + batchLength bytes each); a truncated tail is ignored,
-    // as a consumer would ignore a partially fetched batch
+    // as a consumer would ignore a partially fetched batch.  All segments go to ONE staging buffer and are decoded
+    // and scanned together (one decode, one scan, two host round trips in total).
     std::vector<uint64_t> offs;
-    int64_t pos = 0;
-    while (pos + LOG_HEADER_BYTES <= len) {
-        const uint8_t *p = bytes + pos;
-        const int64_t bl = (int64_t)(int32_t)(((uint32_t)p[8] << 24) | ((uint32_t)p[9] << 16) | ((uint32_t)p[10] << 8) | p[11]);
-        if (bl < LOG_HEADER_BYTES - 12 || pos + 12 + bl > len) break;
-        offs.push_back((uint64_t)pos);
-        pos += 12 + bl;
+    std::vector<int32_t> parts;
+    std::vector<int64_t> used((size_t)nsegs, 0), base((size_t)nsegs, 0);
+    int64_t total = 0;
+    for (int32_t sgi = 0; sgi < nsegs; sgi++) {
+        if (lens[sgi] < 0 || (lens[sgi] && !bytes[sgi])) return fail(KTA_ERR_INVALID, "bad segment %d", sgi);
+        base[(size_t)sgi] = total;
+        int64_t pos = 0;
+        while (pos + LOG_HEADER_BYTES <= lens[sgi]) {
+            const uint8_t *p = bytes[sgi] + pos;
+            const int64_t bl = (int64_t)(int32_t)(((uint32_t)p[8] << 24) | ((uint32_t)p[9] << 16) | ((uint32_t)p[10] << 8) | p[11]);
+            if (bl < LOG_HEADER_BYTES - 12 || pos + 12 + bl > lens[sgi]) break;
+            offs.push_back((uint64_t)(total + pos));
+            parts.push_back(partitions[sgi]);
+            pos += 12 + bl;
+        }
+        used[(size_t)sgi] = pos;
+        total += (pos + 15) & ~(int64_t)15;
     }
     if (offs.empty()) return KTA_OK;
     int rc;
     if ((rc = set_device(h))) return rc;
     cudaStream_t s = h->stream;
-    if ((rc = grow(h->d_log_bytes, h->log_bytes_cap, pos + 64, s))) return rc;
+    if ((rc = grow(h->d_log_bytes, h->log_bytes_cap, total + 64, s))) return rc;
+    CU(cudaStreamSynchronize(s));
     cudaFree(h->d_log_off);
     h->d_log_off = nullptr;
-    CU(cudaMalloc(&h->d_log_off, offs.size() * 8));
-    CU(cudaMemcpyAsync(h->d_log_bytes, bytes, (size_t)pos, cudaMemcpyHostToDevice, s));
+    CU(cudaMalloc(&h->d_log_off, offs.size() * 12));
+    int32_t *d_parts = reinterpret_cast<int32_t *>(h->d_log_off + offs.size());
+    for (int32_t sgi = 0; sgi < nsegs; sgi++)
+        if (used[(size_t)sgi])
+            CU(cudaMemcpyAsync(h->d_log_bytes + base[(size_t)sgi], bytes[sgi], (size_t)used[(size_t)sgi], cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->d_log_off, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, s));
-    if ((rc = kta_scan_log_segment_device(h, partition, h->d_log_bytes, pos, h->d_log_off, (int64_t)offs.size(), records_out))) return rc;
-    CU(cudaStreamSynchronize(s));   // the caller may reuse `bytes`, and the scratch may be reused by the next segment
+    CU(cudaMemcpyAsync(d_parts, parts.data(), parts.size() * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = scan_log_batches(h, 0, d_parts, h->d_log_bytes, total, h->d_log_off, (int64_t)offs.size(), records_out))) return rc;
+    CU(cudaStreamSynchronize(s));   // the caller may reuse its buffers, and the scratch may be reused by the next call
     return collect_timing(h);
+}
+
+extern "C" int kta_push_log_segment_host(kta_handle *h, int32_t partition, const uint8_t *bytes, int64_t len,
+                                         int64_t *records_out) {
+    return kta_push_log_segments_host(h, 1, &partition, &bytes, &len, records_out);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -64,12 +64,12 @@ struct LogBatchInfo {      // one per record batch, filled by log_header_kernel
 
 // thread per batch: validate + read the header
 __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const uint64_t *batch_off, int64_t nbatches,
-                                  int32_t partition, LogBatchInfo *info, uint64_t *rec_count /*[nbatches+1], [b+1]*/,
-                                  uint32_t *error_flags) {
+                                  int32_t partition, const int32_t *batch_partition /* per batch, or NULL = `partition` */,
+                                  LogBatchInfo *info, uint64_t *rec_count /*[nbatches+1], [b+1]*/, uint32_t *error_flags) {
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbatches; b += (int64_t)gridDim.x * blockDim.x) {
         LogBatchInfo bi{};
         bi.off = batch_off[b];
-        bi.partition = partition;
+        bi.partition = batch_partition ? batch_partition[b] : partition;
         bi.flags = LOGB_BAD;
         if (bi.off + LOG_HEADER_BYTES <= (uint64_t)nbytes) {
             const uint8_t *p = bytes + bi.off;

@@ -149,6 +149,17 @@ class KtaEngine:
         check(lib().kta_push_log_segment_host(self._h, partition, buf.ctypes.data, buf.size, C.byref(n)))
         return n.value
 
+    def push_log_segments(self, segments) -> int:
+        """segments: iterable of (partition, bytes-like).  One decode + one scan for all of them."""
+        segs = [(int(p), np.frombuffer(d, dtype=np.uint8) if not isinstance(d, np.ndarray) else d) for p, d in segments]
+        k = len(segs)
+        parts = (C.c_int32 * k)(*[p for p, _ in segs])
+        ptrs = (C.c_void_p * k)(*[d.ctypes.data for _, d in segs])
+        lens = (C.c_int64 * k)(*[d.size for _, d in segs])
+        n = C.c_int64()
+        check(lib().kta_push_log_segments_host(self._h, k, parts, ptrs, lens, C.byref(n)))
+        return n.value
+
     def sync(self) -> None:
         check(lib().kta_sync(self._h))
         self._keep = []

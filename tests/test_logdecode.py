@@ -201,3 +201,13 @@ def test_synthetic_topic_as_log_segments_full_path():
             assert e.push_log_segment(p, synth.encode_segment(spec, p, batch_records=200)) == t.n
         e.finalize()
         assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(11))
+        # the same topic again, all partitions (two segments each) in ONE call
+        e.reset()
+        half = spec.n_total // P // 2
+        segs = []
+        for p in range(P):
+            segs.append((p, synth.encode_segment(spec, p, 0, half, batch_records=57)))
+            segs.append((p, synth.encode_segment(spec, p, half, None, batch_records=57)))
+        assert e.push_log_segments(segs) == spec.n_total
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(11))

@@ -34,7 +34,7 @@ for mode, kw in (("counters", {}), ("fused HLL", dict(hll_precision=14)), ("-c e
         for p in range(P):
             check(lib().kta_scan_log_segment_device(e.handle, p, segs[p].data_ptr(), segs[p].numel(), offs[p].data_ptr(),
                                                     offs[p].numel(), C.byref(n)))
-            tot += n.value
+            tot += n.value   # (one call per segment: three small host round trips each)
         e.finalize()
         best = min(best, time.perf_counter() - t0)
     assert tot == N and e.message_metrics.overall_count() == N
