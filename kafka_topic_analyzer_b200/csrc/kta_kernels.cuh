@@ -294,7 +294,7 @@ __device__ __noinline__ void hll_refresh_slice(const uint32_t *regs, int p, uint
 //
 // SMEM = true: CTA-private u32 rows in shared memory (layout above), updated with RED.SHARED (no return
 // value, nothing to wait for), branch-free per record.  64-bit byte sums are kept as two u32 words —
-// Σ(len & 0xffff) and Σ(len >> 16) — that every warp checks every FOLD_TILES of its tiles and drains into
+// Σ(len & 0xffff) and Σ(len >> 16) — that are checked once per FOLD_TILES tiles finished CTA-wide and drained into
 // the global u64 sums with an atomic exchange before they can overflow (exact).
 // SMEM = false: straight 64-bit global atomics (P too large for shared memory).
 // ------------------------------------------------------------------------------------------------
@@ -359,14 +359,15 @@ struct Counters {
     // first check and no later than 31 tickets after the second (one tile in flight per other warp): at most 95
     // tiles x 128 records x (2^16 - 1) < 2^30 — and a word that passed a check was < 2^30, so it stays < 2^31.
     __device__ __noinline__ void fold_sums(int lane, uint32_t threshold) const {
-        if (!SMEM) return;
-        for (int i = lane; i < 2 * P; i += 32) {
-            const int which = i >= P, p = which ? i - P : i;
-            uint32_t *lo = &s[(ROW_KSUM + 2 * which) * P + p];
-            if (*(volatile uint32_t *)lo >= threshold || *(volatile uint32_t *)(lo + P) >= threshold) {
-                const unsigned long long v = (unsigned long long)atomicExch(lo, 0u) +
-                                             ((unsigned long long)atomicExch(lo + P, 0u) << 16);
-                if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], v);
+        if constexpr (SMEM) {
+            for (int i = lane; i < 2 * P; i += 32) {
+                const int which = i >= P, p = which ? i - P : i;
+                uint32_t *lo = &s[(ROW_KSUM + 2 * which) * P + p];
+                if (*(volatile uint32_t *)lo >= threshold || *(volatile uint32_t *)(lo + P) >= threshold) {
+                    const unsigned long long v = (unsigned long long)atomicExch(lo, 0u) +
+                                                 ((unsigned long long)atomicExch(lo + P, 0u) << 16);
+                    if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], v);
+                }
             }
         }
     }
