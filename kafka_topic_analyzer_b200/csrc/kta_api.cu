@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -150,9 +151,13 @@ static void scan_shape(const kta_handle *h, bool hash, int64_t n, int64_t key_by
         keybuf = (keybuf + 15) / 16 * 16;
     }
     const int P = h->cfg.num_partitions;
+    // Leave the SM some L1: the header loads stream through it, and with (almost) all 228 KB carved out as shared
+    // memory the loads in flight are throttled (measured at P = 256).  KTA_SCAN_L1_RESERVE (bytes) is a tuning knob.
+    static const size_t l1_reserve = [] { const char *e = getenv("KTA_SCAN_L1_RESERVE"); return e ? (size_t)atoll(e) : (size_t)0; }();
+    const size_t budget = h->smem_optin > l1_reserve ? h->smem_optin - l1_reserve : h->smem_optin;
     for (threads = MAX_THREADS;; threads -= 128) {
         smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf);
-        if (smem <= h->smem_optin || threads <= 256) break;
+        if (smem <= budget || threads <= 256) break;
     }
     if (smem > h->smem_optin) {   // still too big with 8 warps: fall back to the smallest stage (long keys go through global)
         keybuf = KEYBUF_MIN;
