@@ -529,16 +529,39 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 for (int k = 0; k < ROWS; k++) {
                     C.buckets(p[k], kl[k], vl[k]);
                     const int p0 = __shfl_sync(full, p[k], 0);
-                    if (__all_sync(full, p[k] == p0 && (kl[k] | vl[k]) < (1 << 26))) {
-                        const uint32_t ks = __reduce_add_sync(full, (uint32_t)max(kl[k], 0));   // each < 2^26: no overflow
-                        const uint32_t vs = __reduce_add_sync(full, (uint32_t)max(vl[k], 0));
+                    const unsigned m0 = __ballot_sync(full, p[k] == p0);
+                    const bool small_row = __all_sync(full, (kl[k] | vl[k]) < (1 << 26));
+                    const uint32_t kv = (uint32_t)max(kl[k], 0), vv = (uint32_t)max(vl[k], 0);
+                    if (m0 == full && small_row) {
+                        const uint32_t ks = __reduce_add_sync(full, kv);   // each < 2^26: no overflow
+                        const uint32_t vs = __reduce_add_sync(full, vv);
                         if (lane == 0) {
                             C.sum_add(0, p0, ks);
                             C.sum_add(1, p0, vs);
                         }
                         any_uni = true;
                     } else {
-                        C.sums(p[k], kl[k], vl[k]);
+                        // a row that straddles a run boundary holds two partitions: left to per-lane adds, its two
+                        // counters would be hit 32 times each, serialised in the shared-memory pipe (measured: +0.09 ms
+                        // at run length 500).  Reduce the two groups separately instead.
+                        const int l1 = __ffs(~m0) - 1;                     // first lane of the second group
+                        const int p1 = __shfl_sync(full, p[k], l1 & 31);
+                        const unsigned m1 = __ballot_sync(full, p[k] == p1);
+                        if (small_row && (m0 | m1) == full) {
+                            const bool in0 = (m0 >> lane) & 1u;
+                            const uint32_t ks0 = __reduce_add_sync(full, in0 ? kv : 0u), vs0 = __reduce_add_sync(full, in0 ? vv : 0u);
+                            const uint32_t ks1 = __reduce_add_sync(full, in0 ? 0u : kv), vs1 = __reduce_add_sync(full, in0 ? 0u : vv);
+                            if (lane == 0) {
+                                C.sum_add(0, p0, ks0);
+                                C.sum_add(1, p0, vs0);
+                            } else if (lane == l1) {
+                                C.sum_add(0, p1, ks1);
+                                C.sum_add(1, p1, vs1);
+                            }
+                            any_uni = true;
+                        } else {
+                            C.sums(p[k], kl[k], vl[k]);
+                        }
                     }
                 }
                 try_uni = any_uni;
