@@ -357,7 +357,7 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int6
     if (mode != MODE_COUNTERS) {
         if (!prm.key_tile_base) return fail(KTA_ERR_INVALID, "internal: key_tile_base missing");
         if (!prm.key_bytes && key_readable > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL but keys are required");
-        prm.stage_limit = (((uintptr_t)prm.key_bytes & 15u) == 0) ? (uint64_t)key_readable : 0;
+        prm.stage_limit = (((uintptr_t)prm.key_bytes & 15u) == 0) ? ((uint64_t)key_readable & ~15ull) : 0;
     }
     const int variant = mode + (capture ? 2 : 0);
     int threads = 0, keybuf = 0;

@@ -35,7 +35,7 @@ __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf) { retur
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
-constexpr int FOLD_TILES = 64;            // the CTA's 16-bit-split sums are checked once per 64 tiles finished CTA-wide
+constexpr int FOLD_TILES = 8;             // every warp checks the CTA's 16-bit-split sums after every 8th tile of its own
 
 // shared-memory counter rows (each row = P u32 words):
 //   0..31 key-size buckets, 32 null keys | 33..64 value-size buckets, 65 tombstones |
@@ -65,7 +65,7 @@ struct ScanParams {
     int64_t ntiles;
     int32_t P;
     int32_t hll_p;                   // HLL index bits (MODE_HLL)
-    uint64_t stage_limit;            // bytes readable from key_bytes by 16-byte bulk copies; 0 = staging not allowed
+    uint64_t stage_limit;            // bytes readable from key_bytes by 16-byte bulk copies, rounded DOWN to 16; 0 = staging not allowed
     int32_t keybuf;                  // bytes of one key stage (multiple of 16, incl. KEYBUF_SLACK)
     int32_t pad0;
     unsigned long long *sums;        // [sums_words(P)]
@@ -123,6 +123,16 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 // [addr] += v unless v == 0, as ONE predicated instruction (no branch, no reconvergence bookkeeping)
+__device__ __forceinline__ uint32_t hi32(long long v) {   // the high word, without a 64-bit shift the compiler then carries around
+    uint32_t hi;
+    asm("{ .reg .b32 lo; mov.b64 {lo, %0}, %1; }" : "=r"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ long long pack64(uint32_t lo, uint32_t hi) {
+    long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
 __device__ __forceinline__ void red_shared_add_nz(uint32_t addr, uint32_t v) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], %1; }" ::"r"(addr), "r"(v) : "memory");
 }
@@ -294,7 +304,7 @@ __device__ __noinline__ void hll_refresh_slice(const uint32_t *regs, int p, uint
 //
 // SMEM = true: CTA-private u32 rows in shared memory (layout above), updated with RED.SHARED (no return
 // value, nothing to wait for), branch-free per record.  64-bit byte sums are kept as two u32 words —
-// Σ(len & 0xffff) and Σ(len >> 16) — that are checked once per FOLD_TILES tiles finished CTA-wide and drained into
+// Σ(len & 0xffff) and Σ(len >> 16) — that every warp checks after every FOLD_TILES-th tile of its own and drains into
 // the global u64 sums with an atomic exchange before they can overflow (exact).
 // SMEM = false: straight 64-bit global atomics (P too large for shared memory).
 // ------------------------------------------------------------------------------------------------
@@ -352,12 +362,43 @@ struct Counters {
         buckets(p, kl, vl);
         sums(p, kl, vl);
     }
+    // the four records of one lane.  When every length of the lane fits 16 bits (one OR chain and one branch for
+    // the lane's eight lengths) the high halves are zero and the low half IS the length: two adds per record
+    // instead of two adds, two shifts, two masks and two guarded adds.
+    __device__ __forceinline__ void record_rows(const int (&p)[ROWS], const int (&kl)[ROWS], const int (&vl)[ROWS]) const {
+        if (SMEM) {
+            uint32_t ks[ROWS], vs[ROWS], any = 0;
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                ks[k] = (uint32_t)max(kl[k], 0);
+                vs[k] = (uint32_t)max(vl[k], 0);
+                any |= ks[k] | vs[k];
+                buckets(p[k], kl[k], vl[k]);
+            }
+            if (any < 0x10000u) {
+                const uint32_t P4 = 4u * (uint32_t)P;
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    const uint32_t pa = sbase + 4u * (uint32_t)p[k];
+                    red_shared_add(pa + ROW_KSUM * P4, ks[k]);
+                    red_shared_add(pa + ROW_VSUM * P4, vs[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) sums(p[k], kl[k], vl[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) record(p[k], kl[k], vl[k]);
+        }
+    }
     // One warp drains split sums that reached `threshold` into the global u64 sums; safe against concurrent
-    // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp takes a ticket from a CTA-wide
-    // counter when it finishes a tile (after that tile's adds), and the warp that draws ticket 63 mod 64 runs the
-    // check.  Adds that reach a word between two consecutive examinations of it belong to tiles ticketed after the
-    // first check and no later than 31 tickets after the second (one tile in flight per other warp): at most 95
-    // tiles x 128 records x (2^16 - 1) < 2^30 — and a word that passed a check was < 2^30, so it stays < 2^31.
+    // adds (atomicExch takes exactly what it zeroes).  Overflow bound: every warp runs the check after every
+    // FOLD_TILES-th tile of its own (after that tile's adds; no CTA-wide counter, no synchronisation).  Take two
+    // consecutive examinations of a word, by whichever warps: after the first, each warp reaches its own next check
+    // within FOLD_TILES tiles, so until the second one every warp has finished fewer than FOLD_TILES tiles and has
+    // at most one more in flight: at most 32 x 9 tiles x 128 records x (2^16 - 1) < 2.42e9 is added to a word that
+    // was < 2^30 after the first examination — it stays below 3.5e9 < 2^32.
     __device__ __noinline__ void fold_sums(int lane, uint32_t threshold) const {
         if constexpr (SMEM) {
             for (int i = lane; i < 2 * P; i += 32) {
@@ -457,7 +498,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     }
     if (tid == 0) {
         s_floor[0] = MODE == MODE_HLL ? ld_cg_u32(prm.hll_floor) : 0u;
-        s_floor[1] = 0;   // CTA-wide count of finished tiles (fold tickets)
     }
     if (HASH && lane == 0) {
         mbar_init(mbar, 1);
@@ -470,15 +510,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     // Returns the span descriptor: bit 0 staged, bits 1..4 = first key's offset inside its 16-byte line.
     auto issue = [&](int64_t tile, int b) -> uint32_t {
         const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
-        const uint64_t a0 = g0 & ~15ull;
-        const uint64_t bytes = ((g1 - a0) + 15ull) & ~15ull;
-        const bool ok = g1 > g0 && bytes + KEYBUF_SLACK <= (uint64_t)KEYBUF && a0 + bytes <= prm.stage_limit;
-        uint32_t info = (ok ? 1u : 0u) | ((uint32_t)(g0 & 15ull) << 1);
+        const uint32_t a = (uint32_t)g0 & 15u;
+        // the copy covers [g0 - a, roundup16(g1)).  Staged iff the tile has key bytes, the copy fits the stage
+        // (KEYBUF and the slack are multiples of 16, so roundup16(g1 - g0 + a) + slack <= KEYBUF ⇔ g1 - g0 <= cap - a)
+        // and it ends inside the readable bytes (stage_limit is a multiple of 16, so roundup16(g1) <= limit ⇔ g1 <= limit)
+        const bool ok = (g1 - g0) - 1ull < (uint64_t)(KEYBUF - (uint32_t)KEYBUF_SLACK - a) && g1 <= prm.stage_limit;
         if (ok) {
-            mbar_arrive_expect_tx(mbar + 8u * b, (uint32_t)bytes);
-            bulk_g2s(keybuf + (uint32_t)b * KEYBUF, prm.key_bytes + a0, (uint32_t)bytes, mbar + 8u * b);
+            const uint32_t bytes = ((uint32_t)(g1 - g0) + a + 15u) & ~15u;
+            mbar_arrive_expect_tx(mbar + 8u * b, bytes);
+            bulk_g2s(keybuf + (uint32_t)b * KEYBUF, prm.key_bytes + (g0 - a), bytes, mbar + 8u * b);
         }
-        return info;
+        return (ok ? 1u : 0u) | (a << 1);
     };
 
     long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
@@ -566,8 +608,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 }
                 try_uni = any_uni;
             } else {
-#pragma unroll
-                for (int k = 0; k < ROWS; k++) C.record(p[k], kl[k], vl[k]);
+                C.record_rows(p, kl, vl);
             }
         } else {
             // tail tile, or a record with a partition outside [0, P): per-record checks
@@ -579,13 +620,36 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 }
             }
         }
+        // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back: the raw
+        // extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps).
+        // Timestamps of one topic share their high word for 49 days at a time: when the lane's four and its running
+        // extrema do, the signed 64-bit order is the unsigned order of the low words (2 + 2 three-input min/max).
+        bool ts_fast = false;
+        if (FULL) {
+            const uint32_t hw = hi32(tmin);
+            uint32_t x = hi32(tmax) ^ hw;
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) x |= hi32(ts[k]) ^ hw;
+            ts_fast = x == 0;
+        }
+        if (ts_fast) {
+            const uint32_t hw = hi32(tmin);
+            const uint32_t l0 = (uint32_t)ts[0], l1 = (uint32_t)ts[1], l2 = (uint32_t)ts[2], l3 = (uint32_t)ts[3];
+            const uint32_t lo = min(min(min(l0, l1), l2), min(l3, (uint32_t)tmin));
+            const uint32_t hi = max(max(max(l0, l1), l2), max(l3, (uint32_t)tmax));
+            tmin = pack64(lo, hw);
+            tmax = pack64(hi, hw);
+        } else {
+            asm volatile("");   // keep this a real branch: if-converted, the 64-bit chain runs every tile
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                tmin = ts[k] < tmin ? ts[k] : tmin;
+                const long long tm = (FULL || valid[k]) ? ts[k] : INT64_MIN;
+                tmax = tm > tmax ? tm : tmax;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
-            // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back: the raw
-            // extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps)
-            tmin = ts[k] < tmin ? ts[k] : tmin;
-            const long long tm = (FULL || valid[k]) ? ts[k] : INT64_MIN;
-            tmax = tm > tmax ? tm : tmax;
             // metric.rs:249-251: size extrema, not for tombstones (invalid rows carry vl = -1)
             const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
             if (vl[k] >= 0) {
@@ -598,19 +662,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
             uint32_t off[ROWS];
             uint32_t h[ROWS];
-            // do all keys of this tile that are not null have ONE length L?  (kl ^ L) & ~(kl >> 31) is 0 for null and L
-            int lmax = kl[0];
-            bool small = true;
-#pragma unroll
-            for (int k = 1; k < ROWS; k++) lmax = max(lmax, kl[k]);
+            // do all keys of this tile that are not null have ONE length L?  L = the longest; read as unsigned, null (-1)
+            // is the largest value, so the unsigned minimum is the shortest non-null key (or "null" if there is none):
+            // one length ⇔ the two agree.  Two three-input min/max per lane and two warp reductions.
+            const int lmax = max(max(kl[0], kl[1]), max(kl[2], kl[3]));
+            const uint32_t lmin = min(min((uint32_t)kl[0], (uint32_t)kl[1]), min((uint32_t)kl[2], (uint32_t)kl[3]));
+            static_assert(ROWS == 4, "written out for four rows");
             const int L = __reduce_max_sync(full, lmax);   // -1 when every key is null
-            uint32_t odd = 0;
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                odd |= ((uint32_t)kl[k] ^ (uint32_t)L) & ~(uint32_t)(kl[k] >> 31);
-                small = small && kl[k] < (1 << 20);
-            }
-            const bool fixL = __all_sync(full, odd == 0) && L < (1 << 16);
+            const bool fixL = __reduce_min_sync(full, lmin) == (uint32_t)L && L < (1 << 16);
+            const bool small = L < (1 << 20);              // warp-uniform
             const bool fix16 = fixL && L == 16;
             if (fixL) {
                 // fixed-width keys (the common case: ids, hashes, UUIDs): offsets from ballots, no shuffle scan
@@ -623,7 +683,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                     before += __popc(m);
                 }
             } else {
-                small = __all_sync(full, small);
                 static_assert(ROWS == 4, "the packed scan below handles exactly four rows");
                 uint32_t mxl = 0;
 #pragma unroll
@@ -754,11 +813,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         const int64_t pt = phys(tile);
         if ((pt + 1) * TILE <= prm.n) body(std::true_type{}, pt, buf, info, has_next);
         else body(std::false_type{}, pt, buf, info, has_next);
-        if (SMEM) {
-            uint32_t ticket = 0;
-            if (lane == 0) ticket = atomicAdd(const_cast<uint32_t *>(s_floor) + 1, 1u);
-            if ((__shfl_sync(full, ticket, 0) & (FOLD_TILES - 1)) == FOLD_TILES - 1) C.fold_sums(lane, 1u << 30);
-        }
+        // every warp examines the CTA's split sums after every 8th tile of its own (bound: see fold_sums)
+        if (SMEM && (it & (FOLD_TILES - 1)) == FOLD_TILES - 1) C.fold_sums(lane, 1u << 30);
         try_uni = try_uni || (it & 15) == 15;   // re-probe for run-structured input now and then
         // HLL floor upkeep: every 4th tile ONE warp of each CTA (the role rotates, so no warp falls behind)
         // refreshes one slice — the 148 CTAs cover all 64 slices about every two tile-times — and republishes

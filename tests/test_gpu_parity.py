@@ -213,24 +213,61 @@ def test_reset_forgets_the_alive_table_in_o1():
         assert_parity(e, o, 8, check_alive=True, hll_regs=o.hll_alive_regs(10))
 
 
-def test_byte_sums_survive_u32_wraparound():
-    """16 M records of one partition with key_len 0x1ffff and value_len 0xffff: every CTA adds far more than 2^32 to
-    its 16-bit-split shared-memory sums, so the result is only exact if the fold logic drains them in time."""
+@pytest.mark.parametrize("layout", ["runs", "interleaved"])
+def test_byte_sums_survive_u32_wraparound(layout):
+    """Every CTA adds far more than 2^32 to its 16-bit-split shared-memory sums, so the result is only exact if the
+    fold logic drains them in time.  "runs": two long runs, lengths 0x1ffff / 0xffff (warp-reduced rows, high halves in
+    use).  "interleaved": three partitions round-robin, every length 0xffff (the per-lane path whose fast branch adds
+    the whole length to the low word: the largest value that branch can add, 48 M times)."""
     import torch
-    n = 16_000_000
-    part = torch.zeros(n, dtype=torch.int32, device="cuda")
-    part[n // 2:] = 1
+    if layout == "runs":
+        n, P, klv, vlv = 16_000_000, 2, 0x1FFFF, 0xFFFF
+        part = torch.zeros(n, dtype=torch.int32, device="cuda")
+        part[n // 2:] = 1
+    else:
+        n, P, klv, vlv = 48_000_000, 3, 0xFFFF, 0xFFFF
+        part = (torch.arange(n, dtype=torch.int64, device="cuda") % 3).to(torch.int32)
     ts = torch.full((n,), 1_600_000_000_000, dtype=torch.int64, device="cuda")
-    kl = torch.full((n,), 0x1FFFF, dtype=torch.int32, device="cuda")
-    vl = torch.full((n,), 0xFFFF, dtype=torch.int32, device="cuda")
-    with KtaEngine(2, now=NOW) as e:
+    kl = torch.full((n,), klv, dtype=torch.int32, device="cuda")
+    vl = torch.full((n,), vlv, dtype=torch.int32, device="cuda")
+    with KtaEngine(P, now=NOW) as e:
         e.scan_batch_device(part, ts, kl, vl)
         e.finalize()
         mm = e.message_metrics
-        for p in (0, 1):
-            assert mm.total(p) == n // 2 and mm.key_size_sum(p) == (n // 2) * 0x1FFFF and mm.value_size_sum(p) == (n // 2) * 0xFFFF
-        assert mm.overall_size() == n * (0x1FFFF + 0xFFFF)
-        assert mm.largest_message() == 0x1FFFF + 0xFFFF == mm.smallest_message()
+        for p in range(P):
+            assert mm.total(p) == n // P and mm.key_size_sum(p) == (n // P) * klv and mm.value_size_sum(p) == (n // P) * vlv
+        assert mm.overall_size() == n * (klv + vlv)
+        assert mm.largest_message() == klv + vlv == mm.smallest_message()
+        assert mm.earliest_message() == (1_600_000_000, 0) and mm.latest_message() == 1_600_000_000
+
+
+@pytest.mark.parametrize("case", ["crossing", "missing_late", "negative_early"])
+def test_timestamp_extrema_across_high_word_boundaries(case):
+    """The scan compares timestamps on their low 32 bits while every high word it has seen agrees and falls back to
+    the 64-bit comparison otherwise (metric.rs:65-72, :209-211).  Topics whose timestamps cross a multiple of 2^32 ms,
+    carry a late "not available" (-1 -> 0) or start negative must report the reference's earliest / latest."""
+    n, P = 1 << 20, 4
+    i = np.arange(n, dtype=np.int64)
+    ts = (350 << 32) - 500_000_000 + i * 1000          # crosses 350 * 2^32 at record 500 000
+    if case == "missing_late":
+        ts = ts.copy()
+        ts[900_001] = -1
+        ts[n - 1] = -1
+    elif case == "negative_early":
+        ts = ts - (350 << 32)                             # -5e8 .. +5.5e8: the high word flips 0xffffffff -> 0
+    part = (i % P).astype(np.int32)
+    kl = np.full(n, -1, dtype=np.int32)
+    vl = np.full(n, 10, dtype=np.int32)
+    o = Oracle(now=NOW)
+    o.handle_batch(part, ts, kl, vl, np.zeros(0, dtype=np.uint8))
+    with KtaEngine(P, now=NOW) as e:
+        e.scan_batch_device(torch_dev(part), torch_dev(ts), torch_dev(kl), torch_dev(vl))
+        e.finalize()
+        assert_parity(e, o, P)
+        mm = e.message_metrics
+        want_min = 0 if case == "missing_late" else int(ts.min())
+        assert mm.earliest_message() == (int(np.trunc(want_min / 1000)), 0)
+        assert mm.latest_message() == max(0, int(ts.max()) // 1000)
 
 
 def test_partition_out_of_range_is_an_error():
