@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--distinct-keys", type=int, default=10_000_000)
     ap.add_argument("--hll", type=int, default=14)
     ap.add_argument("--key-mode", type=int, default=0, help="0 = 16-byte binary keys, 1 = ASCII key-<id>, 2 = variable 0..40 B")
+    ap.add_argument("--zipf-keys", action="store_true", help="stress case: log-uniform (Zipf s = 1 staircase) key ids")
+    ap.add_argument("--geometric-values", action="store_true", help="stress case: geometric-tailed value lengths")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -50,9 +52,14 @@ def parse():
 
 
 def workload_name(a, world):
-    return ("C1 %d partitions, %.0e msgs/GPU x %d GPU, %d B mean value, %s keys, mode=%s "
+    keys = {0: "16 B", 1: "ASCII key-<id>", 2: "variable 0..40 B"}[a.key_mode & 0xFF] + " keys"
+    if a.zipf_keys:
+        keys += " (log-uniform ids)"
+    if a.geometric_values:
+        keys += ", geometric value tail"
+    return ("C1 %d partitions, %.0e msgs/GPU x %d GPU, %d B mean value, %s, mode=%s "
             "(counters+histograms%s), run_len=%d; inputs %.1f GB/GPU > L2, no flush needed" %
-            (a.partitions, a.n, world, a.value_mean, {0: "16 B", 1: "ASCII key-<id>", 2: "variable 0..40 B"}[a.key_mode], a.mode,
+            (a.partitions, a.n, world, a.value_mean, keys, a.mode,
              {"fused": "+FNV32+HLL p%d" % a.hll, "counters": "", "alive": "+FNV32+exact alive-key table"}[a.mode],
              a.run_len, a.n * 36 / 1e9))
 
@@ -111,7 +118,8 @@ def cpu_reference_rate(a, sample, threads, count_alive_keys, topic=None):
     if topic is None:
         spec = synth.make_spec(a.partitions * a.run_len * max(1, sample // (a.partitions * a.run_len)), a.partitions,
                                run_len=a.run_len, distinct_keys=min(a.distinct_keys, max(a.partitions, sample // 10)),
-                               value_mean=a.value_mean)
+                               value_mean=a.value_mean,
+                               key_mode=a.key_mode, zipf_keys=a.zipf_keys, geometric_values=a.geometric_values)
         topic = synth.fill_host(spec)
     n = topic.n
     import numpy as np
@@ -206,7 +214,7 @@ def run_ours(a):
     P = a.partitions
     n_total = a.n * world
     spec = synth.make_spec(n_total, P, run_len=a.run_len, distinct_keys=a.distinct_keys * world, value_mean=a.value_mean,
-                           key_mode=a.key_mode)
+                           key_mode=a.key_mode, zipf_keys=a.zipf_keys, geometric_values=a.geometric_values)
     exact = a.mode == "alive"
     topic = synth.DeviceTopic(spec, rank=rank, world=world, device=local, with_seq=(exact and world > 1))
     n = topic.n

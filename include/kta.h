@@ -213,14 +213,22 @@ int kta_set_stream(kta_handle *h, void *stream);
  * host and device.  Partition p of record i: runs of run_len records, runs dealt round-robin with a
  * per-cycle pseudo-random rotation, so per-partition offsets are closed-form and a rank that owns
  * partitions {p : p % world == rank} can enumerate exactly its records. */
+/* key_mode flags.  Both are integer-only so that host and device generate identical topics.
+ * KEYS_LOGUNIFORM: key ids are drawn log-uniformly (a staircase approximation of Zipf s = 1: id k of a partition
+ *   is about as likely as 1/(k+1)) instead of uniformly — a few hot keys, a long tail of cold ones.
+ * VALUES_GEOMETRIC: the uniform value length is multiplied by 2^g, P(g = k) = 2^-(k+1), g <= 6 — a geometric tail. */
+#define KTA_SYNTH_KEYS_LOGUNIFORM 0x100
+#define KTA_SYNTH_VALUES_GEOMETRIC 0x200
+
 typedef struct kta_synth_spec {
     uint64_t seed;               /* default 0x4B544131 ("KTA1") */
     int64_t n_total;             /* records in the whole topic; multiple of num_partitions*run_len */
     int32_t num_partitions;
     int32_t run_len;             /* >= 1 */
     uint64_t distinct_keys;      /* D; rounded down to a multiple of num_partitions, >= P */
-    int32_t key_mode;            /* 0 = 16-byte binary (id, id*phi64) LE; 1 = ASCII "key-<id>";
-                                    2 = variable-length binary, 0..40 bytes */
+    int32_t key_mode;            /* low byte: 0 = 16-byte binary (id, id*phi64) LE; 1 = ASCII "key-<id>";
+                                    2 = variable-length binary, 0..40 bytes.  Optional flags (stress cases):
+                                    KTA_SYNTH_KEYS_LOGUNIFORM, KTA_SYNTH_VALUES_GEOMETRIC */
     int32_t value_mean;          /* value_len uniform in [mean/2, 3*mean/2] */
     int32_t null_key_per_10k;
     int32_t tombstone_per_10k;

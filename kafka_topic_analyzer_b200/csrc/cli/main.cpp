@@ -2,7 +2,8 @@
 //
 //   -t/--topic TOPIC  -b/--bootstrap-server HOSTS  [--librdkafka k=v,...]  [-c/--count-alive-keys]
 //   --synthetic n=...,partitions=...,value_mean=...,run_len=...,distinct_keys=...,key_mode=...,seed=...,
-//               tombstone_per_10k=...,null_key_per_10k=...      (the in-memory topic of BASELINE.json configs)
+//               tombstone_per_10k=...,null_key_per_10k=...,zipf_keys=1,geometric_values=1
+//                                                                (the in-memory topic of BASELINE.json configs)
 //   --log-dir DIR              read Kafka log segments from DIR/<topic>-<partition>/*.log (a broker's data directory)
 //                              and decode them on the GPU (uncompressed RecordBatch v2)
 //   --feed push|batch|device   how records reach the handlers: kta_push per record (the reference's call shape),
@@ -189,7 +190,8 @@ int main(int argc, char **argv) {
     spec.n_total = geti("n", 100000);
     spec.n_total -= spec.n_total % ((int64_t)spec.num_partitions * spec.run_len);
     spec.distinct_keys = (uint64_t)geti("distinct_keys", spec.n_total / 10 > spec.num_partitions ? spec.n_total / 10 : spec.num_partitions);
-    spec.key_mode = (int32_t)geti("key_mode", 0);
+    spec.key_mode = (int32_t)geti("key_mode", 0) | (geti("zipf_keys", 0) ? KTA_SYNTH_KEYS_LOGUNIFORM : 0) |
+                    (geti("geometric_values", 0) ? KTA_SYNTH_VALUES_GEOMETRIC : 0);
     spec.value_mean = (int32_t)geti("value_mean", 256);
     spec.null_key_per_10k = (int32_t)geti("null_key_per_10k", 100);
     spec.tombstone_per_10k = (int32_t)geti("tombstone_per_10k", 500);

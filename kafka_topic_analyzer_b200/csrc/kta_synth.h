@@ -38,6 +38,8 @@ struct kta_synth_record {
     int32_t value_len;  // -1 = tombstone
 };
 
+KTA_HD int32_t kta_synth_key_format(const kta_synth_spec &s) { return s.key_mode & 0xff; }
+
 KTA_HD uint64_t kta_synth_keys_per_partition(const kta_synth_spec &s) {
     uint64_t d = s.distinct_keys / (uint64_t)s.num_partitions;
     return d ? d : 1;
@@ -45,8 +47,9 @@ KTA_HD uint64_t kta_synth_keys_per_partition(const kta_synth_spec &s) {
 
 // key bytes depend on key_id only (the same key always has the same bytes)
 KTA_HD int32_t kta_synth_key_len(const kta_synth_spec &s, uint64_t key_id) {
-    if (s.key_mode == 0) return 16;
-    if (s.key_mode == 1) {
+    const int32_t fmt = kta_synth_key_format(s);
+    if (fmt == 0) return 16;
+    if (fmt == 1) {
         int32_t n = 5;
         for (uint64_t v = key_id; v >= 10; v /= 10) n++;
         return n;
@@ -57,11 +60,12 @@ KTA_HD int32_t kta_synth_key_len(const kta_synth_spec &s, uint64_t key_id) {
 // writes kta_synth_key_len bytes to out (capacity KTA_SYNTH_MAX_KEY)
 KTA_HD int32_t kta_synth_key_bytes(const kta_synth_spec &s, uint64_t key_id, uint8_t *out) {
     int32_t len = kta_synth_key_len(s, key_id);
-    if (s.key_mode == 0) {
+    const int32_t fmt = kta_synth_key_format(s);
+    if (fmt == 0) {
         uint64_t a = key_id, b = key_id * 0x9E3779B97F4A7C15ull;
         for (int j = 0; j < 8; j++) out[j] = (uint8_t)(a >> (8 * j));
         for (int j = 0; j < 8; j++) out[8 + j] = (uint8_t)(b >> (8 * j));
-    } else if (s.key_mode == 1) {
+    } else if (fmt == 1) {
         out[0] = 'k'; out[1] = 'e'; out[2] = 'y'; out[3] = '-';
         uint64_t v = key_id;
         for (int j = len - 1; j >= 4; j--) { out[j] = (uint8_t)('0' + v % 10); v /= 10; }
@@ -83,7 +87,16 @@ KTA_HD void kta_synth_record_at(const kta_synth_spec &s, uint64_t i, kta_synth_r
     r.partition = (int32_t)p;
     r.offset = (int64_t)(cycle * R + within);
     const bool null_key = (kta_synth_mix(s.seed, i, 1) % 10000u) < (uint64_t)s.null_key_per_10k;
-    r.key_id = (kta_synth_mix(s.seed, i, 2) % kta_synth_keys_per_partition(s)) * P + p;
+    const uint64_t K = kta_synth_keys_per_partition(s);
+    uint64_t kidx = kta_synth_mix(s.seed, i, 2);
+    if (s.key_mode & KTA_SYNTH_KEYS_LOGUNIFORM) {
+        // pick a bit length b uniformly, then an index uniformly among those of that length: [2^b - 1, 2^(b+1) - 2]
+        int nbits = 0;
+        while (nbits < 63 && (2ull << nbits) <= K) nbits++;          // floor(log2 K)
+        const uint32_t b = (uint32_t)((kidx >> 40) % (uint64_t)(nbits + 1));
+        kidx = ((1ull << b) - 1) + (kidx & ((1ull << b) - 1));
+    }
+    r.key_id = (kidx % K) * P + p;
     r.key_len = null_key ? -1 : kta_synth_key_len(s, r.key_id);
     const uint64_t rv = kta_synth_mix(s.seed, i, 3);
     if ((rv % 10000u) < (uint64_t)s.tombstone_per_10k) {
@@ -92,7 +105,15 @@ KTA_HD void kta_synth_record_at(const kta_synth_spec &s, uint64_t i, kta_synth_r
         r.value_len = 0;
     } else {
         const uint64_t m = (uint64_t)s.value_mean;
-        r.value_len = (int32_t)(m / 2 + kta_synth_mix(s.seed, i, 4) % (m + 1));
+        uint64_t v = m / 2 + kta_synth_mix(s.seed, i, 4) % (m + 1);
+        if (s.key_mode & KTA_SYNTH_VALUES_GEOMETRIC) {
+            const uint64_t g = kta_synth_mix(s.seed, i, 6);
+            int k = 0;
+            while (k < 6 && ((g >> k) & 1) == 0) k++;                // P(k) = 2^-(k+1), capped at 6
+            v <<= k;
+            if (v > 0x7fffffffull) v = 0x7fffffffull;
+        }
+        r.value_len = (int32_t)v;
     }
     const uint64_t rt = kta_synth_mix(s.seed, i, 5);
     r.ts_ms = ((rt % 10000u) < (uint64_t)s.ts_missing_per_10k)

@@ -12,6 +12,8 @@ from . import _native as N
 from ._native import SynthSpec, KtaError, lib
 
 DEFAULT_SEED = 0x4B544131  # "KTA1"
+KEYS_LOGUNIFORM = 0x100     # include/kta.h KTA_SYNTH_KEYS_LOGUNIFORM
+VALUES_GEOMETRIC = 0x200    # include/kta.h KTA_SYNTH_VALUES_GEOMETRIC
 
 
 @dataclass
@@ -33,14 +35,16 @@ class HostTopic:
 def make_spec(n_total: int, num_partitions: int, *, seed: int = DEFAULT_SEED, run_len: int = 1,
               distinct_keys: Optional[int] = None, key_mode: int = 0, value_mean: int = 256,
               null_key_per_10k: int = 100, tombstone_per_10k: int = 500, ts_missing_per_10k: int = 0,
-              empty_value_per_10k: int = 0) -> SynthSpec:
+              empty_value_per_10k: int = 0, zipf_keys: bool = False, geometric_values: bool = False) -> SynthSpec:
+    """`zipf_keys`: log-uniform key ids (a Zipf s = 1 staircase: few hot keys, long cold tail);
+    `geometric_values`: value length x 2^g with P(g = k) = 2^-(k+1), g <= 6 (SURVEY.md §8 d stress cases)."""
     s = SynthSpec()
     s.seed = seed
     s.n_total = n_total
     s.num_partitions = num_partitions
     s.run_len = run_len
     s.distinct_keys = distinct_keys if distinct_keys is not None else max(num_partitions, n_total // 10)
-    s.key_mode = key_mode
+    s.key_mode = key_mode | (KEYS_LOGUNIFORM if zipf_keys else 0) | (VALUES_GEOMETRIC if geometric_values else 0)
     s.value_mean = value_mean
     s.null_key_per_10k = null_key_per_10k
     s.tombstone_per_10k = tombstone_per_10k
@@ -122,7 +126,8 @@ class DeviceTopic:
         self.value_len = torch.empty(count, dtype=torch.int32, device=dev)
         self.seq = torch.empty(count, dtype=torch.int64, device=dev) if with_seq else None
         self.offset = torch.empty(count, dtype=torch.int64, device=dev) if with_offset else None
-        per_key = 16 if spec.key_mode == 0 else (24 if spec.key_mode == 1 else max_key)
+        fmt = spec.key_mode & 0xFF
+        per_key = 16 if fmt == 0 else (24 if fmt == 1 else max_key)
         cap = count * per_key + 64
         self.key_bytes = torch.empty(cap, dtype=torch.uint8, device=dev)
         ntiles = (count + N.KTA_KEY_TILE - 1) // N.KTA_KEY_TILE

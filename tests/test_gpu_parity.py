@@ -93,6 +93,26 @@ def test_fused_alive_exact_and_hll(key_mode, run_len, P):
         assert abs(e.alive_keys_hll() - exact) <= max(4 * 1.04 / 64 * exact, 3)
 
 
+@pytest.mark.parametrize("key_mode,P", [(0, 8), (1, 64)])
+def test_stress_distributions_hot_keys_and_value_tail(key_mode, P):
+    """SURVEY.md §8 d stress cases: log-uniform key ids (the hottest key of a partition carries ~8 % of its records, so
+    many stamps of one hash are in flight at once) and geometric-tailed value lengths (lanes below and above 2^16 in
+    the same warp: both byte-sum paths inside one tile)."""
+    n = P * 20_000
+    spec = synth.make_spec(n, P, key_mode=key_mode, distinct_keys=P * 4096, value_mean=2048, tombstone_per_10k=2000,
+                           null_key_per_10k=200, zipf_keys=True, geometric_values=True)
+    t = synth.fill_host(spec)
+    assert int(t.value_len.max()) > (1 << 16) and int((t.value_len < (1 << 16)).sum()) > n // 2
+    o = oracle_for(t, count_alive_keys=True, now=NOW)
+    with KtaEngine(P, count_alive_keys=True, hll_precision=12, now=NOW) as e:
+        scan_device(e, t)
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(12))
+    os_ = oracle_for(t, track_stream=True, now=NOW)
+    with KtaEngine(P, hll_precision=12, now=NOW) as e:          # in-stream sketch (no -c): the fused bench mode
+        scan_device(e, t)
+        assert_parity(e, os_, P, hll_regs=os_.hll_stream_regs(12))
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_ragged_batches(seed):
     """Adversarial inputs: ragged keys 0..40 B, null/empty keys and values, missing and negative

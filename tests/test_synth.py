@@ -92,3 +92,70 @@ def test_numpy_oracle_agrees_with_c_oracle():
     assert o.earliest()[0] == m["min_ts_s"] and o.latest() == m["max_ts_s"]
     alive = np_oracle.alive_set(t.key_len, t.value_len, np_oracle.fnv32_many(t.key_len, t.key_bytes))
     assert o.scalar("sum_all_alive") == len(alive)
+
+
+def test_log_uniform_keys_are_skewed_but_keep_the_topic_structure():
+    """Stress case of SURVEY.md §8 d (Zipf s = 1 staircase): a few hot keys, a long tail; still one partition and one
+    byte string per key, and the uniform default is untouched by the flag's code path."""
+    P, K = 8, 4096                     # 4096 keys per partition
+    base = synth.make_spec(P * 40_000, P, distinct_keys=P * K, null_key_per_10k=0)
+    skew = synth.make_spec(P * 40_000, P, distinct_keys=P * K, null_key_per_10k=0, zipf_keys=True)
+    assert skew.key_mode == base.key_mode | synth.KEYS_LOGUNIFORM
+    tb, ts = synth.fill_host(base), synth.fill_host(skew)
+    assert np.array_equal(tb.partition, ts.partition) and np.array_equal(tb.value_len, ts.value_len)   # only the ids change
+    ids_b = tb.key_bytes.reshape(-1, 16)[:, :8].copy().view(np.uint64).ravel()
+    ids_s = ts.key_bytes.reshape(-1, 16)[:, :8].copy().view(np.uint64).ravel()
+    assert np.all(ids_s % P == ts.partition.astype(np.uint64))            # same key -> same partition
+    within = (ids_s // P).astype(np.int64)
+    assert within.min() == 0 and within.max() < K
+    # the 13 bit lengths 0..12 are equally likely; indices of length b are [2^b - 1, 2^(b+1) - 2], and the top length
+    # wraps around K = 2^12 (a uniform floor under the staircase, so every key stays reachable)
+    for b in (1, 4, 8, 11):
+        frac = float((within < (1 << b) - 1).mean())
+        want = b / 13 + ((1 << b) - 1) / K / 13
+        assert abs(frac - want) < 0.01, (b, frac, want)
+    top = np.sort(np.bincount(within, minlength=K))[::-1]
+    assert top[:41].sum() > 0.40 * ts.n                                   # 1 % of the keys carry > 40 % of the records
+    uniform_top = np.sort(np.bincount((ids_b // P).astype(np.int64), minlength=K))[::-1]
+    assert uniform_top[:41].sum() < 0.02 * tb.n
+
+
+def test_geometric_value_tail():
+    s = synth.make_spec(4 * 100_000, 4, value_mean=1024, tombstone_per_10k=500, geometric_values=True)
+    u = synth.make_spec(4 * 100_000, 4, value_mean=1024, tombstone_per_10k=500)
+    t, tu = synth.fill_host(s), synth.fill_host(u)
+    assert np.array_equal(t.value_len < 0, tu.value_len < 0)              # same tombstones
+    v, vu = t.value_len[t.value_len >= 0].astype(np.int64), tu.value_len[tu.value_len >= 0].astype(np.int64)
+    g = v // vu                                                           # the power of two applied to each record
+    assert np.array_equal(v, vu * g) and set(np.unique(g).tolist()) <= {1, 2, 4, 8, 16, 32, 64}
+    for k in range(6):
+        assert abs(float((g == 1 << k).mean()) - 2.0 ** -(k + 1)) < 0.004, k
+    assert abs(float((g == 64).mean()) - 2.0 ** -6) < 0.002               # the cap collects the rest of the tail
+    assert v.max() >= 32 * 1024 and abs(v.mean() / vu.mean() - 4.0) < 0.1   # E[2^g] = 6 * 1/2 + 64/64 = 4
+
+
+def test_stress_distributions_through_both_oracles():
+    from parity import oracle_for
+    from oracle_lib import COUNTERS
+    s = synth.make_spec(6 * 5000, 6, key_mode=1, distinct_keys=6 * 512, tombstone_per_10k=3000, zipf_keys=True,
+                        geometric_values=True)
+    t = synth.fill_host(s)
+    o = oracle_for(t, count_alive_keys=True)
+    m = np_oracle.message_metrics(6, t.partition, t.ts_ms, t.key_len, t.value_len)
+    for p in range(6):
+        for name in COUNTERS:
+            assert o.counter(name, p) == int(m[name][p]), (name, p)
+        assert o.hist(1, p).tolist() == m["vhist"][p].tolist()
+    alive = np_oracle.alive_set(t.key_len, t.value_len, np_oracle.fnv32_many(t.key_len, t.key_bytes))
+    assert o.scalar("sum_all_alive") == len(alive)
+    assert int((m["vhist"][:, 12:]).sum()) > 0                            # values >= 2 KiB exist: the tail reaches the high buckets
+
+
+def test_invalid_key_mode_flags_are_rejected():
+    s = synth.make_spec(64, 4)
+    s.key_mode = 3
+    assert synth.lib().kta_synth_shard_records(s, 0, 1) == -1
+    s.key_mode = 0x400
+    assert synth.lib().kta_synth_shard_records(s, 0, 1) == -1
+    s.key_mode = 2 | synth.KEYS_LOGUNIFORM | synth.VALUES_GEOMETRIC
+    assert synth.lib().kta_synth_shard_records(s, 0, 1) == 64 and synth.lib().kta_synth_shard_records(s, 1, 4) == 16
