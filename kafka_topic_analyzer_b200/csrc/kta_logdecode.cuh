@@ -77,7 +77,10 @@ __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const ui
             const int magic = (int8_t)__ldg(p + 16);
             const uint32_t attrs = be_u16(p + 21);
             const int32_t count = (int32_t)be_u32(p + 57);
-            if (magic == 2 && batch_len >= LOG_HEADER_BYTES - 12 && bi.off + 12 + (uint64_t)batch_len <= (uint64_t)nbytes && count >= 0) {
+            // recordsCount sizes the output columns, so it must be plausible before anything is allocated for it: the
+            // smallest record is 7 bytes (length, attributes, two deltas, key length, value length, header count)
+            if (magic == 2 && batch_len >= LOG_HEADER_BYTES - 12 && bi.off + 12 + (uint64_t)batch_len <= (uint64_t)nbytes && count >= 0 &&
+                (uint64_t)count * 7u + (uint64_t)(LOG_HEADER_BYTES - 12) <= (uint64_t)batch_len) {
                 bi.len = 12u + (uint32_t)batch_len;
                 bi.base_offset = (int64_t)be_u64(p);
                 bi.base_ts = (int64_t)be_u64(p + 27);

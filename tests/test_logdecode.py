@@ -22,6 +22,15 @@ def test_codec_varints_roundtrip():
     assert kc.varint(-1) == b"\x01" and kc.varint(0) == b"\x00" and kc.varint(1) == b"\x02"
 
 
+def test_smallest_record_is_seven_bytes():
+    """log_header_kernel bounds recordsCount by (batchLength - 49) / 7 before the output columns are sized."""
+    assert len(kc.encode_record(0, 0, None, None)) == 7
+    b = kc.encode_batch(5, 1000, [(i % 64, 0, None, None) for i in range(100)])      # one-byte varints only
+    batch_len = int.from_bytes(b[8:12], "big")
+    count = int.from_bytes(b[57:61], "big")
+    assert count == 100 and count * 7 + 49 == batch_len == len(b) - 12
+
+
 def _partition_lists(t):
     """per-partition record lists (ts, key, value_len) in offset order, from a HostTopic"""
     kl = t.key_len
@@ -97,6 +106,10 @@ def test_compressed_and_malformed_batches_are_rejected():
         bad = bytearray(good)
         bad[61] = 0x7F                                                                           # record length beyond the batch
         with pytest.raises(KtaError):
+            e.push_log_segment(0, bytes(bad))
+        bad = bytearray(good)
+        bad[57:61] = (0x7FFFFFFF).to_bytes(4, "big")                                             # recordsCount the batch cannot hold:
+        with pytest.raises(KtaError):                                                            # rejected before any column is sized by it
             e.push_log_segment(0, bytes(bad))
         assert e.push_log_segment(0, good[:30]) == 0                                             # only a truncated header
 
