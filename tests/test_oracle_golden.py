@@ -227,3 +227,47 @@ def test_hll_estimator_accuracy():
         est = hll_estimate(regs, p)
         sigma = 1.04 / np.sqrt(1 << p)
         assert abs(est - n) <= max(4 * sigma * n, 3), (p, n, est)
+
+
+# ------------------------------------------------------------------------------------------------
+# property test: the two independent restatements (C, record at a time; numpy, vectorised) agree on arbitrary
+# batches — nulls, empties, negative / missing timestamps, colliding and repeated keys, any partition layout
+# ------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st
+from oracle_lib import COUNTERS
+
+_key = st.one_of(st.none(), st.binary(min_size=0, max_size=24), st.sampled_from([b"a", b"b", b"key-0", b"key-1", b""]))
+_val = st.one_of(st.none(), st.integers(min_value=0, max_value=70_000), st.sampled_from([0, 1, 65535, 65536, 2**31 - 1]))
+_ts = st.one_of(st.none(), st.integers(min_value=-10**7, max_value=2 * 10**12), st.sampled_from([0, 999, 1000, -999, -1000, -1]))
+_rec = st.tuples(st.integers(min_value=0, max_value=6), _ts, _key, _val)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(_rec, min_size=0, max_size=60))
+def test_c_and_numpy_restatements_agree_on_arbitrary_batches(records):
+    import np_oracle
+    P = 7
+    o = Oracle(count_alive_keys=True, now=(4102444800, 7))
+    for p, ts, key, vl in records:
+        o.handle_message(p, ts, key, vl)
+    n = len(records)
+    part = np.array([r[0] for r in records], dtype=np.int32)
+    ts = np.array([-1 if r[1] is None else r[1] for r in records], dtype=np.int64)   # None -> "not available" (-1)
+    kl = np.array([-1 if r[2] is None else len(r[2]) for r in records], dtype=np.int32)
+    vl = np.array([-1 if r[3] is None else r[3] for r in records], dtype=np.int32)
+    kb = np.frombuffer(b"".join(r[2] or b"" for r in records), dtype=np.uint8)
+    m = np_oracle.message_metrics(P, part, ts, kl, vl)
+    for p in range(P):
+        for name in COUNTERS:
+            assert o.counter(name, p) == int(m[name][p]), (name, p)
+        assert o.hist(0, p).tolist() == m["khist"][p].tolist() and o.hist(1, p).tolist() == m["vhist"][p].tolist()
+    assert o.scalar("overall_count") == n and o.scalar("overall_size") == m["overall_size"]
+    assert o.scalar("largest_message") == m["largest"] and o.scalar("smallest_message") == m["smallest"]
+    if n:
+        # an explicit -1 and a missing timestamp are the same thing at this boundary (rdkafka: to_millis() == None)
+        assert o.earliest() == (min(m["min_ts_s"], 4102444800), 0 if m["min_ts_s"] <= 4102444800 else 7)
+        assert o.latest() == max(m["max_ts_s"], 0)
+    else:
+        assert o.earliest() == (4102444800, 7) and o.latest() == 0
+    h = np_oracle.fnv32_many(kl, kb)
+    assert o.scalar("sum_all_alive") == len(np_oracle.alive_set(kl, vl, h))
