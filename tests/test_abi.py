@@ -90,3 +90,35 @@ def test_abi_rejects_bad_arguments_without_cuda():
     assert L.kta_merge_words(None, 2) == -1
     spec = _native.SynthSpec()
     assert L.kta_synth_shard_records(C.byref(spec), 0, 1) == -1      # zero partitions
+
+
+def _build_c_example(tmp_path):
+    """integration/c/minimal.c: the boundary used from plain C11 (no C++, no torch)."""
+    exe = str(tmp_path / "kta_minimal")
+    libdir = os.path.join(ROOT, "kafka_topic_analyzer_b200")
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "c", "minimal.c"), "-L", libdir, "-lkta_gpu",
+                        "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_example_links_and_fails_loudly_without_cuda(tmp_path):
+    from kafka_topic_analyzer_b200 import lib
+    lib()                                   # make sure the library is built
+    exe = _build_c_example(tmp_path)
+    if lib().kta_device_count() > 0:
+        pytest.skip("a CUDA device is present: covered by the gpu variant")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and r.stderr.startswith("kta_create:") and r.stdout == ""
+
+
+@pytest.mark.gpu
+def test_c_example_output(tmp_path):
+    r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines() == [
+        "partition 0: total 3 tombstones 1 key bytes 18 value bytes 120 dirty ratio 33.3333",
+        "partition 1: total 2 tombstones 0 key bytes 6 value bytes 90 dirty ratio 0.0000",
+        "alive keys: 2",
+    ]
