@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define KTA_ABI_VERSION 1
+#define KTA_ABI_VERSION 2
 #define KTA_KEY_TILE 128      /* records per key tile (granularity of kta_batch.key_tile_base) */
 #define KTA_HIST_BUCKETS 32   /* bucket(len) = len == 0 ? 0 : 1 + floor(log2(len)) */
 
@@ -62,7 +62,8 @@ typedef struct kta_config {
     int32_t num_partitions;    /* P; partition ids are 0..P-1 (metadata, src/kafka.rs:60-72) */
     int32_t count_alive_keys;  /* 1 = exact alive-key table, i.e. `-c` given once (src/main.rs:77-80) */
     int32_t hll_precision;     /* EXTENSION: 0 = off, else 4..18 HyperLogLog index bits */
-    int32_t reserved0;
+    int32_t alive_table_kib;   /* initial size of the alive-key table in KiB (8 bytes per distinct key hash, kept at
+                                  load <= 0.7 and grown on demand); 0 = default (131072 = 128 MiB: 1e7 keys) */
     int64_t ring_records;      /* records per landing-ring chunk for kta_push / host batches; 0 = default */
     int64_t ring_key_bytes;    /* key bytes per landing-ring chunk; 0 = default */
     int64_t now_s;             /* construction wall clock for earliest_message (Utc::now(), */
@@ -70,10 +71,17 @@ typedef struct kta_config {
     int32_t reserved1;
 } kta_config;
 
+/* kta_batch.seq_base value that means "continue this handle's running count" (what kta_push does: the consumer's
+ * `seq += 1`, src/kafka.rs:99) */
+#define KTA_SEQ_AUTO UINT64_MAX
+
 /* SoA record batch.  Pointers are all host or all device (see the two scan entry points). */
 typedef struct kta_batch {
     int64_t n;                     /* records */
-    uint64_t seq_base;             /* seq of record 0; record i has seq_base + i (src/kafka.rs:99) */
+    uint64_t seq_base;             /* seq of record 0; record i has seq_base + i (src/kafka.rs:99), or KTA_SEQ_AUTO.
+                                      With count_alive_keys the LAST record of a key decides (src/metric.rs:295,298) and
+                                      "last" is by seq: a batch without a seq column whose seq_base lies below the
+                                      handle's running count is refused (it would let older records win silently). */
     const int32_t *partition;      /* [n] */
     const int64_t *offset;         /* [n] carried for the caller; never read by a metric (may be NULL) */
     const int64_t *ts_ms;          /* [n] */
@@ -86,7 +94,10 @@ typedef struct kta_batch {
                                       of the first key of each tile (+ total at the end).  NULL →
                                       the library derives it with one extra pass over key_len. */
     const uint64_t *seq;           /* optional [n] explicit sequence numbers (partition-sharded
-                                      scans, where the global order is not base+i); NULL → seq_base+i */
+                                      scans, where the global order is not base+i); NULL → seq_base+i.
+                                      The alive-key table keeps 31 bits of seq: explicit sequence numbers must stay
+                                      below 2^31 - 2 between kta_reset calls (kta_finalize reports violations);
+                                      implicit ones are unlimited (the table is rebased as the stream advances). */
 } kta_batch;
 
 enum kta_counter_id { /* per-partition counters, src/metric.rs:13-19 / getters :104-130 */
@@ -151,6 +162,9 @@ int kta_global(const kta_handle *h, int which, uint64_t *out);
 int kta_timestamps(const kta_handle *h, int64_t *earliest_s, int32_t *earliest_ns, int64_t *latest_s);
 /* LogCompactionInMemoryMetrics::sum_all_alive, src/metric.rs:282-284 (exact) */
 int kta_alive_keys(const kta_handle *h, uint64_t *out);
+/* records whose partition was outside [0, num_partitions): they are left out of EVERY metric (kta_finalize returns
+ * KTA_ERR_PARTITION to say so; the getters stay valid and describe the in-range records) */
+int kta_bad_partition_records(const kta_handle *h, uint64_t *out);
 
 /* ---- EXTENSIONS: not in the reference ---- */
 /* per-partition log2 size histogram: which = 0 key sizes, 1 value sizes */
@@ -203,6 +217,9 @@ int kta_push_log_segments_host(kta_handle *h, int32_t nsegs, const int32_t *part
 int kta_stats(const kta_handle *h, uint64_t *kernel_launches, uint64_t *records_scanned);
 int kta_set_timing(kta_handle *h, int enabled);
 int kta_scan_time_ms(kta_handle *h, double *total_ms, uint64_t *launches);
+/* alive-key table: slots allocated, slots occupied (= distinct key hashes seen), how often it was grown and how many
+ * batches had to be re-stamped because it was too small when they were scanned (any pointer may be NULL) */
+int kta_alive_table_stats(kta_handle *h, uint64_t *slots, uint64_t *occupied, uint64_t *grows, uint64_t *reruns);
 /* raw cudaStream_t of the handle (so a torch caller can order against it) */
 void *kta_stream(kta_handle *h);
 /* adopt a caller-owned cudaStream_t (e.g. torch's current stream) for all further work of this handle */

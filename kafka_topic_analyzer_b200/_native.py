@@ -19,6 +19,7 @@ INCLUDE = os.path.normpath(os.path.join(_HERE, "..", "include"))
 KTA_KEY_TILE = 128
 KTA_HIST_BUCKETS = 32
 INT64_MIN = -(1 << 63)
+SEQ_AUTO = (1 << 64) - 1   # include/kta.h KTA_SEQ_AUTO
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -62,7 +63,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_PARTITION, ERR_DIV_BY_ZERO, ERR_NOT_EN
 class Config(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("device", C.c_int32), ("num_partitions", C.c_int32),
-        ("count_alive_keys", C.c_int32), ("hll_precision", C.c_int32), ("reserved0", C.c_int32),
+        ("count_alive_keys", C.c_int32), ("hll_precision", C.c_int32), ("alive_table_kib", C.c_int32),
         ("ring_records", C.c_int64), ("ring_key_bytes", C.c_int64), ("now_s", C.c_int64),
         ("now_ns", C.c_int32), ("reserved1", C.c_int32),
     ]
@@ -105,6 +106,9 @@ SYMBOLS = {
     "kta_global": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
     "kta_timestamps": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "kta_alive_keys": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "kta_bad_partition_records": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "kta_alive_table_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]),
     "kta_hist": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(C.c_uint64)]),
     "kta_alive_keys_hll": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "kta_hll_registers": (C.c_int, [_P, _P, C.c_size_t]),
@@ -141,9 +145,13 @@ def lib() -> C.CDLL:
     """Load libkta_gpu.so (building it first if the sources are newer / it is missing)."""
     global _lib
     if _lib is None:
-        path = os.environ.get("KTA_LIB") or LIB_PATH   # KTA_LIB: an experimental build of the same sources
-        if not os.path.exists(path):
-            build()
+        path = os.environ.get("KTA_LIB")   # KTA_LIB: an experimental build of the same sources, used as it is
+        if not path:
+            # (re)build when the library is missing or older than any source; a failed nvcc run surfaces as an error
+            # instead of silently testing a stale binary.  KTA_NO_BUILD=1: use the shipped .so as it is (no nvcc needed).
+            path = LIB_PATH
+            if not (os.environ.get("KTA_NO_BUILD") == "1" and os.path.exists(path)):
+                build()
         _lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(_lib, name)  # AttributeError if the export is missing: loud by design

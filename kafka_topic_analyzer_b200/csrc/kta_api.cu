@@ -61,6 +61,8 @@ extern "C" int kta_device_count(void) {
 // handle
 // ------------------------------------------------------------------------------------------------
 static constexpr int NCHUNK = 3;
+static constexpr int32_t ALIVE_DEFAULT_KIB = 128 * 1024;       // initial alive-key table: 128 MiB
+static constexpr int32_t ALIVE_MAX_KIB = 32 * 1024 * 1024;     // 32 GiB = one slot per possible 32-bit hash
 static constexpr int64_t DEFAULT_RING_RECORDS = 1 << 22;  // 4 Mi records per chunk
 
 struct Chunk {
@@ -71,11 +73,21 @@ struct Chunk {
     uint8_t *d_keys = nullptr;
     uint64_t *d_tile_base = nullptr;
     cudaEvent_t free_ev = nullptr;  // recorded after the scan that reads this chunk
+    uint32_t *h_status = nullptr;   // pinned [2]: snapshot of the alive-table status words taken right after that scan
     // pinned landing area for kta_push
     int32_t *h_partition = nullptr, *h_klen = nullptr, *h_vlen = nullptr;
     int64_t *h_ts = nullptr;
     uint8_t *h_keys = nullptr;
     uint64_t *h_tile_base = nullptr;
+};
+
+// a MODE_EXACT scan whose stamps have not been confirmed yet (the alive table may turn out too small: then it is
+// grown and these are re-run stamps-only; their input buffers are still valid — caller buffers until kta_sync /
+// kta_finalize by contract, ring chunks until they are reused)
+struct PendingScan {
+    ScanParams prm;
+    int64_t key_readable, key_bytes;
+    int chunk;   // ring chunk the columns live in, -1 = caller-owned / scratch device buffers
 };
 
 struct kta_handle {
@@ -90,10 +102,17 @@ struct kta_handle {
     long long *d_minmax = nullptr;
     uint32_t *d_hll = nullptr;
     uint32_t *d_hll_floor = nullptr;
-    unsigned long long *d_alive_table = nullptr;
-    uint8_t *d_alive_dirty = nullptr;
-    unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export counter, [2..] hll floor + slice minima (u32)
-    uint32_t epoch = 1;                      // alive-table epoch (stamps carry it in their top 16 bits)
+    unsigned long long *d_alive_table = nullptr;   // open-addressed last-writer table, 2 * alive_pairs slots
+    uint32_t alive_pairs = 0;
+    uint64_t alive_origin = 0;               // seq that a stamp's field value 1 stands for
+    bool alive_rebased = false;              // a rebase dropped absolute sequence numbers (exports are refused then)
+    uint32_t *d_alive_status = nullptr;      // [0] stamps that found no slot, [1] records outside the seq window
+    uint32_t *h_alive_status = nullptr;      // pinned copy
+    uint64_t alive_window_errors = 0;        // sticky until reset: reported by kta_finalize
+    uint64_t alive_grows = 0, alive_reruns = 0;
+    std::vector<PendingScan> pending;
+    unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export cursor, [2] occupied slots, [3] spare,
+                                             // [4..] hll floor + slice minima (u32)
     uint32_t *d_hash_out = nullptr;          // test hook
     uint64_t *d_tb_scratch = nullptr;        // key_tile_base scratch for device batches
     int64_t tb_scratch_tiles = 0;
@@ -203,19 +222,20 @@ static int state_reset_device(kta_handle *h) {
     h->launches++;
     CU(cudaGetLastError());
     if (h->d_alive_table) {
-        // O(1) reset of the 32 GiB table: a new epoch outranks and invalidates every older stamp.  Only when the
-        // 16-bit epoch wraps is the table really wiped.
-        if (++h->epoch == 0xffffu) {
-            CU(cudaMemsetAsync(h->d_alive_table, 0, ((size_t)1 << 32) * 8, h->stream));
-            h->epoch = 1;
-        }
-        CU(cudaMemsetAsync(h->d_alive_dirty, 0, (size_t)1 << (32 - DIRTY_SHIFT), h->stream));
-        CU(cudaMemsetAsync(h->d_scalar, 0, 16, h->stream));
+        // the table is a few hundred MB at most for the topics it is meant for: wiping it is a ~20 µs memset
+        CU(cudaMemsetAsync(h->d_alive_table, 0xff, (size_t)h->alive_pairs * 16, h->stream));
+        CU(cudaMemsetAsync(h->d_scalar, 0, 32, h->stream));
+        CU(cudaMemsetAsync(h->d_alive_status, 0, 8, h->stream));
+        h->alive_origin = 0;
+        h->alive_rebased = false;
+        h->alive_window_errors = 0;
+        h->pending.clear();
     }
     return KTA_OK;
 }
 
 static void free_chunk(Chunk &c) {
+    cudaFreeHost(c.h_status);
     cudaFree(c.d_partition); cudaFree(c.d_klen); cudaFree(c.d_vlen); cudaFree(c.d_ts); cudaFree(c.d_seq);
     cudaFree(c.d_keys); cudaFree(c.d_tile_base);
     if (c.free_ev) cudaEventDestroy(c.free_ev);
@@ -230,7 +250,7 @@ extern "C" int kta_destroy(kta_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &c : h->chunks) free_chunk(c);
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
-    cudaFree(h->d_alive_dirty); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
+    cudaFree(h->d_alive_status); cudaFreeHost(h->h_alive_status); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
     cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt); cudaFree(h->d_log_kb);
     cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys);
     cudaFree(h->d_log_err);
@@ -276,16 +296,19 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     h->nhll = cfg->hll_precision ? ((size_t)1 << cfg->hll_precision) : 0;
     CU(cudaMalloc(&h->d_sums, h->nsums * 8));
     CU(cudaMalloc(&h->d_minmax, 4 * 8));
-    CU(cudaMalloc(&h->d_scalar, 2 * 8 + (HLL_SLICES + 1) * 4 + 4));
-    h->d_hll_floor = reinterpret_cast<uint32_t *>(h->d_scalar + 2);
+    CU(cudaMalloc(&h->d_scalar, 4 * 8 + (HLL_SLICES + 1) * 4 + 4));
+    h->d_hll_floor = reinterpret_cast<uint32_t *>(h->d_scalar + 4);
     if (h->nhll) CU(cudaMalloc(&h->d_hll, h->nhll * 4));
     if (cfg->count_alive_keys == 1) {
-        // direct-mapped last-writer table over the whole 32-bit hash space: 2^32 × 8 B = 32 GiB
-        CU(cudaMalloc(&h->d_alive_table, ((size_t)1 << 32) * 8));
-        CU(cudaMalloc(&h->d_alive_dirty, (size_t)1 << (32 - DIRTY_SHIFT)));
-        CU(cudaMemsetAsync(h->d_alive_table, 0, ((size_t)1 << 32) * 8, h->stream));
-        CU(cudaMemsetAsync(h->d_alive_dirty, 0, (size_t)1 << (32 - DIRTY_SHIFT), h->stream));
-        h->epoch = 0;   // state_reset_device below moves to epoch 1
+        // open-addressed last-writer table keyed by the 32-bit hash, sized by the number of DISTINCT hashes and grown
+        // on demand (alive_check): 128 MiB = 2^24 slots holds the 1e7 keys of BASELINE configs[2] at load 0.6
+        if (cfg->alive_table_kib < 0 || cfg->alive_table_kib > ALIVE_MAX_KIB)
+            return fail(KTA_ERR_INVALID, "alive_table_kib %d out of range [0, %d]", cfg->alive_table_kib, ALIVE_MAX_KIB);
+        const int64_t kib = cfg->alive_table_kib ? cfg->alive_table_kib : ALIVE_DEFAULT_KIB;
+        h->alive_pairs = (uint32_t)std::max<int64_t>(kib * 64, 16);   // 16 bytes per pair
+        CU(cudaMalloc(&h->d_alive_table, (size_t)h->alive_pairs * 16));
+        CU(cudaMalloc(&h->d_alive_status, 8));
+        CU(cudaHostAlloc(&h->h_alive_status, 8, cudaHostAllocDefault));
     }
     h->smem_optin = prop.sharedMemPerBlockOptin;
     // counters in shared memory as long as at least 8 warps still fit beside them
@@ -332,17 +355,18 @@ extern "C" int kta_set_stream(kta_handle *h, void *stream) {
 // ------------------------------------------------------------------------------------------------
 // scan launch
 // ------------------------------------------------------------------------------------------------
-static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes) {
-    if (prm.n <= 0) return KTA_OK;
+// one launch of the fused scan; prm is complete apart from the state pointers filled in here
+static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes) {
     const int P = h->cfg.num_partitions;
     const bool exact = h->cfg.count_alive_keys == 1;
-    const bool capture = h->d_hash_out != nullptr;
+    const bool capture = h->d_hash_out != nullptr && !prm.alive_only;
     // with -c the sketch is built from the resolved set at finalize, not in-stream.  A capture-only
     // handle (no -c, no HLL) runs the HLL-mode kernel against a null sketch of precision 0.
     const int mode = exact ? MODE_EXACT : (h->cfg.hll_precision || capture) ? MODE_HLL : MODE_COUNTERS;
     if (mode == MODE_HLL && !h->cfg.hll_precision)
         return fail(KTA_ERR_INVALID, "hash capture needs count_alive_keys or hll_precision");
     prm.ntiles = (prm.n + TILE - 1) / TILE;
+    if (prm.ntiles >= (int64_t)1 << 30) return fail(KTA_ERR_INVALID, "batch of %lld records: split it (one scan takes < 2^37 records)", (long long)prm.n);
     prm.P = P;
     prm.hll_p = h->cfg.hll_precision;
     prm.sums = h->d_sums;
@@ -350,10 +374,11 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int6
     prm.hll = h->d_hll;
     prm.hll_floor = h->d_hll_floor;
     prm.alive_table = h->d_alive_table;
-    prm.alive_dirty = h->d_alive_dirty;
+    prm.alive_pairs = h->alive_pairs;
+    prm.alive_origin = h->alive_origin;
     prm.alive_count = h->d_scalar;
-    prm.epoch_tag = (uint64_t)h->epoch << 48;
-    prm.hash_out = h->d_hash_out;
+    prm.alive_status = h->d_alive_status;
+    prm.hash_out = capture ? h->d_hash_out : nullptr;
     if (mode != MODE_COUNTERS) {
         if (!prm.key_tile_base) return fail(KTA_ERR_INVALID, "internal: key_tile_base missing");
         if (!prm.key_bytes && key_readable > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL but keys are required");
@@ -384,8 +409,115 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int6
     CU(cudaGetLastError());
     h->launches++;
     if (h->timing) CU(cudaEventRecord(e1, h->stream));
+    return KTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// alive-key table upkeep: seq window (rebase), confirmation of pending stamps, growth (rehash + re-run)
+// ------------------------------------------------------------------------------------------------
+static int alive_grow(kta_handle *h, uint32_t new_pairs) {
+    cudaStream_t s = h->stream;
+    unsigned long long *nt = nullptr;
+    CU(cudaMalloc(&nt, (size_t)new_pairs * 16));
+    CU(cudaMemsetAsync(nt, 0xff, (size_t)new_pairs * 16, s));
+    const size_t old_slots = (size_t)h->alive_pairs * 2;
+    alive_rehash_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, old_slots, nt, new_pairs, h->d_alive_status);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));
+    cudaFree(h->d_alive_table);
+    h->d_alive_table = nt;
+    h->alive_pairs = new_pairs;
+    h->alive_grows++;
+    return KTA_OK;
+}
+
+// Confirms every pending MODE_EXACT scan: waits for the stream, reads the status words, and while stamps were dropped
+// for lack of room grows the table and re-runs the pending batches stamps-only (idempotent: atomicMax).  Afterwards
+// nothing is pending.  Also grows ahead of need once the table is more than 70 % full.
+static int alive_check(kta_handle *h) {
+    if (!h->d_alive_table) return KTA_OK;
+    cudaStream_t s = h->stream;
+    for (int round = 0;; round++) {
+        unsigned long long occupied = 0;
+        CU(cudaMemcpyAsync(h->h_alive_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(&occupied, h->d_scalar + 2, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        const uint32_t dropped = h->h_alive_status[0];
+        h->alive_window_errors += h->h_alive_status[1];
+        if (dropped || h->h_alive_status[1]) CU(cudaMemsetAsync(h->d_alive_status, 0, 8, s));
+        const uint64_t slots = (uint64_t)h->alive_pairs * 2;
+        const bool crowded = occupied * 10 > slots * 7;
+        if (!dropped && !crowded) break;
+        if (h->alive_pairs >= (uint32_t)ALIVE_MAX_KIB * 64u) {
+            if (dropped) return fail(KTA_ERR_NOMEM, "alive-key table is at its maximum (32 GiB) and still too full");
+            break;
+        }
+        // at least double; enough for every known entry plus every dropped stamp at load <= 0.5
+        uint64_t want = slots * 2;
+        while (want < (occupied + dropped) * 2) want *= 2;
+        want = std::min<uint64_t>(want, (uint64_t)ALIVE_MAX_KIB * 128ull);
+        int rc;
+        if ((rc = alive_grow(h, (uint32_t)(want / 2)))) return rc;
+        if (!dropped) break;   // grown ahead of need: every pending stamp had landed
+        if (round > 40) return fail(KTA_ERR_INVALID, "alive-key table growth did not converge");
+        for (const PendingScan &ps : h->pending) {
+            ScanParams prm = ps.prm;
+            prm.alive_only = 1;
+            if ((rc = launch_scan_raw(h, prm, ps.key_readable, ps.key_bytes))) return rc;
+            h->alive_reruns++;
+        }
+    }
+    h->pending.clear();
+    return KTA_OK;
+}
+
+static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes, int chunk = -1) {
+    if (prm.n <= 0) return KTA_OK;
+    int rc;
+    if (h->cfg.count_alive_keys == 1) {
+        // the stamps of this batch must fit the table's 31-bit window [origin, origin + ALIVE_FIELD_MAX)
+        if ((uint64_t)prm.n > (uint64_t)ALIVE_FIELD_MAX - 1)
+            return fail(KTA_ERR_INVALID, "batch of %lld records with count_alive_keys: split it (< 2^31 per scan)", (long long)prm.n);
+        if (prm.seq_base < h->alive_origin)
+            return fail(KTA_ERR_INVALID, "seq_base %llu lies before the alive-key table's window origin %llu (batches must not "
+                        "go back past a rebase)", (unsigned long long)prm.seq_base, (unsigned long long)h->alive_origin);
+        // explicit seq columns are checked record by record in the kernel; the implicit range is checked here
+        if (!prm.seq && prm.seq_base - h->alive_origin + (uint64_t)prm.n > (uint64_t)ALIVE_FIELD_MAX) {
+            // rebase: everything already in the table is older than this batch; forget by how much
+            if ((rc = alive_check(h))) return rc;
+            alive_rebase_kernel<<<h->sm_count * 8, THREADS, 0, h->stream>>>(h->d_alive_table, (size_t)h->alive_pairs * 2);
+            h->launches++;
+            CU(cudaGetLastError());
+            h->alive_origin = prm.seq_base;
+            h->alive_rebased = true;
+        }
+        prm.alive_fbase = prm.seq_base - h->alive_origin + 1ull;
+        prm.alive_only = 0;
+    }
+    if ((rc = launch_scan_raw(h, prm, key_readable, key_bytes))) return rc;
+    if (h->cfg.count_alive_keys == 1) h->pending.push_back(PendingScan{prm, key_readable, key_bytes, chunk});
     h->records += (uint64_t)prm.n;
     h->finalized = false;
+    return KTA_OK;
+}
+
+// a ring chunk is about to be overwritten: its scan must be confirmed first (the chunk's event has been waited for,
+// so its status snapshot is valid)
+static int alive_release_chunk(kta_handle *h, int ci) {
+    if (!h->d_alive_table || h->pending.empty()) return KTA_OK;
+    bool mine = false;
+    for (const PendingScan &ps : h->pending) mine = mine || ps.chunk == ci;
+    if (!mine) return KTA_OK;
+    const Chunk &c = h->chunks[ci];
+    if (c.h_status[0] | c.h_status[1]) return alive_check(h);   // something was dropped up to this scan: settle everything
+    // nothing dropped up to and including this chunk's scan: it — and every older pending scan — is confirmed
+    size_t keep = 0;
+    bool seen = false;
+    for (size_t i = h->pending.size(); i-- > 0;) {   // find the newest entry of this chunk; drop it and everything older
+        if (h->pending[i].chunk == ci) { keep = i + 1; seen = true; break; }
+    }
+    if (seen) h->pending.erase(h->pending.begin(), h->pending.begin() + (long)keep);
     return KTA_OK;
 }
 
@@ -411,6 +543,22 @@ static int derive_tile_base(kta_handle *h, const int32_t *d_klen, int64_t n, uin
     return KTA_OK;
 }
 
+// seq of a batch's record 0.  KTA_SEQ_AUTO continues the handle's running count (what kta_push and the log-segment
+// entry points do).  With -c and no explicit seq column, last-writer-wins is decided by seq_base + i alone, so a batch
+// that re-uses sequence numbers the handle has already handed out would silently let OLDER records win: refused.
+static int resolve_seq_base(kta_handle *h, const kta_batch *b, uint64_t *out) {
+    if (b->seq_base == KTA_SEQ_AUTO) {
+        *out = h->next_seq;
+        return KTA_OK;
+    }
+    if (h->cfg.count_alive_keys == 1 && !b->seq && b->seq_base < h->next_seq)
+        return fail(KTA_ERR_INVALID, "seq_base %llu < %llu, the next sequence number of this handle: batches without a seq "
+                    "column must be pushed in stream order (use KTA_SEQ_AUTO to continue the running count)",
+                    (unsigned long long)b->seq_base, (unsigned long long)h->next_seq);
+    *out = b->seq_base;
+    return KTA_OK;
+}
+
 extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
     if (!h || !b) return fail(KTA_ERR_INVALID, "null argument");
     if (b->n < 0) return fail(KTA_ERR_INVALID, "negative n");
@@ -419,9 +567,11 @@ extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
         return fail(KTA_ERR_INVALID, "partition/ts_ms/key_len/value_len columns are required");
     int rc;
     if ((rc = set_device(h))) return rc;
+    uint64_t seq_base = 0;
+    if ((rc = resolve_seq_base(h, b, &seq_base))) return rc;
     ScanParams prm{};
     prm.n = b->n;
-    prm.seq_base = b->seq_base;
+    prm.seq_base = seq_base;
     prm.partition = b->partition;
     prm.ts_ms = b->ts_ms;
     prm.key_len = b->key_len;
@@ -444,7 +594,7 @@ extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
         prm.key_tile_base = h->d_tb_scratch;
     }
     if ((rc = launch_scan(h, prm, b->key_bytes_len, b->key_bytes_len))) return rc;
-    h->next_seq = std::max<uint64_t>(h->next_seq, b->seq_base + (uint64_t)b->n);
+    h->next_seq = std::max<uint64_t>(h->next_seq, seq_base + (uint64_t)b->n);
     return KTA_OK;
 }
 
@@ -474,6 +624,7 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     int rc;
     if ((rc = set_device(h))) return rc;
     if ((rc = ring_flush(h))) return rc;   // keep seq order with records pushed earlier
+    if (!h->pending.empty() && (rc = alive_check(h))) return rc;   // the decode scratch of an earlier call is about to be reused
     cudaStream_t s = h->stream;
     if (nbatches + 1 > h->log_batch_cap) {
         CU(cudaStreamSynchronize(s));
@@ -533,7 +684,7 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     }
     kta_batch b{};
     b.n = (int64_t)nrec;
-    b.seq_base = h->next_seq;
+    b.seq_base = KTA_SEQ_AUTO;
     b.partition = h->d_dec_part;
     b.ts_ms = h->d_dec_ts;
     b.key_len = h->d_dec_klen;
@@ -616,6 +767,8 @@ static int ring_dev_init(kta_handle *h) {
         CU(cudaMalloc(&c.d_keys, KB + 64));
         CU(cudaMalloc(&c.d_tile_base, (R / TILE + 2) * 8));
         CU(cudaEventCreateWithFlags(&c.free_ev, cudaEventDisableTiming));
+        CU(cudaHostAlloc(&c.h_status, 8, cudaHostAllocDefault));
+        c.h_status[0] = c.h_status[1] = 0;
     }
     h->ring_dev_ready = true;
     return KTA_OK;
@@ -664,14 +817,15 @@ static int ring_flush(kta_handle *h) {
     prm.key_bytes = c.d_keys;
     prm.key_tile_base = c.d_tile_base;
     int rc;
-    if ((rc = launch_scan(h, prm, (kb + 15) & ~(int64_t)15, kb))) return rc;
+    if ((rc = launch_scan(h, prm, (kb + 15) & ~(int64_t)15, kb, h->cur))) return rc;
+    if (h->d_alive_table) CU(cudaMemcpyAsync(c.h_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(c.free_ev, s));
     h->cur = (h->cur + 1) % NCHUNK;
     h->cur_n = 0;
     h->cur_kb = 0;
     // the next chunk may still be in flight from NCHUNK flushes ago
     CU(cudaEventSynchronize(h->chunks[h->cur].free_ev));
-    return KTA_OK;
+    return alive_release_chunk(h, h->cur);
 }
 
 extern "C" int kta_push(kta_handle *h, int32_t partition, int64_t offset, int64_t ts_ms, const uint8_t *key,
@@ -720,7 +874,10 @@ extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
     if ((rc = set_device(h))) return rc;
     if ((rc = ring_flush(h))) return rc;  // keep seq order with earlier kta_push records
     if ((rc = ring_dev_init(h))) return rc;
+    uint64_t seq_base = 0;
+    if ((rc = resolve_seq_base(h, b, &seq_base))) return rc;
     cudaStream_t s = h->stream;
+    const bool use_seq = b->seq && h->cfg.count_alive_keys == 1;
     std::vector<uint64_t> tb_host;  // only when the caller gave no tile bases
     uint64_t koff = 0;              // absolute key byte offset of the next chunk's first key
     int64_t r0 = 0;
@@ -728,50 +885,52 @@ extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
         int64_t cn = std::min<int64_t>(h->ring_records, b->n - r0);
         const int ci = h->cur;
         Chunk &c = h->chunks[ci];
-        CU(cudaEventSynchronize(c.free_ev));
         uint64_t k0 = 0, k1 = 0;
         const uint64_t *tb_src = nullptr;
         if (hash) {
+            // the chunk ends at a tile boundary chosen so that its keys fit the staging buffer; only a SINGLE tile
+            // whose keys exceed ring_key_bytes cannot be staged
+            const int64_t tiles_max = (cn + TILE - 1) / TILE;
+            int64_t tiles = 0;
             if (b->key_tile_base) {
-                // shrink the chunk until its keys fit the staging buffer
-                for (;;) {
-                    k0 = b->key_tile_base[r0 / TILE];
-                    k1 = b->key_tile_base[(r0 + cn + TILE - 1) / TILE];
-                    if ((int64_t)(k1 - k0) <= h->ring_key_bytes || cn <= TILE) break;
-                    cn = std::max<int64_t>(TILE, (cn / 2 + TILE - 1) / TILE * TILE);
-                }
-                tb_src = b->key_tile_base + r0 / TILE;
+                const uint64_t *tb = b->key_tile_base + r0 / TILE;
+                k0 = tb[0];
+                // largest t with tb[t] - k0 <= ring_key_bytes (tile bases are non-decreasing)
+                tiles = std::upper_bound(tb, tb + tiles_max + 1, k0 + (uint64_t)h->ring_key_bytes) - tb - 1;
+                tiles = std::min<int64_t>(tiles, tiles_max);
+                if (tiles >= 1) k1 = tb[tiles];
+                tb_src = tb;
             } else {
-                tb_host.resize((size_t)(cn / TILE + 2));
+                tb_host.resize((size_t)tiles_max + 1);
                 uint64_t acc = koff;
-                int64_t i = 0;
-                for (; i < cn; i++) {
-                    if ((i & (TILE - 1)) == 0) {
-                        if ((int64_t)(acc - koff) > h->ring_key_bytes - (int64_t)TILE * 64 && i > 0) break;
-                        tb_host[(size_t)(i / TILE)] = acc;
-                    }
-                    const int32_t v = b->key_len[r0 + i];
-                    acc += v > 0 ? (uint64_t)v : 0;
+                tb_host[0] = acc;
+                for (; tiles < tiles_max; tiles++) {
+                    const int64_t lo = r0 + tiles * TILE, hi = std::min<int64_t>(lo + TILE, r0 + cn);
+                    uint64_t tile_bytes = 0;
+                    for (int64_t i = lo; i < hi; i++) tile_bytes += b->key_len[i] > 0 ? (uint64_t)b->key_len[i] : 0;
+                    if (acc + tile_bytes - koff > (uint64_t)h->ring_key_bytes) break;
+                    acc += tile_bytes;
+                    tb_host[(size_t)tiles + 1] = acc;
                 }
-                if (i < cn) {  // stopped early at a tile boundary: recompute the end of the last tile
-                    cn = i;
-                }
-                tb_host[(size_t)((cn + TILE - 1) / TILE)] = acc;
                 k0 = koff;
                 k1 = acc;
                 tb_src = tb_host.data();
             }
-            if ((int64_t)(k1 - k0) > h->ring_key_bytes)
-                return fail(KTA_ERR_INVALID, "keys of one %d-record tile span %llu bytes > ring_key_bytes %lld", TILE,
-                            (unsigned long long)(k1 - k0), (long long)h->ring_key_bytes);
+            if (tiles < 1)
+                return fail(KTA_ERR_INVALID, "the keys of one %d-record tile (records %lld..) exceed ring_key_bytes %lld; "
+                            "%lld earlier record(s) of this batch were scanned", TILE, (long long)r0, (long long)h->ring_key_bytes,
+                            (long long)r0);
+            cn = std::min<int64_t>(cn, tiles * TILE);
         }
+        // chunk ci's buffers are about to be overwritten: wait for the scan that read them and confirm its stamps
+        CU(cudaEventSynchronize(c.free_ev));
+        if ((rc = alive_release_chunk(h, ci))) return rc;
         const int64_t ntiles = (cn + TILE - 1) / TILE;
         CU(cudaMemcpyAsync(c.d_partition, b->partition + r0, cn * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(c.d_ts, b->ts_ms + r0, cn * 8, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(c.d_klen, b->key_len + r0, cn * 4, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(c.d_vlen, b->value_len + r0, cn * 4, cudaMemcpyHostToDevice, s));
-        if (b->seq && h->cfg.count_alive_keys == 1)
-            CU(cudaMemcpyAsync(c.d_seq, b->seq + r0, cn * 8, cudaMemcpyHostToDevice, s));
+        if (use_seq) CU(cudaMemcpyAsync(c.d_seq, b->seq + r0, cn * 8, cudaMemcpyHostToDevice, s));
         ScanParams prm{};
         if (hash) {
             // keep absolute offsets: place the keys so that (virtual base + k0) is where they land and the
@@ -783,13 +942,14 @@ extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
             prm.key_tile_base = c.d_tile_base;
         }
         prm.n = cn;
-        prm.seq_base = b->seq_base + (uint64_t)r0;
+        prm.seq_base = seq_base + (uint64_t)r0;
         prm.partition = c.d_partition;
         prm.ts_ms = c.d_ts;
         prm.key_len = c.d_klen;
         prm.value_len = c.d_vlen;
-        prm.seq = (b->seq && h->cfg.count_alive_keys == 1) ? c.d_seq : nullptr;
-        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull), (int64_t)(k1 - k0)))) return rc;
+        prm.seq = use_seq ? c.d_seq : nullptr;
+        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull), (int64_t)(k1 - k0), ci))) return rc;
+        if (h->d_alive_table) CU(cudaMemcpyAsync(c.h_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, s));
         CU(cudaEventRecord(c.free_ev, s));
         h->cur = (h->cur + 1) % NCHUNK;
         koff = k1;
@@ -799,7 +959,7 @@ extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
     CU(cudaStreamSynchronize(s));
     int rc2;
     if ((rc2 = collect_timing(h))) return rc2;
-    h->next_seq = std::max<uint64_t>(h->next_seq, b->seq_base + (uint64_t)b->n);
+    h->next_seq = std::max<uint64_t>(h->next_seq, seq_base + (uint64_t)b->n);
     return KTA_OK;
 }
 
@@ -809,6 +969,7 @@ extern "C" int kta_sync(kta_handle *h) {
     if ((rc = set_device(h))) return rc;
     if ((rc = ring_flush(h))) return rc;
     CU(cudaStreamSynchronize(h->stream));
+    if ((rc = alive_check(h))) return rc;
     return collect_timing(h);
 }
 
@@ -831,11 +992,12 @@ extern "C" int kta_finalize(kta_handle *h) {
     if ((rc = set_device(h))) return rc;
     if ((rc = ring_flush(h))) return rc;
     cudaStream_t s = h->stream;
+    if ((rc = alive_check(h))) return rc;   // every stamp has landed (grows the table and re-runs batches if it was too small)
     if (h->d_alive_table && h->nhll) {
         // EXTENSION: with -c the sketch describes the resolved alive set, so it is rebuilt from the table
         CU(cudaMemsetAsync(h->d_hll, 0, h->nhll * 4, s));
-        alive_hll_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, h->d_alive_dirty, 1u << (32 - DIRTY_SHIFT),
-                                                             (uint64_t)h->epoch << 48, h->d_hll, h->cfg.hll_precision);
+        alive_hll_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, (size_t)h->alive_pairs * 2, h->d_hll,
+                                                             h->cfg.hll_precision);
         CU(cudaGetLastError());
         h->launches++;
     }
@@ -850,10 +1012,16 @@ extern "C" int kta_finalize(kta_handle *h) {
     if ((rc = collect_timing(h))) return rc;
     h->h_alive = alive;
     h->finalized = true;
+    if (h->alive_window_errors)
+        return fail(KTA_ERR_INVALID, "%llu record(s) carried a sequence number outside the alive-key table's window "
+                    "[origin, origin + 2^31 - 2): with an explicit seq column the span between kta_reset calls is limited",
+                    (unsigned long long)h->alive_window_errors);
+    // Records with a partition outside [0, P) took part in nothing (no counter, no extremum, no alive key): the getters
+    // are valid and describe the in-range records; the status tells the caller that some were left out.
     const uint64_t bad = h->h_sums[h->nsums - 1];
     if (bad)
-        return fail(KTA_ERR_PARTITION, "%llu record(s) had a partition outside [0, %d)", (unsigned long long)bad,
-                    h->cfg.num_partitions);
+        return fail(KTA_ERR_PARTITION, "%llu record(s) had a partition outside [0, %d) and were left out of every metric",
+                    (unsigned long long)bad, h->cfg.num_partitions);
     return KTA_OK;
 }
 
@@ -990,6 +1158,14 @@ extern "C" int kta_alive_keys(const kta_handle *h, uint64_t *out) {
     return KTA_OK;
 }
 
+extern "C" int kta_bad_partition_records(const kta_handle *h, uint64_t *out) {
+    if (!out) return fail(KTA_ERR_INVALID, "bad argument");
+    const int rc = check_read(h, 0, false);
+    if (rc) return rc;
+    *out = h->h_sums[h->nsums - 1];
+    return KTA_OK;
+}
+
 extern "C" int kta_hist(const kta_handle *h, int which, int32_t partition, uint64_t out[KTA_HIST_BUCKETS]) {
     if (!out || which < 0 || which > 1) return fail(KTA_ERR_INVALID, "bad argument");
     const int rc = check_read(h, partition, true);
@@ -1099,6 +1275,7 @@ extern "C" int kta_merge_export_device(kta_handle *h, int32_t rank, int32_t worl
     int rc;
     if ((rc = set_device(h))) return rc;
     if ((rc = ring_flush(h))) return rc;
+    if (!h->pending.empty() && (rc = alive_check(h))) return rc;
     merge_export_kernel<<<h->sm_count, 256, 0, h->stream>>>(h->d_sums, h->nsums, h->d_minmax, h->d_hll, h->nhll, rank,
                                                            world, reinterpret_cast<unsigned long long *>(dev_buf));
     h->launches++;
@@ -1132,9 +1309,13 @@ static int alive_export(kta_handle *h, int mode, uint32_t *dh, uint64_t *ds, int
     int rc;
     if ((rc = set_device(h))) return rc;
     if ((rc = ring_flush(h))) return rc;
+    if ((rc = alive_check(h))) return rc;
+    if (h->alive_rebased)
+        return fail(KTA_ERR_INVALID, "the alive-key table was rebased (more than 2^31 sequence numbers since kta_reset): its "
+                    "entries no longer carry absolute sequence numbers and cannot be merged across GPUs");
     CU(cudaMemsetAsync(h->d_scalar + 1, 0, 8, h->stream));
     alive_export_kernel<<<h->sm_count * 8, THREADS, 0, h->stream>>>(
-        h->d_alive_table, h->d_alive_dirty, 1u << (32 - DIRTY_SHIFT), (uint64_t)h->epoch << 48, mode, h->d_scalar + 1, dh,
+        h->d_alive_table, (size_t)h->alive_pairs * 2, h->alive_origin, mode, h->d_scalar + 1, dh,
         reinterpret_cast<unsigned long long *>(ds), (unsigned long long)cap);
     h->launches++;
     CU(cudaGetLastError());
@@ -1159,13 +1340,24 @@ extern "C" int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, 
     if (count == 0) return KTA_OK;
     int rc;
     if ((rc = set_device(h))) return rc;
-    alive_import_kernel<<<(int)std::min<int64_t>((count + THREADS - 1) / THREADS, (int64_t)h->sm_count * 8), THREADS, 0,
-                          h->stream>>>(h->d_alive_table, h->d_alive_dirty, (uint64_t)h->epoch << 48, dev_hash,
-                                       reinterpret_cast<const unsigned long long *>(dev_stamp), count, h->d_scalar);
-    h->launches++;
-    CU(cudaGetLastError());
+    if ((rc = alive_check(h))) return rc;   // nothing pending: a re-run below only concerns the imported stamps
+    const int grid = (int)std::min<int64_t>((count + THREADS - 1) / THREADS, (int64_t)h->sm_count * 8);
+    for (int round = 0;; round++) {
+        const AliveTable t{h->d_alive_table, h->alive_pairs, h->d_alive_status, 0};
+        alive_import_kernel<<<grid, THREADS, 0, h->stream>>>(t, h->alive_origin, dev_hash,
+                                                             reinterpret_cast<const unsigned long long *>(dev_stamp), count, h->d_scalar);
+        h->launches++;
+        CU(cudaGetLastError());
+        // the imported list is the caller's and still valid: if the table was too small, alive_check grew it (nothing
+        // is pending, so it re-ran nothing) and the import is simply applied again — stamping is idempotent
+        CU(cudaMemcpyAsync(h->h_alive_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        const bool dropped = h->h_alive_status[0] != 0;
+        if ((rc = alive_check(h))) return rc;
+        if (!dropped) break;
+        if (round > 40) return fail(KTA_ERR_INVALID, "alive-key table growth did not converge");
+    }
     h->finalized = false;
-    CU(cudaStreamSynchronize(h->stream));
     return KTA_OK;
 }
 
@@ -1176,6 +1368,21 @@ extern "C" int kta_stats(const kta_handle *h, uint64_t *kernel_launches, uint64_
     if (!h) return fail(KTA_ERR_INVALID, "null handle");
     if (kernel_launches) *kernel_launches = h->launches;
     if (records_scanned) *records_scanned = h->records;
+    return KTA_OK;
+}
+
+extern "C" int kta_alive_table_stats(kta_handle *h, uint64_t *slots, uint64_t *occupied, uint64_t *grows, uint64_t *reruns) {
+    if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    if (!h->d_alive_table) return fail(KTA_ERR_NOT_ENABLED, "count_alive_keys was not enabled");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    unsigned long long occ = 0;
+    CU(cudaMemcpyAsync(&occ, h->d_scalar + 2, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (slots) *slots = (uint64_t)h->alive_pairs * 2;
+    if (occupied) *occupied = occ;
+    if (grows) *grows = h->alive_grows;
+    if (reruns) *reruns = h->alive_reruns;
     return KTA_OK;
 }
 

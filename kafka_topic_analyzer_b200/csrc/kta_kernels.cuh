@@ -7,7 +7,9 @@
 // tiles, per-partition counters live in shared memory (u32 + carry word, native ATOMS), the tile's
 // packed key bytes are staged global→shared with one bulk async copy (cp.async.bulk / UBLKCP, mbarrier
 // completion, double buffered), keys are hashed from shared memory, and the alive-key state is a
-// direct-mapped 2^32-entry table of 64-bit last-writer stamps in HBM (32 GiB of the 180 GB).
+// compact open-addressed table of 64-bit last-writer stamps (hash | seq | alive) sized by the number
+// of distinct key hashes — about the size of the 126 MB L2 for 1e7 keys — so that the one random access every
+// record needs is an L2 hit, not a DRAM sector.
 // No tensor cores: there is no dense contraction anywhere on this path.
 #pragma once
 #include <cuda_runtime.h>
@@ -34,7 +36,6 @@ constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_
 __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf) { return hash ? 128 + 2 * (size_t)keybuf : 128; }
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
-constexpr int DIRTY_SHIFT = 13;           // alive table: one dirty flag per 8192 entries (64 KiB)
 constexpr int FOLD_TILES = 8;             // every warp checks the CTA's 16-bit-split sums after every 8th tile of its own
 
 // shared-memory counter rows (each row = P u32 words):
@@ -73,10 +74,14 @@ struct ScanParams {
     uint32_t *hll;                   // [1 << hll_p] registers (one u32 each so that RED.MAX applies)
     uint32_t *hll_floor;             // [0] lower bound of every register (monotone; lets most records skip the
                                      // table), [1..HLL_SLICES] per-slice minima it is derived from
-    unsigned long long *alive_table; // [2^32] stamps: epoch(16) | seq+1 (47) | alive(1)
-    uint8_t *alive_dirty;            // [2^32 >> DIRTY_SHIFT]
-    unsigned long long *alive_count; // running number of alive entries of the current epoch (two's-complement deltas)
-    uint64_t epoch_tag;              // current epoch << 48
+    unsigned long long *alive_table; // [2 * alive_pairs] stamps: hash(32) | seq - alive_origin + 1 (31) | alive(1); ~0 = empty
+    uint32_t alive_pairs;            // table size in 16-byte pairs of slots (any value >= 1, not only powers of two)
+    int32_t alive_only;              // 1: MODE_EXACT re-run after the table grew — stamps only, no counters / extrema
+    uint64_t alive_origin;           // seq that field value 1 stands for (moved forward by a rebase)
+    uint64_t alive_fbase;            // seq_base - alive_origin + 1: the field of record 0 when seq is implicit
+    unsigned long long *alive_count; // [0] alive entries (two's-complement deltas), [1] export cursor, [2] occupied slots
+    uint32_t *alive_status;          // [0] stamps that found no slot (table too full: host grows it and re-runs the
+                                     //     batch), [1] records whose seq lies outside the 31-bit window of the table
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
 };
 
@@ -116,6 +121,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol)
         : "memory");
 }
 // shared-memory reductions on 32-bit shared-window addresses (no generic→shared conversion in the loop)
@@ -165,6 +176,17 @@ __device__ __forceinline__ int64_t ld_stream_s64(const int64_t *p) {
 __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t *p) {
     uint64_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+// the same with an L2 eviction policy (MODE_EXACT: the stream must not push the alive table out of L2)
+__device__ __forceinline__ int32_t ld_stream_s32(const int32_t *p, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int64_t ld_stream_s64(const int64_t *p, uint64_t pol) {
+    int64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) {  // L2-coherent read
@@ -415,27 +437,122 @@ struct Counters {
 };
 
 // ------------------------------------------------------------------------------------------------
-// alive-key table (LogCompactionInMemoryMetrics, metric.rs:262-305).  table[hash] = the stamp of the LAST
-// record that carried this hash: epoch (16 bits) | seq + 1 (47 bits) | alive (1 bit); atomicMax makes
-// "last" mean highest seq regardless of execution order.  The epoch makes kta_reset O(1): stamps of an older
-// epoch lose against any new stamp and count as "never seen".  The number of alive entries (sum_all_alive,
-// metric.rs:282-284) is maintained incrementally from the value atomicMax returns — the chain of successful
-// updates of one entry telescopes to (final alive − initial alive) — so no pass over the 32 GiB table is needed.
+// alive-key table (LogCompactionInMemoryMetrics, metric.rs:262-305): an open-addressed table with one 64-bit entry per
+// distinct key hash,
+//     hash (32 bits) | seq - origin + 1 (31 bits) | alive (1 bit),          ~0 = empty,
+// holding the stamp of the LAST record that carried this hash.  The reference's BitSet (metric.rs:273-280) is indexed by
+// the hash itself — 2^32 bits, one random DRAM sector per record wherever the state lives; keyed by hash but SIZED by
+// the number of distinct hashes, the same state is about as large as the 126 MB L2 for 1e7 keys, and the one access per
+// record becomes an L2 hit.
+//   * A slot is claimed once (CAS from empty) and keeps its hash for ever; linear probing over 16-byte PAIRS of slots
+//     from home = mulhi(fmix32(hash), pairs), so any table size works, not only powers of two.
+//   * On a slot that holds the record's hash, atomicMax makes "last" mean highest seq regardless of execution order
+//     (the hash sits in the top bits, so max over equal-hash stamps is max over seq).  Entries only grow, so a plain
+//     read is a safe filter: a record that is not the newest for its hash stops after one 16-byte read.  The scan walks
+//     each batch from its newest tile to its oldest, so for a key written k times about (k-1)/k of its records take
+//     that exit.
+//   * sum_all_alive (metric.rs:282-284) is maintained incrementally from the value atomicMax returns — the chain of
+//     successful updates of one entry telescopes to (final alive - initial alive) — so finalize never scans the table.
+//   * 31 bits of seq: when a batch would not fit the window the host REBASES (every entry keeps hash and alive bit, its
+//     seq field drops to 0: older than everything that follows, which is all a later record needs to know).
+//   * A stamp that finds neither its hash nor an empty slot within ALIVE_MAX_PROBES pairs is counted in status[0] and
+//     dropped; the host then grows the table (rehash) and re-runs the batch stamps-only — stamping is idempotent.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int alive_stamp(unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag, uint32_t hash,
-                                           uint64_t seq_plus_1, bool alive) {
-    const unsigned long long stamp = epoch_tag | (seq_plus_1 << 1) | (alive ? 1ull : 0ull);
-    // Entries only grow, so a plain (possibly stale, never too large) read is a safe filter: a record that is not
-    // the newest for its hash stops here with one 32-byte sector read instead of an atomic read-modify-write.
-    // The scan walks each batch from its newest tile to its oldest, so for a key written k times about (k-1)/k
-    // of its records take this exit.
-    if (__ldcg(table + hash) >= stamp) return 0;
-    const unsigned long long old = atomicMax(table + hash, stamp);
-    uint8_t *d = dirty + (hash >> DIRTY_SHIFT);
-    if (__ldca(d) == 0) *d = 1;
-    if (stamp <= old) return 0;   // a later record already spoke for this hash
-    const int was = ((old ^ epoch_tag) >> 48) == 0 ? (int)(old & 1ull) : 0;
-    return (int)alive - was;
+constexpr unsigned long long ALIVE_EMPTY = ~0ull;
+constexpr uint32_t ALIVE_FIELD_MAX = 0x7ffffffeu;   // largest seq field: a stamp's low word is <= 0xfffffffd, never ~0
+constexpr int ALIVE_MAX_PROBES = 96;                // pairs examined before a stamp gives up
+
+#ifndef KTA_L2_HINTS
+#define KTA_L2_HINTS 1
+#endif
+// L2 residency control for MODE_EXACT: the table should stay in L2, the record stream should leave it at once.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ ulonglong2 alive_ld_pair(const unsigned long long *p, uint64_t pol) {
+    ulonglong2 v;
+#if KTA_L2_HINTS
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
+#else
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+#endif
+    return v;
+}
+__device__ __forceinline__ unsigned long long alive_atom_max(unsigned long long *p, unsigned long long v, uint64_t pol) {
+    unsigned long long old;
+#if KTA_L2_HINTS
+    asm volatile("atom.global.max.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(v), "l"(pol) : "memory");
+#else
+    old = atomicMax(p, v);
+#endif
+    return old;
+}
+// (atom.cas takes no cache-policy operand in PTX: a claim is a plain compare-and-swap)
+__device__ __forceinline__ unsigned long long alive_atom_cas(unsigned long long *p, unsigned long long cmp, unsigned long long v,
+                                                             uint64_t) {
+    return atomicCAS(p, cmp, v);
+}
+
+__host__ __device__ __forceinline__ uint32_t alive_home(uint32_t hash, uint32_t npairs) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(hll_mix(hash), npairs);
+#else
+    return (uint32_t)(((uint64_t)hll_mix(hash) * npairs) >> 32);
+#endif
+}
+
+struct AliveTable {
+    unsigned long long *slots;
+    uint32_t npairs;
+    uint32_t *status;
+    uint64_t pol;       // L2 evict_last policy for the table's lines
+};
+
+// The general stamp: probe from `pair` until the hash or an empty slot is found.
+// Returns (change of the alive-entry count, two's complement in bits 0..1) | (claimed a fresh slot) << 2.
+__device__ __noinline__ int alive_stamp_slow(const AliveTable t, uint32_t pair, uint32_t hash, uint32_t low) {
+    const unsigned long long stamp = ((unsigned long long)hash << 32) | low;
+    for (int probe = 0; probe < ALIVE_MAX_PROBES; probe++) {
+        unsigned long long *slot = t.slots + 2 * (size_t)pair;
+        const ulonglong2 e = alive_ld_pair(slot, t.pol);
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            unsigned long long v = s ? e.y : e.x;
+            if (v == ALIVE_EMPTY) {
+                v = alive_atom_cas(slot + s, ALIVE_EMPTY, stamp, t.pol);
+                if (v == ALIVE_EMPTY) return (int)(low & 1u) | 4;   // first record of this hash: mark_key_alive / _dead on a fresh bit
+            }
+            if ((uint32_t)(v >> 32) == hash) {                      // v is a real entry here (never ALIVE_EMPTY)
+                if (v >= stamp) return 0;                           // a later record already spoke for this hash
+                const unsigned long long old = alive_atom_max(slot + s, stamp, t.pol);
+                if (stamp <= old) return 0;
+                return ((int)(low & 1u) - (int)(old & 1ull)) & 3;
+            }
+        }
+        pair = pair + 1 == t.npairs ? 0 : pair + 1;
+    }
+    atomicAdd(t.status, 1u);   // table too full: the host grows it and re-runs this batch's stamps
+    return 0;
+}
+
+// plain insert of an entry whose hash is known to be absent (rehash into a fresh table)
+__device__ __forceinline__ bool alive_insert_unique(unsigned long long *slots, uint32_t npairs, unsigned long long entry) {
+    uint32_t pair = alive_home((uint32_t)(entry >> 32), npairs);
+    for (uint32_t probe = 0; probe < npairs; probe++) {
+        unsigned long long *slot = slots + 2 * (size_t)pair;
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+            if (__ldcg(slot + s) == ALIVE_EMPTY && atomicCAS(slot + s, ALIVE_EMPTY, entry) == ALIVE_EMPTY) return true;
+        pair = pair + 1 == npairs ? 0 : pair + 1;
+    }
+    return false;
 }
 
 // rare path: a tile with a key of >= 1 MiB — 64-bit offsets, keys read straight from global memory.
@@ -491,6 +608,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
     const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P};
+    // MODE_EXACT: the alive table's lines are asked to stay in L2 (evict_last), the record stream to leave first
+    constexpr bool HINTS = MODE == MODE_EXACT && KTA_L2_HINTS;
+    const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
+    const AliveTable AT{prm.alive_table, prm.alive_pairs, prm.alive_status, HINTS ? l2_policy_evict_last() : 0};
+    const bool count_it = !(MODE == MODE_EXACT && prm.alive_only);   // false: a stamps-only re-run after the table grew
 
     if (SMEM) {
         const int nw = P * SMEM_ROWS;
@@ -508,7 +630,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
 
     // lane 0: start the bulk copy of a tile's packed key bytes into stage b.
     // Returns the span descriptor: bit 0 staged, bits 1..4 = first key's offset inside its 16-byte line.
-    auto issue = [&](int64_t tile, int b) -> uint32_t {
+    auto issue = [&](int tile, int b) -> uint32_t {
         const uint64_t g0 = prm.key_tile_base[tile], g1 = prm.key_tile_base[tile + 1];
         const uint32_t a = (uint32_t)g0 & 15u;
         // the copy covers [g0 - a, roundup16(g1)).  Staged iff the tile has key bytes, the copy fits the stage
@@ -518,7 +640,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         if (ok) {
             const uint32_t bytes = ((uint32_t)(g1 - g0) + a + 15u) & ~15u;
             mbar_arrive_expect_tx(mbar + 8u * b, bytes);
-            bulk_g2s(keybuf + (uint32_t)b * KEYBUF, prm.key_bytes + (g0 - a), bytes, mbar + 8u * b);
+            if (HINTS) bulk_g2s(keybuf + (uint32_t)b * KEYBUF, prm.key_bytes + (g0 - a), bytes, mbar + 8u * b, pol_stream);
+            else bulk_g2s(keybuf + (uint32_t)b * KEYBUF, prm.key_bytes + (g0 - a), bytes, mbar + 8u * b);
         }
         return (ok ? 1u : 0u) | (a << 1);
     };
@@ -526,22 +649,26 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
-    int alive_delta = 0;      // MODE_EXACT, direct stamping: change of the alive-entry count caused by this lane
+    int alive_delta = 0;      // MODE_EXACT: change of the alive-entry count caused by this lane
+    uint32_t alive_claims = 0;   // MODE_EXACT: table slots this lane claimed (distinct hashes first seen)
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     uint32_t nxt_info = 0;
 
     // MODE_EXACT walks the batch from its newest tile to its oldest (see alive_stamp); the other modes ascend
-    auto phys = [&](int64_t t) { return MODE == MODE_EXACT ? prm.ntiles - 1 - t : t; };
-    const int64_t gstride = (int64_t)gridDim.x * nwarps;
-    int64_t tile = (int64_t)blockIdx.x * nwarps + warp;
-    if (HASH && lane == 0 && tile < prm.ntiles) nxt_info = issue(phys(tile), 0);
+    // tile indices fit 32 bits (the host refuses batches of 2^31 tiles = 2.7e11 records): the loop control stays out of
+    // 64-bit arithmetic and out of local memory
+    const int ntiles = (int)prm.ntiles;
+    auto phys = [&](int t) { return MODE == MODE_EXACT ? ntiles - 1 - t : t; };
+    const int gstride = (int)gridDim.x * nwarps;
+    int tile = (int)blockIdx.x * nwarps + warp;
+    if (HASH && lane == 0 && tile < ntiles) nxt_info = issue(phys(tile), 0);
 
     // the body of one tile; FULL = every record of the tile exists (no tail predicates)
-    auto body = [&](auto full_tag, int64_t tile, int buf, uint32_t info, bool has_next) {
+    auto body = [&](auto full_tag, int tile, int buf, uint32_t info, bool has_next) {
         constexpr bool FULL = decltype(full_tag)::value;
         // ---- header columns: 4 rows of 32 consecutive records, fully coalesced ----
-        const int64_t rbase = tile * TILE + lane;
+        const int64_t rbase = (int64_t)tile * TILE + lane;
         int p[ROWS], kl[ROWS], vl[ROWS];
         long long ts[ROWS];
         bool valid[ROWS];
@@ -550,22 +677,60 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             const int64_t r = rbase + 32 * k;
             valid[k] = FULL || r < prm.n;
             if (valid[k]) {
-                p[k] = ld_stream_s32(prm.partition + r);
-                ts[k] = ld_stream_s64(prm.ts_ms + r);
-                kl[k] = ld_stream_s32(prm.key_len + r);
-                vl[k] = ld_stream_s32(prm.value_len + r);
+                if (HINTS) {
+                    p[k] = ld_stream_s32(prm.partition + r, pol_stream);
+                    ts[k] = ld_stream_s64(prm.ts_ms + r, pol_stream);
+                    kl[k] = ld_stream_s32(prm.key_len + r, pol_stream);
+                    vl[k] = ld_stream_s32(prm.value_len + r, pol_stream);
+                } else {
+                    p[k] = ld_stream_s32(prm.partition + r);
+                    ts[k] = ld_stream_s64(prm.ts_ms + r);
+                    kl[k] = ld_stream_s32(prm.key_len + r);
+                    vl[k] = ld_stream_s32(prm.value_len + r);
+                }
             } else {
                 p[k] = 0; ts[k] = INT64_MAX; kl[k] = -1; vl[k] = -1;
             }
         }
         // ---- MessageMetrics::handle_message (metric.rs:206-253) ----
+        // A record whose partition lies outside [0, P) is counted in `bad` and takes part in NOTHING else (counters, extrema,
+        // alive keys, sketch), so the state stays consistent; its key bytes still occupy their place in the packed keys.
+        bool use[ROWS];
         bool inrange = true;
 #pragma unroll
-        for (int k = 0; k < ROWS; k++) inrange = inrange && (unsigned)p[k] < (unsigned)P;
-        if (FULL && __all_sync(full, inrange)) {
+        for (int k = 0; k < ROWS; k++) {
+            use[k] = valid[k] && (unsigned)p[k] < (unsigned)P;
+            inrange = inrange && (unsigned)p[k] < (unsigned)P;
+        }
+        const bool clean = FULL && __all_sync(full, inrange);   // warp-uniform: every record of the tile exists and counts
+        if (!count_it) {
+            // stamps-only re-run: the counters and extrema of this batch were taken by the first pass
+        } else if (clean) {
             if (try_uni) {
-                // run-structured input (a Kafka fetch delivers long runs of one partition): the byte sums of a row that
-                // lies inside one run are reduced in the warp (2 REDUX) and added once, instead of 32 same-address adds
+                // run-structured input (a Kafka fetch delivers long runs of one partition).
+                // A whole tile inside one run (3 of 4 tiles at run length 500): one vote, the lane's four lengths added up
+                // first, two warp reductions and two adds for the tile
+                const int p0t = __shfl_sync(full, p[0], 0);
+                uint32_t kv4 = 0, vv4 = 0, big = 0;
+                bool one = true;
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    const uint32_t kv = (uint32_t)max(kl[k], 0), vv = (uint32_t)max(vl[k], 0);
+                    one = one && p[k] == p0t;
+                    kv4 += kv; vv4 += vv; big |= kv | vv;
+                }
+                if (__all_sync(full, one && big < (1u << 24))) {
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) C.buckets(p0t, kl[k], vl[k]);
+                    const uint32_t ks = __reduce_add_sync(full, kv4);   // 128 lengths < 2^24: no overflow
+                    const uint32_t vs = __reduce_add_sync(full, vv4);
+                    if (lane == 0) {
+                        C.sum_add(0, p0t, ks);
+                        C.sum_add(1, p0t, vs);
+                    }
+                } else {
+                // otherwise row by row: the byte sums of a row that lies inside one run are reduced in the warp (2 REDUX)
+                // and added once, instead of 32 same-address adds
                 bool any_uni = false;
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
@@ -607,6 +772,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                     }
                 }
                 try_uni = any_uni;
+                }
             } else {
                 C.record_rows(p, kl, vl);
             }
@@ -614,10 +780,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // tail tile, or a record with a partition outside [0, P): per-record checks
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                if (valid[k]) {
-                    if ((unsigned)p[k] < (unsigned)P) C.record(p[k], kl[k], vl[k]);
-                    else bad++;
-                }
+                if (use[k]) C.record(p[k], kl[k], vl[k]);
+                else if (valid[k]) bad++;
             }
         }
         // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back: the raw
@@ -625,7 +789,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         // Timestamps of one topic share their high word for 49 days at a time: when the lane's four and its running
         // extrema do, the signed 64-bit order is the unsigned order of the low words (2 + 2 three-input min/max).
         bool ts_fast = false;
-        if (FULL) {
+        if (clean && count_it) {
             const uint32_t hw = hi32(tmin);
             uint32_t x = hi32(tmax) ^ hw;
 #pragma unroll
@@ -639,22 +803,25 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             const uint32_t hi = max(max(max(l0, l1), l2), max(l3, (uint32_t)tmax));
             tmin = pack64(lo, hw);
             tmax = pack64(hi, hw);
-        } else {
+        } else if (count_it) {
             asm volatile("");   // keep this a real branch: if-converted, the 64-bit chain runs every tile
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                tmin = ts[k] < tmin ? ts[k] : tmin;
-                const long long tm = (FULL || valid[k]) ? ts[k] : INT64_MIN;
-                tmax = tm > tmax ? tm : tmax;
+                const bool u = clean || use[k];
+                const long long t0 = u ? ts[k] : INT64_MAX, t1 = u ? ts[k] : INT64_MIN;
+                tmin = t0 < tmin ? t0 : tmin;
+                tmax = t1 > tmax ? t1 : tmax;
             }
         }
+        if (count_it) {
 #pragma unroll
-        for (int k = 0; k < ROWS; k++) {
-            // metric.rs:249-251: size extrema, not for tombstones (invalid rows carry vl = -1)
-            const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
-            if (vl[k] >= 0) {
-                smin = min(smin, sz);
-                smax = max(smax, sz);
+            for (int k = 0; k < ROWS; k++) {
+                // metric.rs:249-251: size extrema, not for tombstones (rows that do not exist carry vl = -1)
+                const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
+                if (vl[k] >= 0 && (clean || use[k])) {
+                    smin = min(smin, sz);
+                    smax = max(smax, sz);
+                }
             }
         }
 
@@ -673,14 +840,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             const bool small = L < (1 << 20);              // warp-uniform
             const bool fix16 = fixL && L == 16;
             if (fixL) {
-                // fixed-width keys (the common case: ids, hashes, UUIDs): offsets from ballots, no shuffle scan
-                uint32_t before = 0;
+                // fixed-width keys (the common case: ids, hashes, UUIDs)
                 const uint32_t Lu = (uint32_t)max(L, 0);
+                if (!__any_sync(full, (kl[0] | kl[1] | kl[2] | kl[3]) < 0)) {
+                    // no null key in the tile (every tile of a keyed / compacted topic): record r's key is the r-th
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    const unsigned m = __ballot_sync(full, kl[k] >= 0);
-                    off[k] = Lu * (before + __popc(m & lt_mask));
-                    before += __popc(m);
+                    for (int k = 0; k < ROWS; k++) off[k] = Lu * (uint32_t)(32 * k + lane);
+                } else {
+                    // offsets from ballots, no shuffle scan
+                    uint32_t before = 0;
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {
+                        const unsigned m = __ballot_sync(full, kl[k] >= 0);
+                        off[k] = Lu * (before + __popc(m & lt_mask));
+                        before += __popc(m);
+                    }
                 }
             } else {
                 static_assert(ROWS == 4, "the packed scan below handles exactly four rows");
@@ -771,14 +945,45 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             if (MODE == MODE_EXACT) {
                 // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
                 // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
-                // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
+                // (metric.rs:295 mark_key_alive, :298 mark_key_dead).  All four probes are in flight before the first
+                // is looked at; a record that finds its hash with a stamp at least as new is done after that one read.
+                uint32_t pair[ROWS], low[ROWS];
+                ulonglong2 e[ROWS];
+                bool live[ROWS];
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
-                    if (valid[k] && kl[k] >= 0) {
-                        const int64_t r = rbase + 32 * k;
-                        const uint64_t seq = prm.seq ? ld_stream_u64(prm.seq + r) : prm.seq_base + (uint64_t)r;
-                        alive_delta += alive_stamp(prm.alive_table, prm.alive_dirty, prm.epoch_tag, h[k], seq + 1ull,
-                                                   vl[k] >= 0);
+                    live[k] = (clean || use[k]) && kl[k] >= 0;
+                    const int64_t r = rbase + 32 * k;
+                    uint32_t field;
+                    if (prm.seq) {
+                        // explicit global sequence numbers (partition-sharded scans): must fall into the table's window
+                        const uint64_t f = live[k] ? ld_stream_u64(prm.seq + r) - prm.alive_origin + 1ull : 1ull;
+                        if (f - 1ull >= (uint64_t)ALIVE_FIELD_MAX) {
+                            atomicAdd(prm.alive_status + 1, 1u);
+                            live[k] = false;
+                        }
+                        field = (uint32_t)f;
+                    } else {
+                        field = (uint32_t)prm.alive_fbase + (uint32_t)r;   // host-checked: seq_base + n fits the window
+                    }
+                    low[k] = (field << 1) | (vl[k] >= 0 ? 1u : 0u);
+                    pair[k] = alive_home(h[k], AT.npairs);
+                    if (live[k]) e[k] = alive_ld_pair(AT.slots + 2 * (size_t)pair[k], AT.pol);
+                }
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    if (live[k]) {
+                        const bool hx = hi32((long long)e[k].x) == h[k], hy = hi32((long long)e[k].y) == h[k];
+                        const uint32_t seen = hx ? (uint32_t)e[k].x : (uint32_t)e[k].y;
+                        // equal hash ⇒ the stamps compare like their low words.  A real low word is <= 0xfffffffd and the
+                        // empty pattern's is 0xffffffff, so "seen + 1 > low" is "seen >= low" for real entries and false
+                        // for an empty slot that happens to sit under hash 0xffffffff.
+                        const bool newer = (hx || hy) && seen + 1u > low[k];
+                        if (!newer) {
+                            const int r = alive_stamp_slow(AT, pair[k], h[k], low[k]);
+                            alive_delta += (r << 30) >> 30;
+                            alive_claims += (uint32_t)r >> 2;
+                        }
                     }
                 }
             }
@@ -791,7 +996,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 for (int k = 0; k < ROWS; k++) {
                     // in-stream sketch: every record with a key and a value (invalid rows carry kl = vl = -1)
                     const uint32_t x = hll_mix(h[k]);
-                    if (((x & skip_mask) | (uint32_t)((kl[k] | vl[k]) >> 31)) == 0) hll_raise(prm.hll, prm.hll_p, x);
+                    if (((x & skip_mask) | (uint32_t)((kl[k] | vl[k]) >> 31)) == 0 && (clean || use[k])) hll_raise(prm.hll, prm.hll_p, x);
                 }
             }
 #else
@@ -802,16 +1007,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         }
     };
 
-    for (int it = 0; tile < prm.ntiles; tile += gstride, ++it) {
+    for (int it = 0; tile < ntiles; tile += gstride, ++it) {
         const int buf = it & 1;
         uint32_t info = 0;
         if (HASH) {
             info = __shfl_sync(full, nxt_info, 0);   // also: every lane is done with stage buf^1 before it is refilled
         }
-        const bool has_next = tile + gstride < prm.ntiles;
+        const bool has_next = tile < ntiles - gstride;   // no overflow: gstride <= 148 * 32
         if (HASH && has_next && lane == 0) nxt_info = issue(phys(tile + gstride), buf ^ 1);
-        const int64_t pt = phys(tile);
-        if ((pt + 1) * TILE <= prm.n) body(std::true_type{}, pt, buf, info, has_next);
+        const int pt = phys(tile);
+        if ((int64_t)(pt + 1) * TILE <= prm.n) body(std::true_type{}, pt, buf, info, has_next);
         else body(std::false_type{}, pt, buf, info, has_next);
         // every warp examines the CTA's split sums after every 8th tile of its own (bound: see fold_sums)
         if (SMEM && (it & (FOLD_TILES - 1)) == FOLD_TILES - 1) C.fold_sums(lane, 1u << 30);
@@ -830,7 +1035,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     __syncthreads();
     if (MODE == MODE_EXACT) {
         alive_delta = __reduce_add_sync(full, alive_delta);
+        alive_claims = __reduce_add_sync(full, alive_claims);
         if (lane == 0 && alive_delta) atomicAdd(prm.alive_count, (unsigned long long)(long long)alive_delta);
+        if (lane == 0 && alive_claims) atomicAdd(prm.alive_count + 2, (unsigned long long)alive_claims);
     }
     if (SMEM) {
         // bucket rows → global [which][p][bucket]; row 32 → knull; row 65 (tombstones) is derived, not stored
@@ -938,62 +1145,88 @@ __global__ void __launch_bounds__(1024) tile_base_scan_kernel(uint64_t *tile_bas
 }
 
 // ------------------------------------------------------------------------------------------------
-// alive-key table: HLL over the alive set, export / import
+// alive-key table: HLL over the alive set, export / import, rehash (growth), rebase (seq window)
 // ------------------------------------------------------------------------------------------------
-constexpr int PAGE_ENTRIES = 1 << DIRTY_SHIFT;
 constexpr int THREADS = 256;  // block size of the table / utility kernels below
 // EXTENSION: HyperLogLog over the resolved alive set (only when an HLL precision was asked for together with -c)
-__global__ void __launch_bounds__(THREADS) alive_hll_kernel(const unsigned long long *table, const uint8_t *dirty,
-                                                            uint32_t npages, uint64_t epoch_tag, uint32_t *hll, int hll_p) {
-    for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
-        if (!dirty[page]) continue;
-        const unsigned long long *pg = table + ((size_t)page << DIRTY_SHIFT);
-        for (int i = threadIdx.x; i < PAGE_ENTRIES; i += THREADS) {
-            const unsigned long long v = pg[i];
-            if ((v & 1ull) && ((v ^ epoch_tag) >> 48) == 0) hll_raise(hll, hll_p, hll_mix((page << DIRTY_SHIFT) + (uint32_t)i));
-        }
+__global__ void __launch_bounds__(THREADS) alive_hll_kernel(const unsigned long long *table, size_t nslots, uint32_t *hll, int hll_p) {
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < nslots; i += stride) {
+        const unsigned long long v = table[i];
+        if (v != ALIVE_EMPTY && (v & 1ull)) hll_raise(hll, hll_p, hll_mix((uint32_t)(v >> 32)));
     }
 }
 
-// mode 0: count current-epoch entries; mode 1: append them as (hash, stamp without epoch)
-__global__ void __launch_bounds__(THREADS) alive_export_kernel(const unsigned long long *table, const uint8_t *dirty,
-                                                               uint32_t npages, uint64_t epoch_tag, int mode,
+// mode 0: count the entries; mode 1: append them as (hash, ((seq + 1) << 1) | alive) with absolute sequence numbers
+__global__ void __launch_bounds__(THREADS) alive_export_kernel(const unsigned long long *table, size_t nslots, uint64_t origin, int mode,
                                                                unsigned long long *counter, uint32_t *out_hash,
                                                                unsigned long long *out_stamp, unsigned long long cap) {
     const int lane = threadIdx.x & 31;
-    for (uint32_t page = blockIdx.x; page < npages; page += gridDim.x) {
-        if (!dirty[page]) continue;
-        const unsigned long long *pg = table + ((size_t)page << DIRTY_SHIFT);
-        for (int i = threadIdx.x; i < PAGE_ENTRIES; i += THREADS) {
-            const unsigned long long v = pg[i];
-            const bool live = v != 0 && ((v ^ epoch_tag) >> 48) == 0;
-            const unsigned m = __ballot_sync(0xffffffffu, live);
-            if (!m) continue;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (mode == 1 && live) {
-                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < cap) {
-                    out_hash[slot] = (page << DIRTY_SHIFT) + (uint32_t)i;
-                    out_stamp[slot] = v & 0x0000ffffffffffffull;
-                }
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    const size_t rounds = (nslots + stride - 1) / stride;   // every thread runs the same number of rounds (warp votes inside)
+    for (size_t it = 0; it < rounds; it++) {
+        const size_t i = it * stride + (size_t)blockIdx.x * THREADS + threadIdx.x;
+        const unsigned long long v = i < nslots ? table[i] : ALIVE_EMPTY;
+        const bool live = v != ALIVE_EMPTY;
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (mode == 1 && live) {
+            const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < cap) {
+                const unsigned long long field = (v >> 1) & 0x7fffffffull;
+                out_hash[slot] = (uint32_t)(v >> 32);
+                out_stamp[slot] = ((origin + field) << 1) | (v & 1ull);   // seq + 1 = origin + field
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(THREADS) alive_import_kernel(unsigned long long *table, uint8_t *dirty, uint64_t epoch_tag,
-                                                               const uint32_t *hash, const unsigned long long *stamp,
-                                                               int64_t count, unsigned long long *alive_count) {
+__global__ void __launch_bounds__(THREADS) alive_import_kernel(const AliveTable t, uint64_t origin, const uint32_t *hash,
+                                                               const unsigned long long *stamp, int64_t count,
+                                                               unsigned long long *alive_count) {
     int delta = 0;
+    uint32_t claims = 0;
+    AliveTable tt = t;
+    tt.pol = KTA_L2_HINTS ? l2_policy_evict_last() : 0;
     const int64_t stride = (int64_t)gridDim.x * THREADS;
     for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < count; i += stride) {
         const unsigned long long st = stamp[i];
-        delta += alive_stamp(table, dirty, epoch_tag, hash[i], st >> 1, (st & 1ull) != 0);
+        const unsigned long long field = (st >> 1) - origin;        // seq + 1 - origin
+        if (field - 1ull >= (unsigned long long)ALIVE_FIELD_MAX) {   // outside the table's 31-bit window
+            atomicAdd(t.status + 1, 1u);
+            continue;
+        }
+        const uint32_t h = hash[i];
+        const int r = alive_stamp_slow(tt, alive_home(h, t.npairs), h, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
+        delta += (r << 30) >> 30;
+        claims += (uint32_t)r >> 2;
     }
     delta = __reduce_add_sync(0xffffffffu, delta);
+    claims = __reduce_add_sync(0xffffffffu, claims);
     if ((threadIdx.x & 31) == 0 && delta) atomicAdd(alive_count, (unsigned long long)(long long)delta);
+    if ((threadIdx.x & 31) == 0 && claims) atomicAdd(alive_count + 2, (unsigned long long)claims);
+}
+
+// growth: every entry of the old table moves to its place in the new one (hashes are unique, so plain claims)
+__global__ void __launch_bounds__(THREADS) alive_rehash_kernel(const unsigned long long *old_slots, size_t old_nslots,
+                                                               unsigned long long *new_slots, uint32_t new_npairs, uint32_t *status) {
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < old_nslots; i += stride) {
+        const unsigned long long v = old_slots[i];
+        if (v != ALIVE_EMPTY && !alive_insert_unique(new_slots, new_npairs, v)) atomicAdd(status, 1u);
+    }
+}
+
+// rebase: all entries become "older than anything that follows" (seq field 0), keeping hash and alive bit
+__global__ void __launch_bounds__(THREADS) alive_rebase_kernel(unsigned long long *slots, size_t nslots) {
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < nslots; i += stride) {
+        const unsigned long long v = slots[i];
+        if (v != ALIVE_EMPTY) slots[i] = v & 0xffffffff00000001ull;
+    }
 }
 
 // state (re)initialisation: sums = 0, minmax = {+inf, -inf, u64 max, 0}, hll = 0, hll floor = 0

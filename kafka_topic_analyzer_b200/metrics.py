@@ -53,13 +53,14 @@ class KtaEngine:
 
     def __init__(self, num_partitions: int, count_alive_keys: bool = False, hll_precision: int = 0,
                  device: int = -1, ring_records: int = 0, ring_key_bytes: int = 0,
-                 now: Optional[tuple] = None):
+                 now: Optional[tuple] = None, alive_table_kib: int = 0):
         cfg = Config()
         cfg.struct_size = C.sizeof(Config)
         cfg.device = device
         cfg.num_partitions = num_partitions
         cfg.count_alive_keys = 1 if count_alive_keys else 0
         cfg.hll_precision = hll_precision
+        cfg.alive_table_kib = alive_table_kib   # initial size of the alive-key table (0 = 128 MiB); it grows on demand
         cfg.ring_records = ring_records
         cfg.ring_key_bytes = ring_key_bytes
         if now is None:
@@ -116,7 +117,7 @@ class KtaEngine:
                seq_base, offset) -> Batch:
         b = Batch()
         b.n = n
-        b.seq_base = seq_base
+        b.seq_base = N.SEQ_AUTO if seq_base is None else seq_base   # None: continue the handle's running count
         b.partition, b.offset, b.ts_ms = _ptr(partition), _ptr(offset), _ptr(ts_ms)
         b.key_len, b.value_len, b.key_bytes = _ptr(key_len), _ptr(value_len), _ptr(key_bytes)
         b.key_bytes_len = key_bytes_len
@@ -124,15 +125,16 @@ class KtaEngine:
         return b
 
     def push_batch_host(self, partition, ts_ms, key_len, value_len, key_bytes=None, key_tile_base=None, seq=None,
-                        seq_base: int = 0, offset=None) -> None:
-        """SoA batch in host memory (numpy arrays, or pinned torch CPU tensors)."""
+                        seq_base: Optional[int] = None, offset=None) -> None:
+        """SoA batch in host memory (numpy arrays, or pinned torch CPU tensors).  seq_base None = the records follow
+        everything this engine has seen so far (src/kafka.rs:99: `seq += 1` per polled message)."""
         n = int(partition.shape[0])
         kbl = 0 if key_bytes is None else int(key_bytes.shape[0])
         b = self._batch(n, partition, ts_ms, key_len, value_len, key_bytes, kbl, key_tile_base, seq, seq_base, offset)
         check(lib().kta_push_batch_host(self._h, C.byref(b)))
 
     def scan_batch_device(self, partition, ts_ms, key_len, value_len, key_bytes=None, key_bytes_len: int = 0,
-                          key_tile_base=None, seq=None, seq_base: int = 0, n: Optional[int] = None) -> None:
+                          key_tile_base=None, seq=None, seq_base: Optional[int] = None, n: Optional[int] = None) -> None:
         """SoA batch already in HBM (torch CUDA tensors or raw device addresses).  Asynchronous."""
         if n is None:
             n = int(partition.shape[0])
@@ -207,6 +209,17 @@ class KtaEngine:
         out = C.c_uint64()
         check(lib().kta_alive_keys(self._h, C.byref(out)))
         return out.value
+
+    def bad_partition_records(self) -> int:
+        out = C.c_uint64()
+        check(lib().kta_bad_partition_records(self._h, C.byref(out)))
+        return out.value
+
+    def alive_table_stats(self):
+        """(slots, occupied, grows, reruns) of the alive-key table."""
+        v = [C.c_uint64() for _ in range(4)]
+        check(lib().kta_alive_table_stats(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     def alive_keys_hll(self) -> float:
         out = C.c_double()

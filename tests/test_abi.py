@@ -32,7 +32,7 @@ def test_binding_table_covers_header():
 
 def test_abi_version_and_structs():
     L = lib()
-    assert L.kta_abi_version() == 1
+    assert L.kta_abi_version() == 2
     assert C.sizeof(_native.Config) == 56 and C.sizeof(_native.Batch) == 88 and C.sizeof(_native.SynthSpec) == 56
 
 
