@@ -201,7 +201,10 @@ int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, const uint6
  * <topic>-<partition>/NNN.log and returns in a fetch response.  The library decodes it on the GPU into the SoA
  * columns above (what librdkafka's parser + BorrowedMessage accessors do per message, src/kafka.rs:93,
  * src/metric.rs:208-209,218,233) and scans it.  Control batches are skipped, LogAppendTime batches use
- * maxTimestamp, CRCs are not verified (librdkafka default check.crcs=false), compressed batches are rejected. */
+ * maxTimestamp, a record's timestamp is baseTimestamp + timestampDelta (only a result of -1 is "not available"),
+ * CRCs are not verified (librdkafka default check.crcs=false), compressed batches are rejected.
+ * Differences from a librdkafka consumer: records of aborted transactions ARE delivered (read_committed filtering
+ * needs the transaction index, which is not read), legacy magic 0/1 message sets are reported as malformed. */
 /* raw bytes already in device memory; batch_off[nbatches] = byte offset of every batch header (device memory) */
 int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
                                 const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out);

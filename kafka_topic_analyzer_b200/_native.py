@@ -14,6 +14,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libkta_gpu.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libkta_synth.so")   # host-only synthetic topic generator (no CUDA)
 INCLUDE = os.path.normpath(os.path.join(_HERE, "..", "include"))
 
 KTA_KEY_TILE = 128
@@ -28,7 +29,20 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "kta.h")]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if os.path.isfile(os.path.join(CSRC, f))] + \
+           [os.path.join(INCLUDE, "kta.h")]
+
+
+def build_synth(force: bool = False) -> str:
+    """libkta_synth.so: the host half of the synthetic topic generator, plain g++, no CUDA anywhere."""
+    srcs = [os.path.join(CSRC, "kta_synth_host.cpp"), os.path.join(CSRC, "kta_synth.h"), os.path.join(INCLUDE, "kta.h")]
+    if not force and os.path.exists(SYNTH_LIB_PATH) and os.path.getmtime(SYNTH_LIB_PATH) >= max(os.path.getmtime(p) for p in srcs):
+        return SYNTH_LIB_PATH
+    cmd = [os.environ.get("CXX") or "g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", SYNTH_LIB_PATH, srcs[0]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return SYNTH_LIB_PATH
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
@@ -139,6 +153,21 @@ SYMBOLS = {
 }
 
 _lib = None
+_synth = None
+SYNTH_HOST_SYMBOLS = ("kta_synth_shard_records", "kta_synth_fill_host", "kta_synth_encode_segment_host")
+
+
+def synth_lib() -> C.CDLL:
+    """The host-only generator library (never touches CUDA; safe for the CPU reference arm)."""
+    global _synth
+    if _synth is None:
+        if not (os.environ.get("KTA_NO_BUILD") == "1" and os.path.exists(SYNTH_LIB_PATH)):
+            build_synth()
+        _synth = C.CDLL(SYNTH_LIB_PATH)
+        for name in SYNTH_HOST_SYMBOLS:
+            fn = getattr(_synth, name)
+            fn.restype, fn.argtypes = SYMBOLS[name]
+    return _synth
 
 
 def lib() -> C.CDLL:

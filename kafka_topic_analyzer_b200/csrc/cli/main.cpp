@@ -5,7 +5,10 @@
 //               tombstone_per_10k=...,null_key_per_10k=...,zipf_keys=1,geometric_values=1
 //                                                                (the in-memory topic of BASELINE.json configs)
 //   --log-dir DIR              read Kafka log segments from DIR/<topic>-<partition>/*.log (a broker's data directory)
-//                              and decode them on the GPU (uncompressed RecordBatch v2)
+//                              and decode them on the GPU (RecordBatch v2, magic 2).  Differences from a librdkafka
+//                              consumer: records of ABORTED transactions are counted (a consumer with the default
+//                              isolation.level=read_committed filters them; the .txnindex files are not read here),
+//                              and legacy magic 0/1 message sets are reported as malformed.
 //   --feed push|batch|device   how records reach the handlers: kta_push per record (the reference's call shape),
 //                              kta_push_batch_host, or generated and scanned in HBM
 //
@@ -47,7 +50,7 @@ static bool read_file(const std::string &path, std::vector<uint8_t> &out) {
     return n == 0 || (bool)f.read(reinterpret_cast<char *>(out.data()), n);
 }
 
-static int print_report(kta_handle *h, const std::string &topic, int P, const std::vector<int64_t> &start_offsets,
+static int print_report(kta_handle *h, const std::string &topic, const std::vector<int> &partitions, const std::vector<int64_t> &start_offsets,
                         const std::vector<int64_t> &end_offsets, bool alive, int hll, uint64_t duration_secs);
 
 static int analyze_log_dir(const std::string &topic, const std::string &dir, bool alive, int hll,
@@ -130,7 +133,10 @@ static int analyze_log_dir(const std::string &topic, const std::string &dir, boo
     }
     KTA(kta_finalize(h));
     const uint64_t secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
-    const int rc = print_report(h, topic, P, start_offsets, end_offsets, alive, hll, secs);
+    // the report has one row per partition of the topic's metadata (main.rs:103-106): the <topic>-<n> directories found
+    std::vector<int> present;
+    for (auto &kv : segs) present.push_back(kv.first);
+    const int rc = print_report(h, topic, present, start_offsets, end_offsets, alive, hll, secs);
     kta_destroy(h);
     return rc;
 }
@@ -268,12 +274,14 @@ int main(int argc, char **argv) {
             (long long)n, feed_s, feed_s > 0 ? (double)n / feed_s : 0.0);
     const uint64_t duration_secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
 
-    const int rc = print_report(h, topic, P, start_offsets, end_offsets, cfg.count_alive_keys == 1, hll, duration_secs);
+    std::vector<int> all_partitions(P);
+    for (int p = 0; p < P; p++) all_partitions[p] = p;
+    const int rc = print_report(h, topic, all_partitions, start_offsets, end_offsets, cfg.count_alive_keys == 1, hll, duration_secs);
     kta_destroy(h);
     return rc;
 }
 
-static int print_report(kta_handle *h, const std::string &topic, int P, const std::vector<int64_t> &start_offsets,
+static int print_report(kta_handle *h, const std::string &topic, const std::vector<int> &partitions, const std::vector<int64_t> &start_offsets,
                         const std::vector<int64_t> &end_offsets, bool alive, int hll, uint64_t duration_secs) {
     kta_report::Summary s{};
     s.topic = topic;
@@ -286,7 +294,7 @@ static int print_report(kta_handle *h, const std::string &topic, int P, const st
     s.has_alive_keys = alive;
     if (s.has_alive_keys) KTA(kta_alive_keys(h, &s.alive_keys));
     std::vector<kta_report::PartitionRow> rows;
-    for (int p = 0; p < P; p++) {  // partitions sorted ascending, main.rs:103-106
+    for (int p : partitions) {  // partitions of the metadata, sorted ascending, main.rs:103-106
         kta_report::PartitionRow r{};
         r.partition = p; r.start_offset = start_offsets[p]; r.end_offset = end_offsets[p];
         KTA(kta_counter(h, KTA_TOTAL, p, &r.total)); KTA(kta_counter(h, KTA_ALIVE, p, &r.alive));

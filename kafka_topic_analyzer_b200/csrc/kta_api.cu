@@ -63,6 +63,7 @@ extern "C" int kta_device_count(void) {
 static constexpr int NCHUNK = 3;
 static constexpr int32_t ALIVE_DEFAULT_KIB = 128 * 1024;       // initial alive-key table: 128 MiB
 static constexpr int32_t ALIVE_MAX_KIB = 32 * 1024 * 1024;     // 32 GiB = one slot per possible 32-bit hash
+static constexpr int64_t ALIVE_CACHE_MIN_RECORDS = 1 << 20;    // smaller batches go straight to the table
 static constexpr int64_t DEFAULT_RING_RECORDS = 1 << 22;  // 4 Mi records per chunk
 
 struct Chunk {
@@ -106,10 +107,12 @@ struct kta_handle {
     uint32_t alive_pairs = 0;
     uint64_t alive_origin = 0;               // seq that a stamp's field value 1 stands for
     bool alive_rebased = false;              // a rebase dropped absolute sequence numbers (exports are refused then)
+    uint32_t *d_alive_cache = nullptr;       // seen cache of the batch being scanned (32 MiB, cleared per launch)
     uint32_t *d_alive_status = nullptr;      // [0] stamps that found no slot, [1] records outside the seq window
     uint32_t *h_alive_status = nullptr;      // pinned copy
     uint64_t alive_window_errors = 0;        // sticky until reset: reported by kta_finalize
     uint64_t alive_grows = 0, alive_reruns = 0;
+    uint64_t alive_now = 0, alive_occupied = 0;   // counted by the last alive_check
     std::vector<PendingScan> pending;
     unsigned long long *d_scalar = nullptr;  // [0] alive count, [1] export cursor, [2] occupied slots, [3] spare,
                                              // [4..] hll floor + slice minima (u32)
@@ -226,6 +229,7 @@ static int state_reset_device(kta_handle *h) {
         CU(cudaMemsetAsync(h->d_alive_table, 0xff, (size_t)h->alive_pairs * 16, h->stream));
         CU(cudaMemsetAsync(h->d_scalar, 0, 32, h->stream));
         CU(cudaMemsetAsync(h->d_alive_status, 0, 8, h->stream));
+        h->alive_now = h->alive_occupied = 0;
         h->alive_origin = 0;
         h->alive_rebased = false;
         h->alive_window_errors = 0;
@@ -250,7 +254,7 @@ extern "C" int kta_destroy(kta_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &c : h->chunks) free_chunk(c);
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
-    cudaFree(h->d_alive_status); cudaFreeHost(h->h_alive_status); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
+    cudaFree(h->d_alive_status); cudaFree(h->d_alive_cache); cudaFreeHost(h->h_alive_status); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
     cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt); cudaFree(h->d_log_kb);
     cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys);
     cudaFree(h->d_log_err);
@@ -308,6 +312,7 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
         h->alive_pairs = (uint32_t)std::max<int64_t>(kib * 64, 16);   // 16 bytes per pair
         CU(cudaMalloc(&h->d_alive_table, (size_t)h->alive_pairs * 16));
         CU(cudaMalloc(&h->d_alive_status, 8));
+        CU(cudaMalloc(&h->d_alive_cache, ((size_t)4 << ALIVE_CACHE_SET_BITS)));
         CU(cudaHostAlloc(&h->h_alive_status, 8, cudaHostAllocDefault));
     }
     h->smem_optin = prop.sharedMemPerBlockOptin;
@@ -378,6 +383,18 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     prm.alive_origin = h->alive_origin;
     prm.alive_count = h->d_scalar;
     prm.alive_status = h->d_alive_status;
+    prm.alive_cache = nullptr;
+    if (exact && prm.n >= ALIVE_CACHE_MIN_RECORDS) {
+        // the seen cache pays for its clearing (32 MiB, ~10 µs) on batches of a million records and more
+        static const bool off = getenv("KTA_ALIVE_NO_CACHE") != nullptr;   // tuning / ablation knob
+        if (!off) {
+            CU(cudaMemsetAsync(h->d_alive_cache, 0, (size_t)4 << ALIVE_CACHE_SET_BITS, h->stream));
+            prm.alive_cache = h->d_alive_cache;
+            int sh = 0;
+            while (((prm.n - 1) >> sh) + 1 > (int64_t)ALIVE_CACHE_WAVES) sh++;
+            prm.alive_wave_shift = sh;
+        }
+    }
     prm.hash_out = capture ? h->d_hash_out : nullptr;
     if (mode != MODE_COUNTERS) {
         if (!prm.key_tile_base) return fail(KTA_ERR_INVALID, "internal: key_tile_base missing");
@@ -439,10 +456,17 @@ static int alive_check(kta_handle *h) {
     if (!h->d_alive_table) return KTA_OK;
     cudaStream_t s = h->stream;
     for (int round = 0;; round++) {
-        unsigned long long occupied = 0;
+        unsigned long long counts[3] = {0, 0, 0};   // alive, (export cursor), occupied
+        CU(cudaMemsetAsync(h->d_scalar, 0, 24, s));
+        alive_count_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, (size_t)h->alive_pairs * 2, h->d_scalar);
+        h->launches++;
+        CU(cudaGetLastError());
         CU(cudaMemcpyAsync(h->h_alive_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, s));
-        CU(cudaMemcpyAsync(&occupied, h->d_scalar + 2, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(counts, h->d_scalar, 24, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        const unsigned long long occupied = counts[2];
+        h->alive_now = counts[0];
+        h->alive_occupied = occupied;
         const uint32_t dropped = h->h_alive_status[0];
         h->alive_window_errors += h->h_alive_status[1];
         if (dropped || h->h_alive_status[1]) CU(cudaMemsetAsync(h->d_alive_status, 0, 8, s));
@@ -1006,11 +1030,9 @@ extern "C" int kta_finalize(kta_handle *h) {
     CU(cudaMemcpyAsync(h->h_sums.data(), h->d_sums, h->nsums * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(h->h_minmax, h->d_minmax, 32, cudaMemcpyDeviceToHost, s));
     if (h->nhll) CU(cudaMemcpyAsync(h->h_hll.data(), h->d_hll, h->nhll * 4, cudaMemcpyDeviceToHost, s));
-    unsigned long long alive = 0;
-    if (h->d_alive_table) CU(cudaMemcpyAsync(&alive, h->d_scalar, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if ((rc = collect_timing(h))) return rc;
-    h->h_alive = alive;
+    h->h_alive = h->alive_now;   // counted over the table by alive_check above (sum_all_alive, src/metric.rs:282-284)
     h->finalized = true;
     if (h->alive_window_errors)
         return fail(KTA_ERR_INVALID, "%llu record(s) carried a sequence number outside the alive-key table's window "
@@ -1345,7 +1367,7 @@ extern "C" int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, 
     for (int round = 0;; round++) {
         const AliveTable t{h->d_alive_table, h->alive_pairs, h->d_alive_status, 0};
         alive_import_kernel<<<grid, THREADS, 0, h->stream>>>(t, h->alive_origin, dev_hash,
-                                                             reinterpret_cast<const unsigned long long *>(dev_stamp), count, h->d_scalar);
+                                                             reinterpret_cast<const unsigned long long *>(dev_stamp), count);
         h->launches++;
         CU(cudaGetLastError());
         // the imported list is the caller's and still valid: if the table was too small, alive_check grew it (nothing
@@ -1376,11 +1398,10 @@ extern "C" int kta_alive_table_stats(kta_handle *h, uint64_t *slots, uint64_t *o
     if (!h->d_alive_table) return fail(KTA_ERR_NOT_ENABLED, "count_alive_keys was not enabled");
     int rc;
     if ((rc = set_device(h))) return rc;
-    unsigned long long occ = 0;
-    CU(cudaMemcpyAsync(&occ, h->d_scalar + 2, 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    if ((rc = ring_flush(h))) return rc;
+    if ((rc = alive_check(h))) return rc;   // settles pending stamps and counts the table
     if (slots) *slots = (uint64_t)h->alive_pairs * 2;
-    if (occupied) *occupied = occ;
+    if (occupied) *occupied = h->alive_occupied;
     if (grows) *grows = h->alive_grows;
     if (reruns) *reruns = h->alive_reruns;
     return KTA_OK;

@@ -79,7 +79,10 @@ struct ScanParams {
     int32_t alive_only;              // 1: MODE_EXACT re-run after the table grew — stamps only, no counters / extrema
     uint64_t alive_origin;           // seq that field value 1 stands for (moved forward by a rebase)
     uint64_t alive_fbase;            // seq_base - alive_origin + 1: the field of record 0 when seq is implicit
-    unsigned long long *alive_count; // [0] alive entries (two's-complement deltas), [1] export cursor, [2] occupied slots
+    unsigned long long *alive_count; // scratch u64 words: [0] alive entries, [1] export cursor, [2] occupied slots (count kernels)
+    uint32_t *alive_cache;           // [2^ALIVE_CACHE_SET_BITS] seen cache of this batch (cleared by the host before the launch), or NULL
+    int32_t alive_wave_shift;        // wave of the record at batch index r = 1 + (r >> alive_wave_shift)
+    int32_t pad1;
     uint32_t *alive_status;          // [0] stamps that found no slot (table too full: host grows it and re-runs the
                                      //     batch), [1] records whose seq lies outside the 31-bit window of the table
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
@@ -451,12 +454,24 @@ struct Counters {
 //     read is a safe filter: a record that is not the newest for its hash stops after one 16-byte read.  The scan walks
 //     each batch from its newest tile to its oldest, so for a key written k times about (k-1)/k of its records take
 //     that exit.
-//   * sum_all_alive (metric.rs:282-284) is maintained incrementally from the value atomicMax returns — the chain of
-//     successful updates of one entry telescopes to (final alive - initial alive) — so finalize never scans the table.
+//   * sum_all_alive (metric.rs:282-284) is a count over the table at finalize (a pass over ~128 MiB: tens of µs), so
+//     the stamps themselves need no return value: raising an existing entry is a fire-and-forget RED.MAX.
 //   * 31 bits of seq: when a batch would not fit the window the host REBASES (every entry keeps hash and alive bit, its
 //     seq field drops to 0: older than everything that follows, which is all a later record needs to know).
 //   * A stamp that finds neither its hash nor an empty slot within ALIVE_MAX_PROBES pairs is counted in status[0] and
 //     dropped; the host then grows the table (rehash) and re-runs the batch stamps-only — stamping is idempotent.
+//
+// The SEEN CACHE in front of it.  Measured (profiles/r02_alive_v0_*): a table of 128 MiB does not stay in the 126 MB L2
+// next to a 3.6 GB stream — 73 % of the probes missed — and 1e8 random DRAM sectors cost 2.4 ms.  But 90–99 % of the
+// records of a compacted topic are superseded by a newer record of the same key, and all they need to learn is that
+// fact.  So each batch keeps a 32 MiB, 2-way set-associative, EXACT cache of (hash → newest wave seen), where a wave is
+// 1/127 of the batch in seq order: set = top 23 bits of fmix32(hash) (a bijection), way = 9-bit tag (the other bits) +
+// 7-bit wave.  A record that finds its own tag with a wave NEWER than its own is superseded by construction (waves are
+// a monotone function of seq — no timing assumption) and is done after one L2 hit.  Everything else — the first record
+// seen of each key, same-wave siblings, conflict misses — is compacted across the tile into one dense queue and takes
+// the exact path through the table; whatever the table knows afterwards is written back to the cache.  The cache holds
+// only true facts ("a record of this hash with this wave exists and is being stamped"), so a lost or stale entry costs a
+// table probe, never correctness.
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned long long ALIVE_EMPTY = ~0ull;
 constexpr uint32_t ALIVE_FIELD_MAX = 0x7ffffffeu;   // largest seq field: a stamp's low word is <= 0xfffffffd, never ~0
@@ -515,9 +530,18 @@ struct AliveTable {
     uint64_t pol;       // L2 evict_last policy for the table's lines
 };
 
-// The general stamp: probe from `pair` until the hash or an empty slot is found.
-// Returns (change of the alive-entry count, two's complement in bits 0..1) | (claimed a fresh slot) << 2.
-__device__ __noinline__ int alive_stamp_slow(const AliveTable t, uint32_t pair, uint32_t hash, uint32_t low) {
+// raise an entry that holds this stamp's hash: no return value, the warp does not wait
+__device__ __forceinline__ void alive_red_max(unsigned long long *p, unsigned long long v, uint64_t pol) {
+#if KTA_L2_HINTS
+    asm volatile("red.global.max.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+#else
+    asm volatile("red.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+
+// The general stamp: probe from `pair` until the hash or an empty slot is found.  Returns the low word of the newest
+// stamp known for this hash afterwards (the record's own if it won).
+__device__ __noinline__ uint32_t alive_stamp_slow(const AliveTable t, uint32_t pair, uint32_t hash, uint32_t low) {
     const unsigned long long stamp = ((unsigned long long)hash << 32) | low;
     for (int probe = 0; probe < ALIVE_MAX_PROBES; probe++) {
         unsigned long long *slot = t.slots + 2 * (size_t)pair;
@@ -526,20 +550,68 @@ __device__ __noinline__ int alive_stamp_slow(const AliveTable t, uint32_t pair, 
         for (int s = 0; s < 2; s++) {
             unsigned long long v = s ? e.y : e.x;
             if (v == ALIVE_EMPTY) {
-                v = alive_atom_cas(slot + s, ALIVE_EMPTY, stamp, t.pol);
-                if (v == ALIVE_EMPTY) return (int)(low & 1u) | 4;   // first record of this hash: mark_key_alive / _dead on a fresh bit
+                v = atomicCAS(slot + s, ALIVE_EMPTY, stamp);
+                if (v == ALIVE_EMPTY) return low;                   // first record of this hash: mark_key_alive / _dead on a fresh bit
             }
             if ((uint32_t)(v >> 32) == hash) {                      // v is a real entry here (never ALIVE_EMPTY)
-                if (v >= stamp) return 0;                           // a later record already spoke for this hash
-                const unsigned long long old = alive_atom_max(slot + s, stamp, t.pol);
-                if (stamp <= old) return 0;
-                return ((int)(low & 1u) - (int)(old & 1ull)) & 3;
+                if (v >= stamp) return (uint32_t)v;                 // a later record already spoke for this hash
+                alive_red_max(slot + s, stamp, t.pol);
+                return low;
             }
         }
         pair = pair + 1 == t.npairs ? 0 : pair + 1;
     }
     atomicAdd(t.status, 1u);   // table too full: the host grows it and re-runs this batch's stamps
-    return 0;
+    return low;
+}
+
+// One stamp with the home pair already loaded (`e`): the common cases need no second look at memory.
+__device__ __forceinline__ uint32_t alive_stamp(const AliveTable t, uint32_t pair, const ulonglong2 e, uint32_t hash, uint32_t low) {
+    const bool hx = (uint32_t)(e.x >> 32) == hash, hy = (uint32_t)(e.y >> 32) == hash;
+    const uint32_t seen = hx ? (uint32_t)e.x : (uint32_t)e.y;
+    // equal hash ⇒ the stamps compare like their low words.  A real low word is <= 0xfffffffd and the empty pattern's is
+    // 0xffffffff, so "seen + 1 > low" is "seen >= low" for real entries and false for an empty slot under hash 0xffffffff
+    if ((hx || hy) && seen + 1u > low) return seen;                 // a later record already spoke for this hash
+    unsigned long long *slot = t.slots + 2 * (size_t)pair;
+    const unsigned long long stamp = ((unsigned long long)hash << 32) | low;
+    if ((hx && e.x != ALIVE_EMPTY) || (!hx && hy && e.y != ALIVE_EMPTY)) {   // the hash is here with an older stamp
+        alive_red_max(slot + (hx ? 0 : 1), stamp, t.pol);
+        return low;
+    }
+    return alive_stamp_slow(t, pair, hash, low);                    // claim a slot / probe on
+}
+
+// ---- seen cache: nsets = 2^ALIVE_CACHE_SET_BITS sets of two 16-bit ways: tag (9 bits) << 7 | wave (7 bits), 0 = empty ----
+constexpr int ALIVE_CACHE_SET_BITS = 23, ALIVE_CACHE_TAG_BITS = 32 - ALIVE_CACHE_SET_BITS, ALIVE_CACHE_WAVE_BITS = 16 - ALIVE_CACHE_TAG_BITS;
+constexpr uint32_t ALIVE_CACHE_WAVES = (1u << ALIVE_CACHE_WAVE_BITS) - 1;   // waves 1..127 (0 = empty way)
+static_assert(ALIVE_CACHE_TAG_BITS == 9 && ALIVE_CACHE_WAVE_BITS == 7, "16-bit ways");
+__device__ __forceinline__ uint32_t alive_cache_ld(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+#if KTA_L2_HINTS
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+#else
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
+    return v;
+}
+// is a record of mixed hash x and wave `wv` superseded according to set word c?
+__device__ __forceinline__ bool alive_cache_newer(uint32_t c, uint32_t x, uint32_t wv) {
+    const uint32_t tag = x & ((1u << ALIVE_CACHE_TAG_BITS) - 1u);
+    const uint32_t w0 = c & 0xffffu, w1 = c >> 16;
+    // same tag and a larger wave  ⇔  way in (tag << 7 | wv, tag << 7 | 127]
+    const uint32_t lo = (tag << ALIVE_CACHE_WAVE_BITS) | wv;
+    return (w0 - lo - 1u < ALIVE_CACHE_WAVES - wv) || (w1 - lo - 1u < ALIVE_CACHE_WAVES - wv);
+}
+// record the fact "hash x has a record of wave wv" (wv >= 1) in its set; c = the set word as last read
+__device__ __forceinline__ void alive_cache_put(uint32_t *set, uint32_t c, uint32_t x, uint32_t wv, uint32_t pick) {
+    const uint32_t tag = x & ((1u << ALIVE_CACHE_TAG_BITS) - 1u);
+    const uint32_t mine = (tag << ALIVE_CACHE_WAVE_BITS) | wv;
+    const uint32_t w0 = c & 0xffffu, w1 = c >> 16;
+    int way;
+    if ((w0 >> ALIVE_CACHE_WAVE_BITS) == tag && w0) way = w0 >= mine ? -1 : 0;          // already known at least as new
+    else if ((w1 >> ALIVE_CACHE_WAVE_BITS) == tag && w1) way = w1 >= mine ? -1 : 1;
+    else way = w0 == 0 ? 0 : w1 == 0 ? 1 : (int)(pick & 1u);
+    if (way >= 0) reinterpret_cast<unsigned short *>(set)[way] = (unsigned short)mine;   // little-endian: way 0 = low half
 }
 
 // plain insert of an entry whose hash is known to be absent (rehash into a fresh table)
@@ -649,8 +721,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     long long tmin = INT64_MAX, tmax = INT64_MIN;         // raw ts_ms extrema (None → 0 applied at read-back)
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
-    int alive_delta = 0;      // MODE_EXACT: change of the alive-entry count caused by this lane
-    uint32_t alive_claims = 0;   // MODE_EXACT: table slots this lane claimed (distinct hashes first seen)
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     uint32_t nxt_info = 0;
@@ -945,10 +1015,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             if (MODE == MODE_EXACT) {
                 // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
                 // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
-                // (metric.rs:295 mark_key_alive, :298 mark_key_dead).  All four probes are in flight before the first
-                // is looked at; a record that finds its hash with a stamp at least as new is done after that one read.
-                uint32_t pair[ROWS], low[ROWS];
-                ulonglong2 e[ROWS];
+                // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
+                // Step 1, per row: the seen cache (one L2 word per record).  A record superseded by a newer wave of its
+                // own hash is done.  The others are compacted into one dense queue in the warp's spent key stage.
+                uint2 *queue = reinterpret_cast<uint2 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (hash, low word) per entry
+                uint32_t *qwave = reinterpret_cast<uint32_t *>(queue + TILE);                  // its wave (12 B x 128 <= stage)
+                const bool cached = prm.alive_cache != nullptr;
+                uint32_t low[ROWS], cw[ROWS];
                 bool live[ROWS];
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
@@ -967,25 +1040,50 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                         field = (uint32_t)prm.alive_fbase + (uint32_t)r;   // host-checked: seq_base + n fits the window
                     }
                     low[k] = (field << 1) | (vl[k] >= 0 ? 1u : 0u);
-                    pair[k] = alive_home(h[k], AT.npairs);
-                    if (live[k]) e[k] = alive_ld_pair(AT.slots + 2 * (size_t)pair[k], AT.pol);
+                    cw[k] = 0;
+                    if (cached && live[k])
+                        cw[k] = alive_cache_ld(prm.alive_cache + (hll_mix(h[k]) >> ALIVE_CACHE_TAG_BITS), AT.pol);
                 }
+                uint32_t qn = 0;   // warp-uniform
 #pragma unroll
                 for (int k = 0; k < ROWS; k++) {
-                    if (live[k]) {
-                        const bool hx = hi32((long long)e[k].x) == h[k], hy = hi32((long long)e[k].y) == h[k];
-                        const uint32_t seen = hx ? (uint32_t)e[k].x : (uint32_t)e[k].y;
-                        // equal hash ⇒ the stamps compare like their low words.  A real low word is <= 0xfffffffd and the
-                        // empty pattern's is 0xffffffff, so "seen + 1 > low" is "seen >= low" for real entries and false
-                        // for an empty slot that happens to sit under hash 0xffffffff.
-                        const bool newer = (hx || hy) && seen + 1u > low[k];
-                        if (!newer) {
-                            const int r = alive_stamp_slow(AT, pair[k], h[k], low[k]);
-                            alive_delta += (r << 30) >> 30;
-                            alive_claims += (uint32_t)r >> 2;
+                    const uint32_t wv = 1u + (uint32_t)((rbase + 32 * k) >> prm.alive_wave_shift);
+                    const bool go = live[k] && !(cached && alive_cache_newer(cw[k], hll_mix(h[k]), wv));
+                    const unsigned m = __ballot_sync(full, go);
+                    if (go) {
+                        const uint32_t qi = qn + __popc(m & lt_mask);
+                        queue[qi] = make_uint2(h[k], low[k]);
+                        qwave[qi] = wv;
+                    }
+                    qn += __popc(m);
+                }
+                __syncwarp();
+                // Step 2, dense: the exact path through the table, then tell the cache what the table knows now
+                for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+                    const bool on = q0 + lane < qn;
+                    const uint2 item = on ? queue[q0 + lane] : make_uint2(0u, 0u);
+                    const uint32_t x = hll_mix(item.x);
+                    const uint32_t pr = __umulhi(x, AT.npairs);
+                    if (on) {
+                        const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
+                        uint32_t *cset = cached ? prm.alive_cache + (x >> ALIVE_CACHE_TAG_BITS) : nullptr;
+                        const uint32_t c = cached ? alive_cache_ld(cset, AT.pol) : 0u;
+                        const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
+                        if (cached) {
+                            // what the table knows now, as a wave of THIS batch: the record's own wave, or — when the stamp
+                            // that beat it is from this batch and seq is implicit (field - fbase = batch index) — that
+                            // stamp's.  Stamps of earlier batches and rebased ones are older than every record here.
+                            uint32_t wv = qwave[q0 + lane];
+                            const uint32_t idx = (newest >> 1) - (uint32_t)prm.alive_fbase;
+                            if (!prm.seq && idx < (uint32_t)prm.n) wv = max(wv, 1u + (idx >> prm.alive_wave_shift));
+                            alive_cache_put(cset, c, x, wv, newest >> 1);
                         }
                     }
                 }
+                // the queue lives in a key stage that the TMA engine refills next iteration: order these generic-proxy
+                // accesses before that async-proxy write
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
             }
 #ifndef KTA_EXP_NO_HLL
             if (MODE == MODE_HLL) {
@@ -1033,12 +1131,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
 
     // ---- flush CTA-private state ----
     __syncthreads();
-    if (MODE == MODE_EXACT) {
-        alive_delta = __reduce_add_sync(full, alive_delta);
-        alive_claims = __reduce_add_sync(full, alive_claims);
-        if (lane == 0 && alive_delta) atomicAdd(prm.alive_count, (unsigned long long)(long long)alive_delta);
-        if (lane == 0 && alive_claims) atomicAdd(prm.alive_count + 2, (unsigned long long)alive_claims);
-    }
     if (SMEM) {
         // bucket rows → global [which][p][bucket]; row 32 → knull; row 65 (tombstones) is derived, not stored
         const int nh = (ROW_V + NB) * P;
@@ -1185,10 +1277,7 @@ __global__ void __launch_bounds__(THREADS) alive_export_kernel(const unsigned lo
 }
 
 __global__ void __launch_bounds__(THREADS) alive_import_kernel(const AliveTable t, uint64_t origin, const uint32_t *hash,
-                                                               const unsigned long long *stamp, int64_t count,
-                                                               unsigned long long *alive_count) {
-    int delta = 0;
-    uint32_t claims = 0;
+                                                               const unsigned long long *stamp, int64_t count) {
     AliveTable tt = t;
     tt.pol = KTA_L2_HINTS ? l2_policy_evict_last() : 0;
     const int64_t stride = (int64_t)gridDim.x * THREADS;
@@ -1200,14 +1289,25 @@ __global__ void __launch_bounds__(THREADS) alive_import_kernel(const AliveTable 
             continue;
         }
         const uint32_t h = hash[i];
-        const int r = alive_stamp_slow(tt, alive_home(h, t.npairs), h, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
-        delta += (r << 30) >> 30;
-        claims += (uint32_t)r >> 2;
+        alive_stamp_slow(tt, alive_home(h, t.npairs), h, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
     }
-    delta = __reduce_add_sync(0xffffffffu, delta);
-    claims = __reduce_add_sync(0xffffffffu, claims);
-    if ((threadIdx.x & 31) == 0 && delta) atomicAdd(alive_count, (unsigned long long)(long long)delta);
-    if ((threadIdx.x & 31) == 0 && claims) atomicAdd(alive_count + 2, (unsigned long long)claims);
+}
+
+// sum_all_alive (metric.rs:282-284): out[0] += entries whose last writer carried a value, out[2] += occupied slots
+__global__ void __launch_bounds__(THREADS) alive_count_kernel(const unsigned long long *table, size_t nslots, unsigned long long *out) {
+    const size_t stride = (size_t)gridDim.x * THREADS;
+    unsigned alive = 0, occ = 0;
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < nslots; i += stride) {
+        const unsigned long long v = table[i];
+        occ += v != ALIVE_EMPTY;
+        alive += v != ALIVE_EMPTY && (v & 1ull);
+    }
+    alive = __reduce_add_sync(0xffffffffu, alive);
+    occ = __reduce_add_sync(0xffffffffu, occ);
+    if ((threadIdx.x & 31) == 0) {
+        if (alive) atomicAdd(out, (unsigned long long)alive);
+        if (occ) atomicAdd(out + 2, (unsigned long long)occ);
+    }
 }
 
 // growth: every entry of the old table moves to its place in the new one (hashes are unique, so plain claims)

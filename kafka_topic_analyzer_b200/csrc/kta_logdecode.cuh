@@ -10,9 +10,11 @@
 //   record: length varint | attributes i8 | timestampDelta varlong | offsetDelta varint | keyLength varint | key |
 //     valueLength varint | value | headersCount varint | headers…          (varints are zig-zag, LSB group first)
 // Semantics kept from the consumer: control batches (attributes bit 5) are not delivered to the application;
-// LogAppendTime batches (attributes bit 3) stamp every record with maxTimestamp; a timestamp of -1 means
-// "not available"; key/value length -1 means null.  CRCs are not verified (librdkafka's default check.crcs=false).
-// Compressed batches (attributes bits 0-2) are rejected: no decompressor here.
+// LogAppendTime batches (attributes bit 3) stamp every record with maxTimestamp; a record's timestamp is baseTimestamp +
+// timestampDelta as the consumer computes it, and only a RESULT of -1 means "not available"; key/value length -1 means
+// null.  CRCs are not verified (librdkafka's default check.crcs=false).
+// Not handled: records of aborted transactions are delivered (a read_committed consumer would filter them through the
+// .txnindex / abort markers), legacy magic 0/1 message sets are flagged as malformed.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(LOG_DECODE_THREADS) log_decode_kernel(
                         const uint64_t r = r0 + (uint64_t)i0 + lane;
                         partition[r] = bi.partition;
                         if (offset) offset[r] = bi.base_offset + off_delta;
-                        ts_ms[r] = bi.log_append_time ? bi.max_ts : (bi.base_ts == -1 ? -1 : bi.base_ts + ts_delta);
+                        ts_ms[r] = bi.log_append_time ? bi.max_ts : bi.base_ts + ts_delta;
                         key_len[r] = (int32_t)klen;
                         value_len[r] = (int32_t)vlen;
                     }

@@ -10,8 +10,9 @@ from __future__ import annotations
 from .metrics import KtaEngine
 
 
-def allreduce_merge(engine: KtaEngine, group=None) -> None:
-    """After this, every rank's engine holds the merged state (call finalize() to read it)."""
+def allreduce_merge(engine: KtaEngine, group=None, counters_only: bool = False) -> None:
+    """After this, every rank's engine holds the merged state (call finalize() to read it).
+    counters_only skips the exact alive-key exchange (used to time the all-reduce part alone)."""
     import torch
     import torch.distributed as dist
 
@@ -28,7 +29,7 @@ def allreduce_merge(engine: KtaEngine, group=None) -> None:
     if not engine.shares_caller_stream:
         torch.cuda.current_stream().synchronize()
     engine.merge_import(world, buf)
-    if engine.count_alive_keys:
+    if engine.count_alive_keys and not counters_only:
         n_local = engine.alive_export_count()
         counts = torch.zeros(world, dtype=torch.int64, device=dev)
         counts[rank] = n_local

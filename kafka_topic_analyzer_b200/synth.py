@@ -9,7 +9,7 @@ from typing import Optional
 import numpy as np
 
 from . import _native as N
-from ._native import SynthSpec, KtaError, lib
+from ._native import SynthSpec, KtaError, lib, synth_lib
 
 DEFAULT_SEED = 0x4B544131  # "KTA1"
 KEYS_LOGUNIFORM = 0x100     # include/kta.h KTA_SYNTH_KEYS_LOGUNIFORM
@@ -54,7 +54,7 @@ def make_spec(n_total: int, num_partitions: int, *, seed: int = DEFAULT_SEED, ru
 
 
 def shard_records(spec: SynthSpec, rank: int = 0, world: int = 1) -> int:
-    n = lib().kta_synth_shard_records(C.byref(spec), rank, world)
+    n = synth_lib().kta_synth_shard_records(C.byref(spec), rank, world)
     if n < 0:
         raise KtaError(N.ERR_INVALID, "invalid synthetic topic spec (n_total must be a multiple of "
                        "num_partitions*run_len; num_partitions a multiple of world)")
@@ -85,7 +85,7 @@ def fill_host(spec: SynthSpec, rank: int = 0, world: int = 1, start: int = 0, co
     cap = count * 40 + 16
     kb = np.zeros(cap, dtype=np.uint8)
     kbl = C.c_int64()
-    rc = lib().kta_synth_fill_host(C.byref(spec), rank, world, start, count, part.ctypes.data, off.ctypes.data,
+    rc = synth_lib().kta_synth_fill_host(C.byref(spec), rank, world, start, count, part.ctypes.data, off.ctypes.data,
                                    ts.ctypes.data, kl.ctypes.data, vl.ctypes.data, seq.ctypes.data, kb.ctypes.data,
                                    cap, C.byref(kbl))
     if rc != 0:
@@ -99,11 +99,11 @@ def encode_segment(spec: SynthSpec, partition: int, start: int = 0, count: Optio
     if count is None:
         count = spec.n_total // spec.num_partitions - start
     n = C.c_int64()
-    rc = lib().kta_synth_encode_segment_host(C.byref(spec), partition, start, count, batch_records, None, 0, C.byref(n))
+    rc = synth_lib().kta_synth_encode_segment_host(C.byref(spec), partition, start, count, batch_records, None, 0, C.byref(n))
     if rc != 0:
         raise KtaError(rc, "kta_synth_encode_segment_host failed")
     out = np.empty(n.value, dtype=np.uint8)
-    rc = lib().kta_synth_encode_segment_host(C.byref(spec), partition, start, count, batch_records, out.ctypes.data, out.size, C.byref(n))
+    rc = synth_lib().kta_synth_encode_segment_host(C.byref(spec), partition, start, count, batch_records, out.ctypes.data, out.size, C.byref(n))
     if rc != 0:
         raise KtaError(rc, "kta_synth_encode_segment_host failed")
     return out

@@ -211,8 +211,8 @@ def test_edge_cases():
         assert e.message_metrics.overall_count() == 0 and e.alive_keys() == 0
 
 
-def test_reset_forgets_the_alive_table_in_o1():
-    """kta_reset starts a new epoch instead of wiping 32 GiB: stamps of the previous topic must not leak."""
+def test_reset_forgets_the_alive_table():
+    """kta_reset wipes the alive-key table: stamps of the previous topic must not leak."""
     sa = synth.make_spec(8 * 4000, 8, distinct_keys=800, tombstone_per_10k=1000, key_mode=1)
     sb = synth.make_spec(8 * 3000, 8, distinct_keys=800, tombstone_per_10k=6000, key_mode=1, seed=77)   # same key space
     ta, tb = synth.fill_host(sa), synth.fill_host(sb)
@@ -298,6 +298,185 @@ def test_partition_out_of_range_is_an_error():
         assert ei.value.code == 4
 
 
+def test_out_of_range_partitions_are_left_out_of_every_metric():
+    """A record whose partition is outside [0, P) takes part in nothing — counters, sums, extrema, alive keys — so the
+    state stays consistent and equals the reference fed with the in-range records only; finalize says how many."""
+    rng = np.random.default_rng(21)
+    P = 6
+    t = random_topic(rng, 40_000, P)
+    badp = rng.random(t.n) < 0.07
+    part = t.partition.copy()
+    part[badp] = rng.choice(np.array([-1, -5, P, P + 1, 1 << 30], dtype=np.int32), size=int(badp.sum()))
+    # the bad records carry the extreme timestamps and sizes: they must not show up in the extrema either
+    ts, vl = t.ts_ms.copy(), t.value_len.copy()
+    ts[badp] = np.where(rng.random(int(badp.sum())) < 0.5, 1, 4_000_000_000_000)
+    vl[badp] = (1 << 31) - 1
+    from kafka_topic_analyzer_b200.synth import HostTopic
+    tb = HostTopic(part, t.offset, ts, t.key_len, vl, t.seq, t.key_bytes, t.key_tile_base)
+    # oracle: the in-range records only, in order
+    good = ~badp
+    kl0 = np.maximum(t.key_len, 0).astype(np.int64)
+    koff = np.concatenate([[0], np.cumsum(kl0)])
+    keep = np.concatenate([t.key_bytes[koff[i]:koff[i + 1]] for i in np.nonzero(good)[0]] or [np.zeros(0, np.uint8)])
+    o = Oracle(count_alive_keys=True, now=NOW)
+    o.handle_batch(part[good], ts[good], t.key_len[good], vl[good], keep.astype(np.uint8))
+    for mode in ("device", "host"):
+        with KtaEngine(P, count_alive_keys=True, hll_precision=10, now=NOW, ring_records=8192) as e:
+            with pytest.raises(KtaError) as ei:
+                if mode == "device":
+                    scan_device(e, tb)
+                else:
+                    e.push_batch_host(tb.partition, tb.ts_ms, tb.key_len, tb.value_len, tb.key_bytes, None)
+                    e.finalize()
+            assert ei.value.code == 4
+            assert e.bad_partition_records() == int(badp.sum())
+            assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10), extra_partitions=())
+
+
+# ------------------------------------------------------------------------------------------------
+# the alive-key table itself: growth + re-run, seq window (rebase), ordering contract
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["device", "host_batch", "push", "device_batches"])
+def test_alive_table_grows_and_restamps(mode):
+    """A table that starts far too small (1 KiB = 128 slots for 6000 keys) drops stamps, is grown (rehash) and the pending
+    batches are re-run stamps-only: the result must equal the BitSet replay, counters must not be counted twice."""
+    P, n = 8, 120_000
+    spec = synth.make_spec(n, P, key_mode=1, distinct_keys=6000, tombstone_per_10k=3000, null_key_per_10k=200)
+    t = synth.fill_host(spec)
+    o = oracle_for(t, count_alive_keys=True, now=NOW)
+    with KtaEngine(P, count_alive_keys=True, hll_precision=11, now=NOW, ring_records=4096, alive_table_kib=1) as e:
+        assert e.alive_table_stats()[0] == 128
+        if mode == "device":
+            scan_device(e, t)
+        elif mode == "host_batch":
+            e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base)   # 30 ring chunks
+            e.finalize()
+        elif mode == "push":
+            off = 0
+            for i in range(n):
+                kl = int(t.key_len[i])
+                key = None if kl < 0 else t.key_bytes[off:off + kl].tobytes()
+                off += max(kl, 0)
+                e.push(int(t.partition[i]), int(t.offset[i]), int(t.ts_ms[i]), key, int(t.value_len[i]))
+            e.finalize()
+        else:
+            # several device batches queued before the first confirmation: all of them are re-run
+            import torch
+            T = N.KTA_KEY_TILE
+            kb = torch.zeros(t.key_bytes.size + 16, dtype=torch.uint8, device="cuda")
+            kb[: t.key_bytes.size] = torch_dev(t.key_bytes)
+            cols = [torch_dev(c) for c in (t.partition, t.ts_ms, t.key_len, t.value_len)]
+            tb = torch_dev(t.key_tile_base)
+            cuts = [0, 40 * T, 300 * T, 301 * T, n]
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                e.scan_batch_device(*[c[lo:hi] for c in cols], key_bytes=kb, key_bytes_len=int(t.key_bytes.size),
+                                    key_tile_base=tb[lo // T:])
+            e.finalize()
+        slots, occupied, grows, reruns = e.alive_table_stats()
+        assert grows >= 1 and reruns >= 1 and occupied * 10 <= slots * 7
+        distinct = len(set(np_oracle.fnv32_many(t.key_len, t.key_bytes)[t.key_len >= 0].tolist()))
+        assert occupied == distinct
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(11))
+        # and the grown table keeps working: the same topic again (new sequence numbers) changes nothing but the counters
+        before = e.alive_keys()
+        e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base)
+        e.finalize()
+        assert e.alive_keys() == before and e.message_metrics.overall_count() == 2 * n
+
+
+def test_alive_table_rebase_keeps_last_writer_across_the_seq_window():
+    """The table keeps 31 bits of seq.  Batches whose sequence numbers leave the window force a rebase (every entry
+    becomes 'older than anything that follows'); the result is still the BitSet replay in batch order."""
+    rng = np.random.default_rng(3)
+    P = 4
+    o = Oracle(count_alive_keys=True, now=NOW)
+    bases = [0, (1 << 31) - 1000, (1 << 31) + 10_000, (1 << 33) + 5, (1 << 33) + 20_000, (1 << 40)]
+    with KtaEngine(P, count_alive_keys=True, hll_precision=9, now=NOW, alive_table_kib=64) as e:
+        for b, base in enumerate(bases):
+            t = random_topic(rng, 6000, P, max_key=6)      # short keys: plenty of overwrites between batches
+            o.handle_batch(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes)
+            if b % 2:
+                e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base, seq_base=base)
+            else:
+                import torch
+                kb = torch.zeros(t.key_bytes.size + 16, dtype=torch.uint8, device="cuda")
+                kb[: t.key_bytes.size] = torch_dev(t.key_bytes)
+                e.scan_batch_device(torch_dev(t.partition), torch_dev(t.ts_ms), torch_dev(t.key_len), torch_dev(t.value_len),
+                                    key_bytes=kb, key_bytes_len=int(t.key_bytes.size), seq_base=base)
+            e.finalize()
+            assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(9))
+        # a batch that goes back before the window: refused, state untouched
+        t = random_topic(rng, 100, P)
+        with pytest.raises(KtaError) as ei:
+            e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base, seq_base=5)
+        assert ei.value.code == 1
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True)
+        # exports need absolute sequence numbers, which a rebase forgets
+        with pytest.raises(KtaError):
+            e.alive_export_count()
+
+
+def test_seq_contract():
+    """Last-writer-wins is decided by seq (src/kafka.rs:99).  Default = the handle's running count across every entry
+    point; re-using sequence numbers without a seq column is refused; explicit seq columns must fit the 31-bit window."""
+    rng = np.random.default_rng(9)
+    P = 3
+    o = Oracle(count_alive_keys=True, now=NOW)
+    with KtaEngine(P, count_alive_keys=True, now=NOW) as e:
+        for b in range(4):
+            t = random_topic(rng, 3000, P, max_key=5)
+            o.handle_batch(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes)
+            if b == 1:     # per-record pushes in between: the batches after them must count on from there
+                off = 0
+                for i in range(t.n):
+                    kl = int(t.key_len[i])
+                    e.push(int(t.partition[i]), 0, int(t.ts_ms[i]), None if kl < 0 else t.key_bytes[off:off + kl].tobytes(),
+                           int(t.value_len[i]))
+                    off += max(kl, 0)
+            else:
+                e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base)   # seq_base=None
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True)
+        t = random_topic(rng, 500, P)
+        with pytest.raises(KtaError) as ei:
+            e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base, seq_base=0)
+        assert ei.value.code == 1 and "seq_base" in str(ei.value)
+        # explicit seq outside the window: reported by finalize, the offending records are left out of the table
+        seq = np.arange(t.n, dtype=np.uint64) + np.uint64((1 << 31) + 10)
+        e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base, seq=seq)
+        with pytest.raises(KtaError) as ei:
+            e.finalize()
+        assert ei.value.code == 1 and "window" in str(ei.value)
+
+
+@pytest.mark.parametrize("L,with_tile_base", [(150, False), (150, True), (1000, False), (40_000, False)])
+def test_host_batch_whose_keys_exceed_the_staging_ring(L, with_tile_base):
+    """kta_push_batch_host splits a batch into chunks whose key bytes fit ring_key_bytes; tiles heavier than 64 B per
+    record used to trip the split.  Fixed-length L-byte keys, total far above the ring's key capacity."""
+    from kafka_topic_analyzer_b200.synth import HostTopic, tile_base_from_key_len
+    rng = np.random.default_rng(L)
+    n = 40_000 if L < 10_000 else 1500
+    kl = np.where(rng.random(n) < 0.02, -1, L).astype(np.int32)
+    pool = rng.integers(0, 256, size=(300, L), dtype=np.uint8)
+    kb = pool[rng.integers(0, 300, size=int((kl >= 0).sum()))].reshape(-1)
+    t = HostTopic(rng.integers(0, 4, size=n).astype(np.int32), np.zeros(n, dtype=np.int64),
+                  (1_600_000_000_000 + np.arange(n)).astype(np.int64), kl, rng.integers(-1, 300, size=n).astype(np.int32),
+                  np.arange(n, dtype=np.uint64), kb, tile_base_from_key_len(kl))
+    o = oracle_for(t, count_alive_keys=True, now=NOW)
+    ring_kb = 1 << 20 if L < 10_000 else 6 << 20       # one 128-record tile of 40 KB keys is 5 MB
+    assert kb.size > 4 * ring_kb
+    with KtaEngine(4, count_alive_keys=True, now=NOW, ring_records=16384, ring_key_bytes=ring_kb) as e:
+        e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, t.key_tile_base if with_tile_base else None)
+        e.finalize()
+        assert_parity(e, o, 4, check_alive=True)
+    # a single tile that cannot fit is the one case that is refused, and it says so
+    with KtaEngine(4, count_alive_keys=True, now=NOW, ring_records=16384, ring_key_bytes=100 * L) as e:
+        with pytest.raises(KtaError) as ei:
+            e.push_batch_host(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes, None)
+        assert ei.value.code == 1 and "ring_key_bytes" in str(ei.value)
+
+
 def test_long_keys_fall_back_to_global_reads():
     """A tile whose keys exceed the 20 KiB staging buffer takes the direct-global path; results equal."""
     rng = np.random.default_rng(5)
@@ -380,7 +559,10 @@ def test_config1_full_size_properties():
             assert mm.key_size_sum(p) == 16 * mm.key_non_null(p)           # key_mode 0: 16-byte keys
             assert 128 * mm.alive(p) <= mm.value_size_sum(p) <= 384 * mm.alive(p)
         assert mm.smallest_message() == 128 and mm.largest_message() == 16 + 384
-        assert mm.earliest_message()[0] == 1_500_000_000 and mm.latest_message() == (1_500_000_000_000 + (n - 1) * 7 + 999) // 1000 or True
+        # generator: ts = 1.5e12 + 7 i + jitter(0..999); the true extrema come from the column itself (torch reduction)
+        assert mm.earliest_message() == (int(topic.ts_ms.min().item()) // 1000, 0) == (1_500_000_000, 0)
+        assert mm.latest_message() == int(topic.ts_ms.max().item()) // 1000
+        assert (1_500_000_000_000 + (n - 1) * 7) // 1000 <= mm.latest_message() <= (1_500_000_000_000 + (n - 1) * 7 + 999) // 1000
         # halves
         e.reset()
         T = N.KTA_KEY_TILE
@@ -422,14 +604,93 @@ def test_alive_keys_large_vs_exact_set():
         lib().kta_set_hash_capture(e.handle, None)
         got = e.alive_keys()
         est = e.alive_keys_hll()
-    # independent: stamp = seq*2 + alive, max per hash via a sort (torch is plumbing here, not the product)
-    h64 = hashes.to(torch.int64) & 0xFFFFFFFF
-    stamp = (torch.arange(n, device="cuda", dtype=torch.int64) << 1) | (topic.value_len >= 0).to(torch.int64)
-    key = (h64 << 32) | 0  # sort by hash then by stamp: pack hash in the high half of a float-free composite
-    order = torch.argsort(key * 0 + h64, stable=True)
-    hs, ss = h64[order], stamp[order]          # stable sort keeps seq order inside one hash
-    last = torch.ones(n, dtype=torch.bool, device="cuda")
-    last[:-1] = hs[1:] != hs[:-1]
-    want = int((last & ((ss & 1) == 1)).sum().item())
+    want, _ = _alive_by_sort(hashes, topic.value_len, None)
     assert got == want
     assert abs(est - want) <= 4 * 1.04 / 128 * want
+
+
+def _alive_by_sort(hashes_i32, value_len, keyed):
+    """Independent statement of metric.rs:288-305 on the device: composite (hash, seq, alive) keys sorted; the last
+    element of every hash run is that hash's last writer.  torch is plumbing for the CHECK here, not the product."""
+    import torch
+    n = hashes_i32.shape[0]
+    assert n < (1 << 30)
+    comp = ((hashes_i32.to(torch.int64) & 0xFFFFFFFF) << 31) | (torch.arange(n, device="cuda", dtype=torch.int64) << 1)
+    comp |= (value_len >= 0).to(torch.int64)
+    if keyed is not None:
+        comp = comp[keyed]
+    comp = torch.sort(comp)[0]
+    last = torch.ones(comp.shape[0], dtype=torch.bool, device="cuda")
+    last[:-1] = (comp[1:] >> 31) != (comp[:-1] >> 31)
+    return int((last & ((comp & 1) == 1)).sum().item()), int(last.sum().item())
+
+
+def test_config2_full_size_alive_exact():
+    """BASELINE configs[2] at its stated size: 64 partitions, 1e9 messages, 1e7 distinct keys, -c.  The exact alive count
+    of the compact table vs the sort-based statement over all 1e9 (hash, seq, alive) triples; the table must hold exactly
+    the distinct hashes; HLL over the resolved set within 4 sigma."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~80 GB of HBM")
+    P, n = 64, 1_000_000_000
+    spec = synth.make_spec(n, P, distinct_keys=10_000_000, null_key_per_10k=0)     # compacted topic: every record keyed, 5 % tombstones
+    topic = synth.DeviceTopic(spec)
+    hashes = torch.empty(n, dtype=torch.int32, device="cuda")
+    with KtaEngine(P, count_alive_keys=True, hll_precision=14, now=NOW) as e:
+        lib().kta_set_hash_capture(e.handle, hashes.data_ptr())
+        e.scan_batch_device(topic.partition, topic.ts_ms, topic.key_len, topic.value_len, key_bytes=topic.key_bytes,
+                            key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        lib().kta_set_hash_capture(e.handle, None)
+        got, est = e.alive_keys(), e.alive_keys_hll()
+        slots, occupied, grows, reruns = e.alive_table_stats()
+        assert e.message_metrics.overall_count() == n
+        # the timed configuration of bench.py --config C2: no capture
+        e.reset()
+        e.scan_batch_device(topic.partition, topic.ts_ms, topic.key_len, topic.value_len, key_bytes=topic.key_bytes,
+                            key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        assert e.alive_keys() == got
+    vl = topic.value_len
+    del topic.partition, topic.ts_ms, topic.key_bytes
+    want, distinct = _alive_by_sort(hashes, vl, None)
+    assert got == want
+    assert occupied == distinct and 9_900_000 < distinct <= 10_000_000      # FNV32 collisions merge a few keys (SURVEY a9)
+    assert abs(est - want) <= 4 * 1.04 / 128 * want
+
+
+def test_config3_rank_shape_256_partitions():
+    """BASELINE configs[3] as ONE of its 8 ranks sees it: 256 partitions of which only p = r (mod 8) occur, 1 KiB mean
+    values, 5e7 of the rank's 5e8 records (the bench runs the full 5e8).  Closed-form shares, identities, and the first
+    2^20 records bit-exact against the oracle (which also checks the shard enumeration of the generator)."""
+    P, world, rank = 256, 8, 5
+    n_total = 400_000_000
+    spec = synth.make_spec(n_total, P, distinct_keys=8_000_000, value_mean=1024)
+    topic = synth.DeviceTopic(spec, rank=rank, world=world)
+    n = topic.n
+    assert n == n_total // world
+    with KtaEngine(P, hll_precision=14, now=NOW) as e:
+        e.scan_batch_device(topic.partition, topic.ts_ms, topic.key_len, topic.value_len, key_bytes=topic.key_bytes,
+                            key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        mm = e.message_metrics
+        assert mm.overall_count() == n
+        for p in range(P):
+            assert mm.total(p) == (n_total // P if p % world == rank else 0)
+            assert mm.key_null(p) + mm.key_non_null(p) == mm.total(p) == mm.alive(p) + mm.tombstones(p)
+            assert mm.key_size_sum(p) == 16 * mm.key_non_null(p)
+            assert 512 * mm.alive(p) <= mm.value_size_sum(p) <= 1536 * mm.alive(p)
+            assert int(e.hist(0, p).sum()) == mm.key_non_null(p) and int(e.hist(1, p).sum()) == mm.alive(p)
+        assert mm.smallest_message() == 512 and mm.largest_message() == 16 + 1536
+        assert mm.earliest_message() == (int(topic.ts_ms.min().item()) // 1000, 0)
+        assert mm.latest_message() == int(topic.ts_ms.max().item()) // 1000
+        m = 1 << 20
+        e.reset()
+        e.scan_batch_device(topic.partition[:m], topic.ts_ms[:m], topic.key_len[:m], topic.value_len[:m],
+                            key_bytes=topic.key_bytes, key_bytes_len=topic.key_bytes_len, key_tile_base=topic.key_tile_base)
+        e.finalize()
+        th = synth.fill_host(spec, rank=rank, world=world, count=m)
+        assert np.array_equal(topic.partition[:m].cpu().numpy(), th.partition) and set(th.partition.tolist()) <= set(range(rank, P, world))
+        o = oracle_for(th, track_stream=True, now=NOW)
+        assert_parity(e, o, P, hll_regs=o.hll_stream_regs(14))

@@ -3,8 +3,7 @@ import glob
 from kafka_topic_analyzer_b200 import _native as N
 variants = {
  'base': [],
- 'nohll': ['KTA_EXP_NO_HLL'],
- 'nofnv': ['KTA_EXP_NO_FNV'],
+ 'nohints': ['KTA_L2_HINTS=0'],
 }
 for f in glob.glob(N.LIB_PATH.replace('.so','_exp_*.so')): os.remove(f)
 import concurrent.futures as cf
