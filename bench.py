@@ -262,9 +262,11 @@ def run_reference(a):
 
 
 # --------------------------------------------------------------------------------------------------
-def make_engine(kta, a, mode, device):
+def make_engine(kta, a, mode, device, shard=None):
+    """shard = (rank, world) for a partition-sharded scan: the kernel carves counter columns for the owned partitions only"""
     return kta.KtaEngine(a.partitions, count_alive_keys=mode in ("fused", "alive"),
-                         hll_precision=a.hll if mode in ("fused", "hll") else 0, device=device, alive_table_kib=a.alive_table_kib)
+                         hll_precision=a.hll if mode in ("fused", "hll") else 0, device=device, alive_table_kib=a.alive_table_kib,
+                         shard=shard if shard and shard[1] > 1 else None)
 
 
 def scan_topic(eng, topic, mode):
@@ -337,7 +339,7 @@ def measure(a, ctx, full):
     assert n == a.n
     alg_bytes = 20 * n + (topic.key_bytes_len if a.mode != "counters" else 0)
 
-    eng = make_engine(kta, a, a.mode, local)
+    eng = make_engine(kta, a, a.mode, local, shard=(rank, vw))
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
 

@@ -69,6 +69,10 @@ typedef struct kta_config {
     int64_t now_s;             /* construction wall clock for earliest_message (Utc::now(), */
     int32_t now_ns;            /*   src/metric.rs:39); now_s == INT64_MIN → library reads the clock */
     int32_t reserved1;
+    int32_t shard_world;       /* partition-sharded job (one handle per GPU, gpu = partition mod G, SURVEY.md §8 e): this */
+    int32_t shard_rank;        /*   handle scans only partitions p with p % shard_world == shard_rank; records of other
+                                    partitions are left out like out-of-range ones.  0 or 1 = not sharded.  The handle
+                                    still holds (and, after kta_merge_import_device, reports) all num_partitions. */
 } kta_config;
 
 /* kta_batch.seq_base value that means "continue this handle's running count" (what kta_push does: the consumer's

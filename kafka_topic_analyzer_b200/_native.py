@@ -79,7 +79,7 @@ class Config(C.Structure):
         ("struct_size", C.c_int32), ("device", C.c_int32), ("num_partitions", C.c_int32),
         ("count_alive_keys", C.c_int32), ("hll_precision", C.c_int32), ("alive_table_kib", C.c_int32),
         ("ring_records", C.c_int64), ("ring_key_bytes", C.c_int64), ("now_s", C.c_int64),
-        ("now_ns", C.c_int32), ("reserved1", C.c_int32),
+        ("now_ns", C.c_int32), ("reserved1", C.c_int32), ("shard_world", C.c_int32), ("shard_rank", C.c_int32),
     ]
 
 

@@ -132,9 +132,17 @@ struct kta_handle {
     bool ring_dev_ready = false, ring_host_ready = false;
     int64_t ring_records = 0, ring_key_bytes = 0;
     int cur = 0;          // chunk being filled by kta_push
-    int64_t cur_n = 0;    // records in it
-    int64_t cur_kb = 0;   // key bytes in it
-    uint64_t next_seq = 0;
+    // kta_push's hot state: raw cursors into that chunk's pinned landing area (one cache line, no indirection per call)
+    struct PushCursor {
+        int32_t *part = nullptr, *klen = nullptr, *vlen = nullptr;
+        int64_t *ts = nullptr;
+        uint8_t *keys = nullptr;
+        uint64_t *tile_base = nullptr;
+        int64_t n = 0, cap = 0;     // records in the chunk / its capacity (0 until the ring exists: first push takes the slow path)
+        int64_t kb = 0, kcap = 0;   // key bytes in the chunk / capacity
+        bool hash = false;          // key bytes travel only when they are hashed
+    } pc;
+    uint64_t next_seq = 0;   // seq of the first record not yet handed to a scan (records in the open chunk follow it)
     // host mirror (valid after finalize)
     bool finalized = false;
     std::vector<uint64_t> h_sums;
@@ -142,6 +150,8 @@ struct kta_handle {
     std::vector<uint32_t> h_hll;
     uint64_t h_alive = 0;
     // occupancy-derived grids
+    int shard_world = 1, shard_rank = 0;     // partition-sharded scan: only partitions p % world == rank reach this handle
+    int columns = 0;                         // counter columns the scan kernel carves = partitions this handle owns
     bool smem_counters = true;               // per-partition counters fit in shared memory
     size_t smem_optin = 0;
     // stats / timing
@@ -172,7 +182,7 @@ static void scan_shape(const kta_handle *h, bool hash, int64_t n, int64_t key_by
         keybuf = (int)std::min<int64_t>(std::max<int64_t>(want, KEYBUF_MIN), KEYBUF_MAX);
         keybuf = (keybuf + 15) / 16 * 16;
     }
-    const int P = h->cfg.num_partitions;
+    const int P = h->columns;
     // Leave the SM some L1: the header loads stream through it, and with (almost) all 228 KB carved out as shared
     // memory the loads in flight are throttled (measured at P = 256).  KTA_SCAN_L1_RESERVE (bytes) is a tuning knob.
     static const size_t l1_reserve = [] { const char *e = getenv("KTA_SCAN_L1_RESERVE"); return e ? (size_t)atoll(e) : (size_t)0; }();
@@ -191,21 +201,24 @@ static void scan_shape(const kta_handle *h, bool hash, int64_t n, int64_t key_by
 }
 
 // one persistent CTA per SM; every variant may use the whole opt-in shared memory (the shape is chosen per launch).
-// variant index: 0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture
-template <int MODE, bool SMEM, bool CAPTURE>
+// variant index: 0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture, 5..7 = 0..2 for a partition-sharded handle
+template <int MODE, bool SMEM, bool CAPTURE, bool SHARD>
 static int prepare_variant(kta_handle *h) {
-    CU(cudaFuncSetAttribute(scan_kernel<MODE, SMEM, CAPTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    CU(cudaFuncSetAttribute(scan_kernel<MODE, SMEM, CAPTURE, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
     return KTA_OK;
 }
 
 template <bool SMEM>
 static int prepare_all(kta_handle *h) {
     int rc;
-    if ((rc = prepare_variant<MODE_COUNTERS, SMEM, false>(h))) return rc;
-    if ((rc = prepare_variant<MODE_HLL, SMEM, false>(h))) return rc;
-    if ((rc = prepare_variant<MODE_EXACT, SMEM, false>(h))) return rc;
-    if ((rc = prepare_variant<MODE_HLL, SMEM, true>(h))) return rc;
-    if ((rc = prepare_variant<MODE_EXACT, SMEM, true>(h))) return rc;
+    if ((rc = prepare_variant<MODE_COUNTERS, SMEM, false, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_HLL, SMEM, false, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_EXACT, SMEM, false, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_HLL, SMEM, true, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_EXACT, SMEM, true, false>(h))) return rc;
+    if ((rc = prepare_variant<MODE_COUNTERS, SMEM, false, true>(h))) return rc;
+    if ((rc = prepare_variant<MODE_HLL, SMEM, false, true>(h))) return rc;
+    if ((rc = prepare_variant<MODE_EXACT, SMEM, false, true>(h))) return rc;
     return KTA_OK;
 }
 
@@ -216,7 +229,10 @@ static void launch_variant(int v, int grid, int threads, size_t sm, cudaStream_t
         case 1: scan_kernel<MODE_HLL, SMEM, false><<<grid, threads, sm, st>>>(prm); break;
         case 2: scan_kernel<MODE_EXACT, SMEM, false><<<grid, threads, sm, st>>>(prm); break;
         case 3: scan_kernel<MODE_HLL, SMEM, true><<<grid, threads, sm, st>>>(prm); break;
-        default: scan_kernel<MODE_EXACT, SMEM, true><<<grid, threads, sm, st>>>(prm); break;
+        case 4: scan_kernel<MODE_EXACT, SMEM, true><<<grid, threads, sm, st>>>(prm); break;
+        case 5: scan_kernel<MODE_COUNTERS, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
+        case 6: scan_kernel<MODE_HLL, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
+        default: scan_kernel<MODE_EXACT, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
     }
 }
 
@@ -316,8 +332,15 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
         CU(cudaHostAlloc(&h->h_alive_status, 8, cudaHostAllocDefault));
     }
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cfg->shard_world > 1) {
+        if (cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_world || cfg->shard_world > P)
+            return fail(KTA_ERR_INVALID, "shard_rank %d / shard_world %d invalid for %d partitions", cfg->shard_rank, cfg->shard_world, P);
+        h->shard_world = cfg->shard_world;
+        h->shard_rank = cfg->shard_rank;
+    }
+    h->columns = (P - h->shard_rank + h->shard_world - 1) / h->shard_world;   // partitions p < P with p % world == rank
     // counters in shared memory as long as at least 8 warps still fit beside them
-    h->smem_counters = smem_counter_bytes(P) + 8 * warp_smem_bytes(true, KEYBUF_MIN) <= h->smem_optin;
+    h->smem_counters = smem_counter_bytes(h->columns) + 8 * warp_smem_bytes(true, KEYBUF_MIN) <= h->smem_optin;
     int rc;
     if ((rc = h->smem_counters ? prepare_all<true>(h) : prepare_all<false>(h))) return rc;
     if ((rc = state_reset_device(h))) return rc;
@@ -328,7 +351,7 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
 extern "C" int kta_create(const kta_config *cfg, kta_handle **out) {
     if (!cfg || !out) return fail(KTA_ERR_INVALID, "null argument");
     if (cfg->struct_size != (int32_t)sizeof(kta_config))
-        return fail(KTA_ERR_INVALID, "kta_config.struct_size %d != %zu", cfg->struct_size, sizeof(kta_config));
+        return fail(KTA_ERR_INVALID, "kta_config.struct_size %d != %zu (ABI version %d)", cfg->struct_size, sizeof(kta_config), KTA_ABI_VERSION);
     kta_handle *h = new (std::nothrow) kta_handle();
     if (!h) return fail(KTA_ERR_NOMEM, "out of host memory");
     const int rc = create_impl(cfg, h);
@@ -370,6 +393,10 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     const int mode = exact ? MODE_EXACT : (h->cfg.hll_precision || capture) ? MODE_HLL : MODE_COUNTERS;
     if (mode == MODE_HLL && !h->cfg.hll_precision)
         return fail(KTA_ERR_INVALID, "hash capture needs count_alive_keys or hll_precision");
+    prm.shard_world = h->shard_world;
+    prm.shard_rank = h->shard_rank;
+    prm.Pc = h->columns;
+    prm.shard_magic = h->shard_world > 1 ? (uint32_t)((((uint64_t)1 << 32) + (uint64_t)h->shard_world - 1) / (uint64_t)h->shard_world) : 0u;
     prm.ntiles = (prm.n + TILE - 1) / TILE;
     if (prm.ntiles >= (int64_t)1 << 30) return fail(KTA_ERR_INVALID, "batch of %lld records: split it (one scan takes < 2^37 records)", (long long)prm.n);
     prm.P = P;
@@ -401,7 +428,8 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
         if (!prm.key_bytes && key_readable > 0) return fail(KTA_ERR_INVALID, "key_bytes is NULL but keys are required");
         prm.stage_limit = (((uintptr_t)prm.key_bytes & 15u) == 0) ? ((uint64_t)key_readable & ~15ull) : 0;
     }
-    const int variant = mode + (capture ? 2 : 0);
+    if (capture && h->shard_world > 1) return fail(KTA_ERR_INVALID, "hash capture is not available on a partition-sharded handle");
+    const int variant = h->shard_world > 1 ? 5 + mode : mode + (capture ? 2 : 0);
     int threads = 0, keybuf = 0;
     size_t sm = 0;
     scan_shape(h, mode != MODE_COUNTERS, prm.n, key_bytes, threads, keybuf, sm);
@@ -567,6 +595,8 @@ static int derive_tile_base(kta_handle *h, const int32_t *d_klen, int64_t n, uin
     return KTA_OK;
 }
 
+static int ring_flush(kta_handle *h);
+
 // seq of a batch's record 0.  KTA_SEQ_AUTO continues the handle's running count (what kta_push and the log-segment
 // entry points do).  With -c and no explicit seq column, last-writer-wins is decided by seq_base + i alone, so a batch
 // that re-uses sequence numbers the handle has already handed out would silently let OLDER records win: refused.
@@ -591,6 +621,7 @@ extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
         return fail(KTA_ERR_INVALID, "partition/ts_ms/key_len/value_len columns are required");
     int rc;
     if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;   // records pushed earlier come first in seq order
     uint64_t seq_base = 0;
     if ((rc = resolve_seq_base(h, b, &seq_base))) return rc;
     ScanParams prm{};
@@ -625,7 +656,6 @@ extern "C" int kta_scan_batch_device(kta_handle *h, const kta_batch *b) {
 // ------------------------------------------------------------------------------------------------
 // Kafka RecordBatch v2 segments → SoA → scan (kernels in kta_logdecode.cuh)
 // ------------------------------------------------------------------------------------------------
-static int ring_flush(kta_handle *h);
 
 template <typename T>
 static int grow(T *&ptr, int64_t &cap, int64_t need, cudaStream_t s) {
@@ -815,11 +845,21 @@ static int ring_host_init(kta_handle *h) {
     return KTA_OK;
 }
 
+static void push_cursor_bind(kta_handle *h) {
+    Chunk &c = h->chunks[h->cur];
+    auto &pc = h->pc;
+    pc.part = c.h_partition; pc.klen = c.h_klen; pc.vlen = c.h_vlen; pc.ts = c.h_ts; pc.keys = c.h_keys; pc.tile_base = c.h_tile_base;
+    pc.n = 0; pc.kb = 0;
+    pc.cap = h->ring_host_ready ? h->ring_records : 0;
+    pc.kcap = h->ring_key_bytes;
+    pc.hash = h->need_hash || h->d_hash_out;
+}
+
 // stage one pinned chunk and scan it
 static int ring_flush(kta_handle *h) {
-    if (h->cur_n == 0) return KTA_OK;
+    if (h->pc.n == 0) return KTA_OK;
     Chunk &c = h->chunks[h->cur];
-    const int64_t n = h->cur_n, kb = h->cur_kb;
+    const int64_t n = h->pc.n, kb = h->pc.kb;
     const int64_t ntiles = (n + TILE - 1) / TILE;
     c.h_tile_base[ntiles] = (uint64_t)kb;
     cudaStream_t s = h->stream;
@@ -833,7 +873,7 @@ static int ring_flush(kta_handle *h) {
     }
     ScanParams prm{};
     prm.n = n;
-    prm.seq_base = h->next_seq - (uint64_t)n;
+    prm.seq_base = h->next_seq;
     prm.partition = c.d_partition;
     prm.ts_ms = c.d_ts;
     prm.key_len = c.d_klen;
@@ -842,46 +882,60 @@ static int ring_flush(kta_handle *h) {
     prm.key_tile_base = c.d_tile_base;
     int rc;
     if ((rc = launch_scan(h, prm, (kb + 15) & ~(int64_t)15, kb, h->cur))) return rc;
+    h->next_seq += (uint64_t)n;
     if (h->d_alive_table) CU(cudaMemcpyAsync(c.h_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(c.free_ev, s));
     h->cur = (h->cur + 1) % NCHUNK;
-    h->cur_n = 0;
-    h->cur_kb = 0;
+    push_cursor_bind(h);
     // the next chunk may still be in flight from NCHUNK flushes ago
     CU(cudaEventSynchronize(h->chunks[h->cur].free_ev));
     return alive_release_chunk(h, h->cur);
 }
 
+// kta_push off the fast path: first call (ring not yet allocated), chunk full, or an oversized key
+static int __attribute__((noinline)) push_slow(kta_handle *h, int64_t kl) {
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if (!h->ring_host_ready) {
+        if ((rc = ring_host_init(h))) return rc;
+        push_cursor_bind(h);
+    }
+    if (kl > h->ring_key_bytes) return fail(KTA_ERR_INVALID, "key of %lld bytes exceeds ring_key_bytes", (long long)kl);
+    if (h->pc.n == h->pc.cap || h->pc.kb + kl > h->pc.kcap) return ring_flush(h);
+    return KTA_OK;
+}
+
 extern "C" int kta_push(kta_handle *h, int32_t partition, int64_t offset, int64_t ts_ms, const uint8_t *key,
                         int32_t key_len, int32_t value_len) {
     (void)offset;  // never read by a metric; termination logic stays with the caller
-    if (!h) return fail(KTA_ERR_INVALID, "null handle");
-    int rc;
-    if (!h->ring_host_ready) {
-        if ((rc = set_device(h))) return rc;
-        if ((rc = ring_host_init(h))) return rc;
+    if (__builtin_expect(!h, 0)) return fail(KTA_ERR_INVALID, "null handle");
+    auto &pc = h->pc;
+    const int64_t kl = (pc.hash && key_len > 0) ? key_len : 0;  // key bytes only travel when they are hashed
+    if (__builtin_expect(pc.n == pc.cap || pc.kb + kl > pc.kcap, 0)) {
+        const int rc = push_slow(h, kl);
+        if (rc) return rc;
     }
-    const bool hash = h->need_hash || h->d_hash_out;
-    const int64_t kl = (hash && key_len > 0) ? key_len : 0;  // key bytes only travel when they are hashed
-    if (kl > h->ring_key_bytes) return fail(KTA_ERR_INVALID, "key of %lld bytes exceeds ring_key_bytes", (long long)kl);
-    if (h->cur_n == h->ring_records || h->cur_kb + kl > h->ring_key_bytes) {
-        if ((rc = set_device(h))) return rc;
-        if ((rc = ring_flush(h))) return rc;
-    }
-    Chunk &c = h->chunks[h->cur];
-    const int64_t i = h->cur_n;
-    if ((i & (TILE - 1)) == 0) c.h_tile_base[i / TILE] = (uint64_t)h->cur_kb;
-    c.h_partition[i] = partition;
-    c.h_ts[i] = ts_ms;
-    c.h_klen[i] = key_len < 0 ? -1 : key_len;
-    c.h_vlen[i] = value_len < 0 ? -1 : value_len;
+    const int64_t i = pc.n;
+    if ((i & (TILE - 1)) == 0) pc.tile_base[i / TILE] = (uint64_t)pc.kb;
+    pc.part[i] = partition;
+    pc.ts[i] = ts_ms;
+    pc.klen[i] = key_len < 0 ? -1 : key_len;
+    pc.vlen[i] = value_len < 0 ? -1 : value_len;
     if (kl) {
-        if (!key) return fail(KTA_ERR_INVALID, "key is NULL with key_len %d", key_len);
-        memcpy(c.h_keys + h->cur_kb, key, (size_t)kl);
-        h->cur_kb += kl;
+        if (__builtin_expect(!key, 0)) return fail(KTA_ERR_INVALID, "key is NULL with key_len %d", key_len);
+        uint8_t *dst = pc.keys + pc.kb;
+        if (kl == 16) {            // ids, hashes, UUIDs: two register moves instead of a call
+            uint64_t a, b;
+            memcpy(&a, key, 8); memcpy(&b, key + 8, 8);
+            memcpy(dst, &a, 8); memcpy(dst + 8, &b, 8);
+        } else if (kl <= 8) {      // short keys: byte-exact, no call (the landing area has slack only at its end)
+            for (int64_t j = 0; j < kl; j++) dst[j] = key[j];
+        } else {
+            memcpy(dst, key, (size_t)kl);
+        }
+        pc.kb += kl;
     }
-    h->cur_n = i + 1;
-    h->next_seq++;
+    pc.n = i + 1;
     h->finalized = false;
     return KTA_OK;
 }
@@ -1001,8 +1055,8 @@ extern "C" int kta_reset(kta_handle *h) {
     if (!h) return fail(KTA_ERR_INVALID, "null handle");
     int rc;
     if ((rc = set_device(h))) return rc;
-    h->cur_n = 0;
-    h->cur_kb = 0;
+    h->pc.n = 0;
+    h->pc.kb = 0;
     h->next_seq = 0;
     h->finalized = false;
     h->launches = 0;

@@ -64,7 +64,10 @@ struct ScanParams {
     const uint64_t *key_tile_base;   // [ntiles+1] absolute byte offsets relative to key_bytes
     const uint64_t *seq;             // optional explicit seq column
     int64_t ntiles;
-    int32_t P;
+    int32_t P;                       // partitions of the topic (ids 0..P-1)
+    int32_t shard_world, shard_rank; // this handle scans only partitions p with p % shard_world == shard_rank (1, 0 = all)
+    int32_t Pc;                      // counter columns = owned partitions; column c holds partition c * shard_world + shard_rank
+    uint32_t shard_magic;            // ceil(2^32 / shard_world): p / shard_world = mulhi(p, magic) for p < 2^20
     int32_t hll_p;                   // HLL index bits (MODE_HLL)
     uint64_t stage_limit;            // bytes readable from key_bytes by 16-byte bulk copies, rounded DOWN to 16; 0 = staging not allowed
     int32_t keybuf;                  // bytes of one key stage (multiple of 16, incl. KEYBUF_SLACK)
@@ -283,6 +286,16 @@ __host__ __device__ __forceinline__ uint32_t hll_mix(uint32_t h) {
 #endif
 }
 
+// the inverse bijection (the alive-key table stores mixed hashes; exports and the tests want the reference hash back)
+__host__ __device__ __forceinline__ uint32_t hll_unmix(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x7ed1b41du;              // 0xc2b2ae35^-1 mod 2^32
+    h ^= (h >> 13) ^ (h >> 26);
+    h *= 0xa5cb9243u;              // 0x85ebca6b^-1 mod 2^32
+    h ^= h >> 16;
+    return h;
+}
+
 __device__ __forceinline__ uint32_t hll_skip_mask(int p, uint32_t floor) {
     const uint32_t f = min(floor, (uint32_t)(32 - p));
     return f ? (((1u << f) - 1u) << (32 - p - f)) : 0u;
@@ -338,13 +351,15 @@ struct Counters {
     uint32_t sbase;            // shared-window address of row 0
     uint32_t *s;               // the same, as a generic pointer (flush / fold)
     unsigned long long *g;
-    int P;
-    // row r of partition p += c (uniform-row path, flush)
+    int P;                     // counter COLUMNS (= partitions, or the owned ones of a partition-sharded scan)
+    int Pg, G, R;              // partitions of the topic; column c is partition c * G + R
+    __device__ __forceinline__ int part(int c) const { return c * G + R; }
+    // row r of column p += c (uniform-row path, flush)
     __device__ __forceinline__ void row_add(int r, int p, uint32_t c) const {
         if (SMEM) red_shared_add(sbase + 4u * (uint32_t)(r * P + p), c);
-        else if (r < NB) atomicAdd(&g[(size_t)p * NB + r], (unsigned long long)c);                       // khist
-        else if (r == NB) atomicAdd(&g[(size_t)P * (2 * NB + 2) + p], (unsigned long long)c);           // knull
-        else if (r < ROW_V + NB) atomicAdd(&g[(size_t)(P + p) * NB + (r - ROW_V)], (unsigned long long)c);  // vhist
+        else if (r < NB) atomicAdd(&g[(size_t)part(p) * NB + r], (unsigned long long)c);                       // khist
+        else if (r == NB) atomicAdd(&g[(size_t)Pg * (2 * NB + 2) + part(p)], (unsigned long long)c);          // knull
+        else if (r < ROW_V + NB) atomicAdd(&g[(size_t)(Pg + part(p)) * NB + (r - ROW_V)], (unsigned long long)c);  // vhist
         // r == ROW_V + NB (tombstones) is derived, nothing to store
     }
     __device__ __forceinline__ void sum_add(int which /*0 key, 1 value*/, int p, uint32_t v) const {
@@ -352,7 +367,7 @@ struct Counters {
             const uint32_t a = sbase + 4u * (uint32_t)((ROW_KSUM + 2 * which) * P + p);
             red_shared_add(a, v & 0xffffu);
             red_shared_add_nz(a + 4u * (uint32_t)P, v >> 16);
-        } else if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], (unsigned long long)v);
+        } else if (v) atomicAdd(&g[(size_t)Pg * (2 * NB + which) + part(p)], (unsigned long long)v);
     }
     // one record, partition already validated; MessageMetrics::handle_message's increments (metric.rs:215-244).
     // buckets(): the two counting increments.  Lanes that hit the same counter are merged by the hardware
@@ -432,7 +447,7 @@ struct Counters {
                 if (*(volatile uint32_t *)lo >= threshold || *(volatile uint32_t *)(lo + P) >= threshold) {
                     const unsigned long long v = (unsigned long long)atomicExch(lo, 0u) +
                                                  ((unsigned long long)atomicExch(lo + P, 0u) << 16);
-                    if (v) atomicAdd(&g[(size_t)P * (2 * NB + which) + p], v);
+                    if (v) atomicAdd(&g[(size_t)Pg * (2 * NB + which) + part(p)], v);
                 }
             }
         }
@@ -442,13 +457,14 @@ struct Counters {
 // ------------------------------------------------------------------------------------------------
 // alive-key table (LogCompactionInMemoryMetrics, metric.rs:262-305): an open-addressed table with one 64-bit entry per
 // distinct key hash,
-//     hash (32 bits) | seq - origin + 1 (31 bits) | alive (1 bit),          ~0 = empty,
-// holding the stamp of the LAST record that carried this hash.  The reference's BitSet (metric.rs:273-280) is indexed by
+//     x (32 bits) | seq - origin + 1 (31 bits) | alive (1 bit),          ~0 = empty,        x = fmix32(hash),
+// holding the stamp of the LAST record that carried this hash (fmix32 is a bijection: x names the hash exactly, and it
+// is what the table, the seen cache and the HLL sketch all index by, so it is computed once per record).  The reference's BitSet (metric.rs:273-280) is indexed by
 // the hash itself — 2^32 bits, one random DRAM sector per record wherever the state lives; keyed by hash but SIZED by
 // the number of distinct hashes, the same state is about as large as the 126 MB L2 for 1e7 keys, and the one access per
 // record becomes an L2 hit.
 //   * A slot is claimed once (CAS from empty) and keeps its hash for ever; linear probing over 16-byte PAIRS of slots
-//     from home = mulhi(fmix32(hash), pairs), so any table size works, not only powers of two.
+//     from home = mulhi(x, pairs), so any table size works, not only powers of two.
 //   * On a slot that holds the record's hash, atomicMax makes "last" mean highest seq regardless of execution order
 //     (the hash sits in the top bits, so max over equal-hash stamps is max over seq).  Entries only grow, so a plain
 //     read is a safe filter: a record that is not the newest for its hash stops after one 16-byte read.  The scan walks
@@ -479,6 +495,9 @@ constexpr int ALIVE_MAX_PROBES = 96;                // pairs examined before a s
 
 #ifndef KTA_L2_HINTS
 #define KTA_L2_HINTS 1
+#endif
+#ifndef KTA_EXP_ALIVE_STAGE   // ablation knob: 0 = hashes only, 1 = + seen-cache probe and queue, 2 = everything (the product)
+#define KTA_EXP_ALIVE_STAGE 2
 #endif
 // L2 residency control for MODE_EXACT: the table should stay in L2, the record stream should leave it at once.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
@@ -515,11 +534,11 @@ __device__ __forceinline__ unsigned long long alive_atom_cas(unsigned long long 
     return atomicCAS(p, cmp, v);
 }
 
-__host__ __device__ __forceinline__ uint32_t alive_home(uint32_t hash, uint32_t npairs) {
+__host__ __device__ __forceinline__ uint32_t alive_home(uint32_t x /* mixed hash */, uint32_t npairs) {
 #ifdef __CUDA_ARCH__
-    return __umulhi(hll_mix(hash), npairs);
+    return __umulhi(x, npairs);
 #else
-    return (uint32_t)(((uint64_t)hll_mix(hash) * npairs) >> 32);
+    return (uint32_t)(((uint64_t)x * npairs) >> 32);
 #endif
 }
 
@@ -566,6 +585,7 @@ __device__ __noinline__ uint32_t alive_stamp_slow(const AliveTable t, uint32_t p
 }
 
 // One stamp with the home pair already loaded (`e`): the common cases need no second look at memory.
+// (`hash` is the mixed hash x throughout the table code.)
 __device__ __forceinline__ uint32_t alive_stamp(const AliveTable t, uint32_t pair, const ulonglong2 e, uint32_t hash, uint32_t low) {
     const bool hx = (uint32_t)(e.x >> 32) == hash, hy = (uint32_t)(e.y >> 32) == hash;
     const uint32_t seen = hx ? (uint32_t)e.x : (uint32_t)e.y;
@@ -574,11 +594,22 @@ __device__ __forceinline__ uint32_t alive_stamp(const AliveTable t, uint32_t pai
     if ((hx || hy) && seen + 1u > low) return seen;                 // a later record already spoke for this hash
     unsigned long long *slot = t.slots + 2 * (size_t)pair;
     const unsigned long long stamp = ((unsigned long long)hash << 32) | low;
-    if ((hx && e.x != ALIVE_EMPTY) || (!hx && hy && e.y != ALIVE_EMPTY)) {   // the hash is here with an older stamp
+    const bool ex = e.x == ALIVE_EMPTY, ey = e.y == ALIVE_EMPTY;
+    if ((hx && !ex) || (!hx && hy && !ey)) {                        // the hash is here with an older stamp: raise it
         alive_red_max(slot + (hx ? 0 : 1), stamp, t.pol);
         return low;
     }
-    return alive_stamp_slow(t, pair, hash, low);                    // claim a slot / probe on
+    if (ex || ey) {                                                 // first record of this hash: claim the free slot
+        unsigned long long *sl = slot + (ex ? 0 : 1);
+        const unsigned long long old = atomicCAS(sl, ALIVE_EMPTY, stamp);
+        if (old == ALIVE_EMPTY) return low;
+        if ((uint32_t)(old >> 32) == hash) {                        // a sibling claimed it in the meantime
+            if (old >= stamp) return (uint32_t)old;
+            alive_red_max(sl, stamp, t.pol);
+            return low;
+        }
+    }
+    return alive_stamp_slow(t, pair, hash, low);                    // displaced: probe on
 }
 
 // ---- seen cache: nsets = 2^ALIVE_CACHE_SET_BITS sets of two 16-bit ways: tag (9 bits) << 7 | wave (7 bits), 0 = empty ----
@@ -662,24 +693,25 @@ __device__ __noinline__ void wide_tile_hashes(const int32_t *key_len, int64_t n,
 // warp — there is no __syncthreads in the loop, so the load phase of one warp overlaps the hash phase of
 // the others.  Only the per-partition counters are shared (shared-memory reductions).
 // ------------------------------------------------------------------------------------------------
-template <int MODE, bool SMEM, bool CAPTURE>
+template <int MODE, bool SMEM, bool CAPTURE, bool SHARD = false>
 __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams prm) {
     constexpr bool HASH = MODE != MODE_COUNTERS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int P = prm.P;
+    // SHARD: a partition-sharded scan (SURVEY.md §8 e: gpu = partition mod G) carves counter columns only for the
+    // partitions it owns — a rank of BASELINE configs[3] holds 32 columns, not 256
+    const int P = SHARD ? prm.Pc : prm.P;
     // layout: counter rows (SMEM) | per warp: mbar[2] + 112 B scratch | keybuf[2]
     uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
     const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : CTA_SCRATCH;
-    volatile uint32_t *s_floor = reinterpret_cast<volatile uint32_t *>(smem_raw + cta_bytes - CTA_SCRATCH);
     const uint32_t KEYBUF = (uint32_t)prm.keybuf;
     const size_t warp_bytes = warp_smem_bytes(HASH, prm.keybuf);
     unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * warp_bytes;
     const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
-    const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P};
+    const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P, prm.P, SHARD ? prm.shard_world : 1, SHARD ? prm.shard_rank : 0};
     // MODE_EXACT: the alive table's lines are asked to stay in L2 (evict_last), the record stream to leave first
     constexpr bool HINTS = MODE == MODE_EXACT && KTA_L2_HINTS;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
@@ -689,9 +721,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     if (SMEM) {
         const int nw = P * SMEM_ROWS;
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
-    }
-    if (tid == 0) {
-        s_floor[0] = MODE == MODE_HLL ? ld_cg_u32(prm.hll_floor) : 0u;
     }
     if (HASH && lane == 0) {
         mbar_init(mbar, 1);
@@ -723,6 +752,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t bad = 0;
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
+    // MODE_HLL: the warp's copy of the sketch floor (a lower bound of every register: monotone, so a stale copy only
+    // filters less).  Re-read from its global word after the first tiles and then every 16th tile — one global word read by
+    // every warp for EVERY tile made a single L2 line the bottleneck of the whole kernel (measured: +0.46 ms).
+    uint32_t floor_reg = MODE == MODE_HLL ? ld_cg_u32(prm.hll_floor) : 0u;
     uint32_t nxt_info = 0;
 
     // MODE_EXACT walks the batch from its newest tile to its oldest (see alive_stamp); the other modes ascend
@@ -769,136 +802,148 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         bool inrange = true;
 #pragma unroll
         for (int k = 0; k < ROWS; k++) {
-            use[k] = valid[k] && (unsigned)p[k] < (unsigned)P;
-            inrange = inrange && (unsigned)p[k] < (unsigned)P;
+            bool ok = (unsigned)p[k] < (unsigned)prm.P;
+            if (SHARD) {
+                // partition → column: c = p / G, and the partition must be one of this shard's (p - c G == rank);
+                // others are left out like out-of-range ones.  From here on p[k] is the column.
+                const int c = (int)__umulhi((uint32_t)p[k], prm.shard_magic);
+                ok = ok && p[k] - c * prm.shard_world == prm.shard_rank;
+                p[k] = ok ? c : 0;
+            }
+            use[k] = valid[k] && ok;
+            inrange = inrange && ok;
         }
         const bool clean = FULL && __all_sync(full, inrange);   // warp-uniform: every record of the tile exists and counts
-        if (!count_it) {
-            // stamps-only re-run: the counters and extrema of this batch were taken by the first pass
-        } else if (clean) {
-            if (try_uni) {
-                // run-structured input (a Kafka fetch delivers long runs of one partition).
-                // A whole tile inside one run (3 of 4 tiles at run length 500): one vote, the lane's four lengths added up
-                // first, two warp reductions and two adds for the tile
-                const int p0t = __shfl_sync(full, p[0], 0);
-                uint32_t kv4 = 0, vv4 = 0, big = 0;
-                bool one = true;
+        uint32_t h[ROWS] = {0u, 0u, 0u, 0u};   // the reference hash of each of the lane's four keys (0 for null keys)
+        // The two halves of the per-record work are independent of each other: MODE_EXACT runs the hashes FIRST, sends the
+        // seen-cache probes off, and counts while they are in flight; the other modes count first (the key bytes arrive later).
+        auto count_records = [&]() {
+            if (!count_it) {
+                // stamps-only re-run: the counters and extrema of this batch were taken by the first pass
+            } else if (clean) {
+                if (try_uni) {
+                    // run-structured input (a Kafka fetch delivers long runs of one partition).
+                    // A whole tile inside one run (3 of 4 tiles at run length 500): one vote, the lane's four lengths added up
+                    // first, two warp reductions and two adds for the tile
+                    const int p0t = __shfl_sync(full, p[0], 0);
+                    uint32_t kv4 = 0, vv4 = 0, big = 0;
+                    bool one = true;
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    const uint32_t kv = (uint32_t)max(kl[k], 0), vv = (uint32_t)max(vl[k], 0);
-                    one = one && p[k] == p0t;
-                    kv4 += kv; vv4 += vv; big |= kv | vv;
-                }
-                if (__all_sync(full, one && big < (1u << 24))) {
-#pragma unroll
-                    for (int k = 0; k < ROWS; k++) C.buckets(p0t, kl[k], vl[k]);
-                    const uint32_t ks = __reduce_add_sync(full, kv4);   // 128 lengths < 2^24: no overflow
-                    const uint32_t vs = __reduce_add_sync(full, vv4);
-                    if (lane == 0) {
-                        C.sum_add(0, p0t, ks);
-                        C.sum_add(1, p0t, vs);
+                    for (int k = 0; k < ROWS; k++) {
+                        const uint32_t kv = (uint32_t)max(kl[k], 0), vv = (uint32_t)max(vl[k], 0);
+                        one = one && p[k] == p0t;
+                        kv4 += kv; vv4 += vv; big |= kv | vv;
                     }
-                } else {
-                // otherwise row by row: the byte sums of a row that lies inside one run are reduced in the warp (2 REDUX)
-                // and added once, instead of 32 same-address adds
-                bool any_uni = false;
+                    if (__all_sync(full, one && big < (1u << 24))) {
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    C.buckets(p[k], kl[k], vl[k]);
-                    const int p0 = __shfl_sync(full, p[k], 0);
-                    const unsigned m0 = __ballot_sync(full, p[k] == p0);
-                    const bool small_row = __all_sync(full, (kl[k] | vl[k]) < (1 << 26));
-                    const uint32_t kv = (uint32_t)max(kl[k], 0), vv = (uint32_t)max(vl[k], 0);
-                    if (m0 == full && small_row) {
-                        const uint32_t ks = __reduce_add_sync(full, kv);   // each < 2^26: no overflow
-                        const uint32_t vs = __reduce_add_sync(full, vv);
+                        for (int k = 0; k < ROWS; k++) C.buckets(p0t, kl[k], vl[k]);
+                        const uint32_t ks = __reduce_add_sync(full, kv4);   // 128 lengths < 2^24: no overflow
+                        const uint32_t vs = __reduce_add_sync(full, vv4);
                         if (lane == 0) {
-                            C.sum_add(0, p0, ks);
-                            C.sum_add(1, p0, vs);
+                            C.sum_add(0, p0t, ks);
+                            C.sum_add(1, p0t, vs);
                         }
-                        any_uni = true;
                     } else {
-                        // a row that straddles a run boundary holds two partitions: left to per-lane adds, its two
-                        // counters would be hit 32 times each, serialised in the shared-memory pipe (measured: +0.09 ms
-                        // at run length 500).  Reduce the two groups separately instead.
-                        const int l1 = __ffs(~m0) - 1;                     // first lane of the second group
-                        const int p1 = __shfl_sync(full, p[k], l1 & 31);
-                        const unsigned m1 = __ballot_sync(full, p[k] == p1);
-                        if (small_row && (m0 | m1) == full) {
-                            const bool in0 = (m0 >> lane) & 1u;
-                            const uint32_t ks0 = __reduce_add_sync(full, in0 ? kv : 0u), vs0 = __reduce_add_sync(full, in0 ? vv : 0u);
-                            const uint32_t ks1 = __reduce_add_sync(full, in0 ? 0u : kv), vs1 = __reduce_add_sync(full, in0 ? 0u : vv);
+                    // otherwise row by row: the byte sums of a row that lies inside one run are reduced in the warp (2 REDUX)
+                    // and added once, instead of 32 same-address adds
+                    bool any_uni = false;
+#pragma unroll
+                    for (int k = 0; k < ROWS; k++) {
+                        C.buckets(p[k], kl[k], vl[k]);
+                        const int p0 = __shfl_sync(full, p[k], 0);
+                        const unsigned m0 = __ballot_sync(full, p[k] == p0);
+                        const bool small_row = __all_sync(full, (kl[k] | vl[k]) < (1 << 26));
+                        const uint32_t kv = (uint32_t)max(kl[k], 0), vv = (uint32_t)max(vl[k], 0);
+                        if (m0 == full && small_row) {
+                            const uint32_t ks = __reduce_add_sync(full, kv);   // each < 2^26: no overflow
+                            const uint32_t vs = __reduce_add_sync(full, vv);
                             if (lane == 0) {
-                                C.sum_add(0, p0, ks0);
-                                C.sum_add(1, p0, vs0);
-                            } else if (lane == l1) {
-                                C.sum_add(0, p1, ks1);
-                                C.sum_add(1, p1, vs1);
+                                C.sum_add(0, p0, ks);
+                                C.sum_add(1, p0, vs);
                             }
                             any_uni = true;
                         } else {
-                            C.sums(p[k], kl[k], vl[k]);
+                            // a row that straddles a run boundary holds two partitions: left to per-lane adds, its two
+                            // counters would be hit 32 times each, serialised in the shared-memory pipe (measured: +0.09 ms
+                            // at run length 500).  Reduce the two groups separately instead.
+                            const int l1 = __ffs(~m0) - 1;                     // first lane of the second group
+                            const int p1 = __shfl_sync(full, p[k], l1 & 31);
+                            const unsigned m1 = __ballot_sync(full, p[k] == p1);
+                            if (small_row && (m0 | m1) == full) {
+                                const bool in0 = (m0 >> lane) & 1u;
+                                const uint32_t ks0 = __reduce_add_sync(full, in0 ? kv : 0u), vs0 = __reduce_add_sync(full, in0 ? vv : 0u);
+                                const uint32_t ks1 = __reduce_add_sync(full, in0 ? 0u : kv), vs1 = __reduce_add_sync(full, in0 ? 0u : vv);
+                                if (lane == 0) {
+                                    C.sum_add(0, p0, ks0);
+                                    C.sum_add(1, p0, vs0);
+                                } else if (lane == l1) {
+                                    C.sum_add(0, p1, ks1);
+                                    C.sum_add(1, p1, vs1);
+                                }
+                                any_uni = true;
+                            } else {
+                                C.sums(p[k], kl[k], vl[k]);
+                            }
                         }
                     }
-                }
-                try_uni = any_uni;
+                    try_uni = any_uni;
+                    }
+                } else {
+                    C.record_rows(p, kl, vl);
                 }
             } else {
-                C.record_rows(p, kl, vl);
-            }
-        } else {
-            // tail tile, or a record with a partition outside [0, P): per-record checks
+                // tail tile, or a record with a partition outside [0, P): per-record checks
 #pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                if (use[k]) C.record(p[k], kl[k], vl[k]);
-                else if (valid[k]) bad++;
-            }
-        }
-        // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back: the raw
-        // extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps).
-        // Timestamps of one topic share their high word for 49 days at a time: when the lane's four and its running
-        // extrema do, the signed 64-bit order is the unsigned order of the low words (2 + 2 three-input min/max).
-        bool ts_fast = false;
-        if (clean && count_it) {
-            const uint32_t hw = hi32(tmin);
-            uint32_t x = hi32(tmax) ^ hw;
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) x |= hi32(ts[k]) ^ hw;
-            ts_fast = x == 0;
-        }
-        if (ts_fast) {
-            const uint32_t hw = hi32(tmin);
-            const uint32_t l0 = (uint32_t)ts[0], l1 = (uint32_t)ts[1], l2 = (uint32_t)ts[2], l3 = (uint32_t)ts[3];
-            const uint32_t lo = min(min(min(l0, l1), l2), min(l3, (uint32_t)tmin));
-            const uint32_t hi = max(max(max(l0, l1), l2), max(l3, (uint32_t)tmax));
-            tmin = pack64(lo, hw);
-            tmax = pack64(hi, hw);
-        } else if (count_it) {
-            asm volatile("");   // keep this a real branch: if-converted, the 64-bit chain runs every tile
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                const bool u = clean || use[k];
-                const long long t0 = u ? ts[k] : INT64_MAX, t1 = u ? ts[k] : INT64_MIN;
-                tmin = t0 < tmin ? t0 : tmin;
-                tmax = t1 > tmax ? t1 : tmax;
-            }
-        }
-        if (count_it) {
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                // metric.rs:249-251: size extrema, not for tombstones (rows that do not exist carry vl = -1)
-                const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
-                if (vl[k] >= 0 && (clean || use[k])) {
-                    smin = min(smin, sz);
-                    smax = max(smax, sz);
+                for (int k = 0; k < ROWS; k++) {
+                    if (use[k]) C.record(p[k], kl[k], vl[k]);
+                    else if (valid[k]) bad++;
                 }
             }
-        }
+            // metric.rs:209,247: None → 0 and ms → s are monotone maps, applied once at read-back: the raw
+            // extrema determine the mapped extrema (raw == -1 ⇔ mapped 0, see kta_timestamps).
+            // Timestamps of one topic share their high word for 49 days at a time: when the lane's four and its running
+            // extrema do, the signed 64-bit order is the unsigned order of the low words (2 + 2 three-input min/max).
+            bool ts_fast = false;
+            if (clean && count_it) {
+                const uint32_t hw = hi32(tmin);
+                uint32_t x = hi32(tmax) ^ hw;
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) x |= hi32(ts[k]) ^ hw;
+                ts_fast = x == 0;
+            }
+            if (ts_fast) {
+                const uint32_t hw = hi32(tmin);
+                const uint32_t l0 = (uint32_t)ts[0], l1 = (uint32_t)ts[1], l2 = (uint32_t)ts[2], l3 = (uint32_t)ts[3];
+                const uint32_t lo = min(min(min(l0, l1), l2), min(l3, (uint32_t)tmin));
+                const uint32_t hi = max(max(max(l0, l1), l2), max(l3, (uint32_t)tmax));
+                tmin = pack64(lo, hw);
+                tmax = pack64(hi, hw);
+            } else if (count_it) {
+                asm volatile("");   // keep this a real branch: if-converted, the 64-bit chain runs every tile
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    const bool u = clean || use[k];
+                    const long long t0 = u ? ts[k] : INT64_MAX, t1 = u ? ts[k] : INT64_MIN;
+                    tmin = t0 < tmin ? t0 : tmin;
+                    tmax = t1 > tmax ? t1 : tmax;
+                }
+            }
+            if (count_it) {
+#pragma unroll
+                for (int k = 0; k < ROWS; k++) {
+                    // metric.rs:249-251: size extrema, not for tombstones (rows that do not exist carry vl = -1)
+                    const uint32_t sz = (uint32_t)max(kl[k], 0) + (uint32_t)vl[k];
+                    if (vl[k] >= 0 && (clean || use[k])) {
+                        smin = min(smin, sz);
+                        smax = max(smax, sz);
+                    }
+                }
+            }
 
-        if (HASH) {
+        };
+        auto hash_keys = [&]() {
             // ---- byte offset of each key inside the tile: exclusive scan of max(key_len, 0) ----
             uint32_t off[ROWS];
-            uint32_t h[ROWS];
             // do all keys of this tile that are not null have ONE length L?  L = the longest; read as unsigned, null (-1)
             // is the largest value, so the unsigned minimum is the shortest non-null key (or "null" if there is none):
             // one length ⇔ the two agree.  Two three-input min/max per lane and two warp reductions.
@@ -1006,103 +1051,102 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 for (int k = 0; k < ROWS; k++) h[k] = scratch[32 * k + lane];
             }
 
+
             // ---- LogCompactionInMemoryMetrics::handle_message, metric.rs:288-305 ----
             if (CAPTURE) {
 #pragma unroll
                 for (int k = 0; k < ROWS; k++)
                     if (valid[k]) prm.hash_out[rbase + 32 * k] = kl[k] >= 0 ? h[k] : 0u;
             }
-            if (MODE == MODE_EXACT) {
-                // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
-                // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
-                // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
-                // Step 1, per row: the seen cache (one L2 word per record).  A record superseded by a newer wave of its
-                // own hash is done.  The others are compacted into one dense queue in the warp's spent key stage.
-                uint2 *queue = reinterpret_cast<uint2 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (hash, low word) per entry
-                uint32_t *qwave = reinterpret_cast<uint32_t *>(queue + TILE);                  // its wave (12 B x 128 <= stage)
-                const bool cached = prm.alive_cache != nullptr;
-                uint32_t low[ROWS], cw[ROWS];
-                bool live[ROWS];
+        };
+        if (MODE != MODE_EXACT) count_records();
+        if (HASH) hash_keys();
+        if (MODE == MODE_EXACT) {
+            // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
+            // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
+            // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
+            // Step 1: the seen-cache probes (one L2 word per record) go out, and the records are COUNTED while they fly.
+            uint4 *queue = reinterpret_cast<uint4 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (x, low word, wave, set word) x 128 <= stage
+            const bool cached = prm.alive_cache != nullptr;
+            const uint32_t r32 = (uint32_t)rbase;   // index in the batch (< 2^31: host-checked)
+            uint32_t x[ROWS], low[ROWS], cw[ROWS];
+            bool live[ROWS];
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    live[k] = (clean || use[k]) && kl[k] >= 0;
-                    const int64_t r = rbase + 32 * k;
-                    uint32_t field;
-                    if (prm.seq) {
-                        // explicit global sequence numbers (partition-sharded scans): must fall into the table's window
-                        const uint64_t f = live[k] ? ld_stream_u64(prm.seq + r) - prm.alive_origin + 1ull : 1ull;
-                        if (f - 1ull >= (uint64_t)ALIVE_FIELD_MAX) {
-                            atomicAdd(prm.alive_status + 1, 1u);
-                            live[k] = false;
-                        }
-                        field = (uint32_t)f;
-                    } else {
-                        field = (uint32_t)prm.alive_fbase + (uint32_t)r;   // host-checked: seq_base + n fits the window
+            for (int k = 0; k < ROWS; k++) {
+                live[k] = (clean || use[k]) && kl[k] >= 0;
+                uint32_t field;
+                if (prm.seq) {
+                    // explicit global sequence numbers (partition-sharded scans): must fall into the table's window
+                    const uint64_t f = live[k] ? ld_stream_u64(prm.seq + rbase + 32 * k) - prm.alive_origin + 1ull : 1ull;
+                    if (f - 1ull >= (uint64_t)ALIVE_FIELD_MAX) {
+                        atomicAdd(prm.alive_status + 1, 1u);
+                        live[k] = false;
                     }
-                    low[k] = (field << 1) | (vl[k] >= 0 ? 1u : 0u);
-                    cw[k] = 0;
-                    if (cached && live[k])
-                        cw[k] = alive_cache_ld(prm.alive_cache + (hll_mix(h[k]) >> ALIVE_CACHE_TAG_BITS), AT.pol);
+                    field = (uint32_t)f;
+                } else {
+                    field = (uint32_t)prm.alive_fbase + r32 + 32u * k;   // host-checked: seq_base + n fits the window
                 }
-                uint32_t qn = 0;   // warp-uniform
-#pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    const uint32_t wv = 1u + (uint32_t)((rbase + 32 * k) >> prm.alive_wave_shift);
-                    const bool go = live[k] && !(cached && alive_cache_newer(cw[k], hll_mix(h[k]), wv));
-                    const unsigned m = __ballot_sync(full, go);
-                    if (go) {
-                        const uint32_t qi = qn + __popc(m & lt_mask);
-                        queue[qi] = make_uint2(h[k], low[k]);
-                        qwave[qi] = wv;
-                    }
-                    qn += __popc(m);
-                }
-                __syncwarp();
-                // Step 2, dense: the exact path through the table, then tell the cache what the table knows now
-                for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
-                    const bool on = q0 + lane < qn;
-                    const uint2 item = on ? queue[q0 + lane] : make_uint2(0u, 0u);
-                    const uint32_t x = hll_mix(item.x);
-                    const uint32_t pr = __umulhi(x, AT.npairs);
-                    if (on) {
-                        const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
-                        uint32_t *cset = cached ? prm.alive_cache + (x >> ALIVE_CACHE_TAG_BITS) : nullptr;
-                        const uint32_t c = cached ? alive_cache_ld(cset, AT.pol) : 0u;
-                        const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
-                        if (cached) {
-                            // what the table knows now, as a wave of THIS batch: the record's own wave, or — when the stamp
-                            // that beat it is from this batch and seq is implicit (field - fbase = batch index) — that
-                            // stamp's.  Stamps of earlier batches and rebased ones are older than every record here.
-                            uint32_t wv = qwave[q0 + lane];
-                            const uint32_t idx = (newest >> 1) - (uint32_t)prm.alive_fbase;
-                            if (!prm.seq && idx < (uint32_t)prm.n) wv = max(wv, 1u + (idx >> prm.alive_wave_shift));
-                            alive_cache_put(cset, c, x, wv, newest >> 1);
-                        }
-                    }
-                }
-                // the queue lives in a key stage that the TMA engine refills next iteration: order these generic-proxy
-                // accesses before that async-proxy write
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
+                low[k] = (field << 1) | (vl[k] >= 0 ? 1u : 0u);
+                x[k] = hll_mix(h[k]);
+                cw[k] = 0;
+                if (cached && live[k]) cw[k] = alive_cache_ld(prm.alive_cache + (x[k] >> ALIVE_CACHE_TAG_BITS), AT.pol);
             }
-#ifndef KTA_EXP_NO_HLL
-            if (MODE == MODE_HLL) {
-                // the floor comes from the CTA's shared-memory copy: one global word read by every warp for every tile
-                // would make a single L2 line the bottleneck of the whole kernel (measured: +0.46 ms)
-                const uint32_t skip_mask = hll_skip_mask(prm.hll_p, *s_floor);
+            count_records();
+#if KTA_EXP_ALIVE_STAGE >= 1
+            // A record superseded by a newer wave of its own hash is done.  The others are compacted across the tile into
+            // one dense queue in the warp's spent key stage.
+            __syncwarp();      // every lane is done reading its keys from this stage before any lane overwrites it
+            uint32_t qn = 0;   // warp-uniform
 #pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    // in-stream sketch: every record with a key and a value (invalid rows carry kl = vl = -1)
-                    const uint32_t x = hll_mix(h[k]);
-                    if (((x & skip_mask) | (uint32_t)((kl[k] | vl[k]) >> 31)) == 0 && (clean || use[k])) hll_raise(prm.hll, prm.hll_p, x);
-                }
+            for (int k = 0; k < ROWS; k++) {
+                const uint32_t wv = 1u + ((r32 + 32u * k) >> prm.alive_wave_shift);
+                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], wv));
+                const unsigned m = __ballot_sync(full, go);
+                if (go) queue[qn + __popc(m & lt_mask)] = make_uint4(x[k], low[k], wv, cw[k]);
+                qn += __popc(m);
             }
-#else
-            if (MODE == MODE_HLL) {   // experiment: keep the hashes alive without the sketch
-                if ((h[0] ^ h[1] ^ h[2] ^ h[3]) == 0x12345678u) prm.hll[0] = 1;
+            __syncwarp();
+#if KTA_EXP_ALIVE_STAGE >= 2
+            // Step 2, dense: the exact path through the table, then tell the cache what the table knows now
+            for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+                if (q0 + lane < qn) {
+                    const uint4 item = queue[q0 + lane];
+                    const uint32_t pr = alive_home(item.x, AT.npairs);
+                    const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
+                    const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
+                    if (cached) {
+                        // what the table knows now, as a wave of THIS batch: the record's own wave, or — when the stamp
+                        // that beat it is from this batch and seq is implicit (field - fbase = batch index) — that
+                        // stamp's.  Stamps of earlier batches and rebased ones are older than every record here.
+                        uint32_t wv = item.z;
+                        const uint32_t idx = (newest >> 1) - (uint32_t)prm.alive_fbase;
+                        if (!prm.seq && idx < (uint32_t)prm.n) wv = max(wv, 1u + (idx >> prm.alive_wave_shift));
+                        alive_cache_put(prm.alive_cache + (item.x >> ALIVE_CACHE_TAG_BITS), item.w, item.x, wv, newest >> 1);
+                    }
+                }
             }
 #endif
+            // the queue lives in a key stage that the TMA engine refills next iteration: order these generic-proxy
+            // accesses before that async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+#endif
         }
+#ifndef KTA_EXP_NO_HLL
+        if (MODE == MODE_HLL) {
+            const uint32_t skip_mask = hll_skip_mask(prm.hll_p, floor_reg);
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                // in-stream sketch: every record with a key and a value (invalid rows carry kl = vl = -1)
+                const uint32_t x = hll_mix(h[k]);
+                if (((x & skip_mask) | (uint32_t)((kl[k] | vl[k]) >> 31)) == 0 && (clean || use[k])) hll_raise(prm.hll, prm.hll_p, x);
+            }
+        }
+#else
+        if (MODE == MODE_HLL) {   // experiment: keep the hashes alive without the sketch
+            if ((h[0] ^ h[1] ^ h[2] ^ h[3]) == 0x12345678u) prm.hll[0] = 1;
+        }
+#endif
     };
 
     for (int it = 0; tile < ntiles; tile += gstride, ++it) {
@@ -1121,11 +1165,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         try_uni = try_uni || (it & 15) == 15;   // re-probe for run-structured input now and then
         // HLL floor upkeep: every 4th tile ONE warp of each CTA (the role rotates, so no warp falls behind)
         // refreshes one slice — the 148 CTAs cover all 64 slices about every two tile-times — and republishes
-        // the floor to its CTA through shared memory
-        // (plus two early refreshes after the first and second tile, so that a cold sketch stops taking every record)
-        if (MODE == MODE_HLL && (((it & 3) == 3 && ((it >> 2) & 31) == (warp & 31)) || (it < 2 && warp == it + 1))) {
-            hll_refresh_slice(prm.hll, prm.hll_p, prm.hll_floor, (blockIdx.x + (uint32_t)(it >> 2) * 37u) & (HLL_SLICES - 1), lane);
-            if (lane == 0) *s_floor = ld_cg_u32(prm.hll_floor);
+        // the floor (plus two early refreshes after the first and second tile, so that a cold sketch stops taking every
+        // record); every warp picks the published floor up after its first tiles and then every 16th
+        if (MODE == MODE_HLL) {
+            if (((it & 3) == 3 && ((it >> 2) & 31) == (warp & 31)) || (it < 2 && warp == it + 1))
+                hll_refresh_slice(prm.hll, prm.hll_p, prm.hll_floor, (blockIdx.x + (uint32_t)(it >> 2) * 37u) & (HLL_SLICES - 1), lane);
+            if (it < 4 || (it & 15) == 15) floor_reg = ld_cg_u32(prm.hll_floor);
         }
     }
 
@@ -1137,10 +1182,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         for (int i = tid; i < nh; i += blockDim.x) {
             const uint32_t v = scnt[i];
             if (v) {
-                const int row = i / P, pp = i - row * P;
+                const int row = i / P, pp = C.part(i - row * P);
                 if (row < NB) atomicAdd(&prm.sums[(size_t)pp * NB + row], (unsigned long long)v);
-                else if (row == NB) atomicAdd(&prm.sums[(size_t)P * (2 * NB + 2) + pp], (unsigned long long)v);
-                else atomicAdd(&prm.sums[(size_t)(P + pp) * NB + (row - ROW_V)], (unsigned long long)v);
+                else if (row == NB) atomicAdd(&prm.sums[(size_t)prm.P * (2 * NB + 2) + pp], (unsigned long long)v);
+                else atomicAdd(&prm.sums[(size_t)(prm.P + pp) * NB + (row - ROW_V)], (unsigned long long)v);
             }
         }
         if (warp == 0) C.fold_sums(lane, 1u);
@@ -1161,7 +1206,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     long long *red = reinterpret_cast<long long *>(wsm + 64);   // per-warp scratch (4 × i64)
     if (lane == 0) {
         red[0] = tmin; red[1] = tmax; red[2] = smin64; red[3] = smax64;
-        if (bad) atomicAdd(&prm.sums[sums_words(P) - 1], (unsigned long long)bad);
+        if (bad) atomicAdd(&prm.sums[sums_words(prm.P) - 1], (unsigned long long)bad);
     }
     __syncthreads();
     if (tid == 0) {
@@ -1245,7 +1290,7 @@ __global__ void __launch_bounds__(THREADS) alive_hll_kernel(const unsigned long 
     const size_t stride = (size_t)gridDim.x * THREADS;
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < nslots; i += stride) {
         const unsigned long long v = table[i];
-        if (v != ALIVE_EMPTY && (v & 1ull)) hll_raise(hll, hll_p, hll_mix((uint32_t)(v >> 32)));
+        if (v != ALIVE_EMPTY && (v & 1ull)) hll_raise(hll, hll_p, (uint32_t)(v >> 32));   // the table holds x = fmix32(hash)
     }
 }
 
@@ -1269,7 +1314,7 @@ __global__ void __launch_bounds__(THREADS) alive_export_kernel(const unsigned lo
             const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
             if (slot < cap) {
                 const unsigned long long field = (v >> 1) & 0x7fffffffull;
-                out_hash[slot] = (uint32_t)(v >> 32);
+                out_hash[slot] = hll_unmix((uint32_t)(v >> 32));   // back to the reference hash
                 out_stamp[slot] = ((origin + field) << 1) | (v & 1ull);   // seq + 1 = origin + field
             }
         }
@@ -1288,8 +1333,8 @@ __global__ void __launch_bounds__(THREADS) alive_import_kernel(const AliveTable 
             atomicAdd(t.status + 1, 1u);
             continue;
         }
-        const uint32_t h = hash[i];
-        alive_stamp_slow(tt, alive_home(h, t.npairs), h, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
+        const uint32_t x = hll_mix(hash[i]);
+        alive_stamp_slow(tt, alive_home(x, t.npairs), x, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
     }
 }
 

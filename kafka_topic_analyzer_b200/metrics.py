@@ -53,7 +53,8 @@ class KtaEngine:
 
     def __init__(self, num_partitions: int, count_alive_keys: bool = False, hll_precision: int = 0,
                  device: int = -1, ring_records: int = 0, ring_key_bytes: int = 0,
-                 now: Optional[tuple] = None, alive_table_kib: int = 0):
+                 now: Optional[tuple] = None, alive_table_kib: int = 0, shard: Optional[tuple] = None):
+        """shard = (rank, world): this engine scans only partitions p with p % world == rank (a partition-sharded job)."""
         cfg = Config()
         cfg.struct_size = C.sizeof(Config)
         cfg.device = device
@@ -63,6 +64,8 @@ class KtaEngine:
         cfg.alive_table_kib = alive_table_kib   # initial size of the alive-key table (0 = 128 MiB); it grows on demand
         cfg.ring_records = ring_records
         cfg.ring_key_bytes = ring_key_bytes
+        if shard is not None:
+            cfg.shard_rank, cfg.shard_world = shard
         if now is None:
             cfg.now_s, cfg.now_ns = N.INT64_MIN, 0
         else:

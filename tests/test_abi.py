@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import pytest
 
@@ -33,7 +34,7 @@ def test_binding_table_covers_header():
 def test_abi_version_and_structs():
     L = lib()
     assert L.kta_abi_version() == 2
-    assert C.sizeof(_native.Config) == 56 and C.sizeof(_native.Batch) == 88 and C.sizeof(_native.SynthSpec) == 56
+    assert C.sizeof(_native.Config) == 64 and C.sizeof(_native.Batch) == 88 and C.sizeof(_native.SynthSpec) == 56
 
 
 def test_header_is_plain_c():
@@ -122,3 +123,17 @@ def test_c_example_output(tmp_path):
         "partition 1: total 2 tombstones 0 key bytes 6 value bytes 90 dirty ratio 0.0000",
         "alive keys: 2",
     ]
+
+
+def test_reference_arm_never_maps_the_gpu_library():
+    """bench.py --impl reference is a CPU arm: its topic comes from the host-only generator (libkta_synth.so) and the
+    oracle; libkta_gpu.so must not even be loaded into that process."""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-sample', '50000'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "maps = open('/proc/self/maps').read();"
+            "assert 'libkta_synth.so' in maps and 'libkta_oracle.so' in maps, 'expected libraries missing';"
+            "assert 'libkta_gpu' not in maps, 'the reference arm mapped the GPU library'") % os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = __import__("json").loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["config"]["config"] == "C1" and d["config"]["records_per_gpu"] == 100_000_000

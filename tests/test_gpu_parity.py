@@ -694,3 +694,53 @@ def test_config3_rank_shape_256_partitions():
         assert np.array_equal(topic.partition[:m].cpu().numpy(), th.partition) and set(th.partition.tolist()) <= set(range(rank, P, world))
         o = oracle_for(th, track_stream=True, now=NOW)
         assert_parity(e, o, P, hll_regs=o.hll_stream_regs(14))
+
+
+@pytest.mark.parametrize("P,world,run_len", [(16, 4, 3), (256, 8, 1), (10, 3, 1)])
+def test_partition_sharded_engines_merge_to_the_whole_topic(P, world, run_len):
+    """SURVEY.md §8 e on one device: `world` engines, engine r scanning only the partitions p = r (mod world) with counter
+    columns carved for those alone (kta_config.shard_*); their exported merge buffers summed (what the ONE all-reduce does)
+    and imported give the whole topic's state, bit for bit the oracle's.  A record of a foreign partition is left out."""
+    import torch
+    n = P * run_len * max(1, 60_000 // (P * run_len))
+    spec = synth.make_spec(n, P, run_len=run_len, key_mode=1, distinct_keys=max(P, n // 10), tombstone_per_10k=2000,
+                           null_key_per_10k=300, ts_missing_per_10k=10)
+    whole = synth.fill_host(spec)
+    o = oracle_for(whole, track_stream=True, now=NOW)
+    engines = [KtaEngine(P, hll_precision=11, now=NOW, shard=(r, world)) for r in range(world)]
+    try:
+        words = engines[0].merge_words(world)
+        total = torch.zeros(words, dtype=torch.int64, device="cuda")
+        for r, e in enumerate(engines):
+            # shard r of the topic = the records whose partition is r mod world, in seq order
+            sel = (whole.partition % world) == r
+            kl0 = np.maximum(whole.key_len, 0).astype(np.int64)
+            koff = np.concatenate([[0], np.cumsum(kl0)])
+            idx = np.nonzero(sel)[0]
+            kb = np.concatenate([whole.key_bytes[koff[i]:koff[i + 1]] for i in idx] or [np.zeros(0, np.uint8)]).astype(np.uint8)
+            from kafka_topic_analyzer_b200.synth import HostTopic, tile_base_from_key_len
+            t = HostTopic(whole.partition[sel], whole.offset[sel], whole.ts_ms[sel], whole.key_len[sel], whole.value_len[sel],
+                          whole.seq[sel], kb, tile_base_from_key_len(whole.key_len[sel]))
+            scan_device(e, t)
+            # the shard alone: its own partitions as the oracle sees them, the others untouched
+            mm = e.message_metrics
+            for p in range(P):
+                assert mm.total(p) == (o.counter("total", p) if p % world == r else 0)
+            buf = torch.zeros(words, dtype=torch.int64, device="cuda")
+            e.merge_export(r, world, buf)
+            torch.cuda.synchronize()
+            total += buf
+        engines[0].merge_import(world, total)
+        engines[0].finalize()
+        assert_parity(engines[0], o, P, hll_regs=o.hll_stream_regs(11))
+        # a foreign partition's record on a sharded handle is left out and reported
+        e = engines[1 % world]
+        e.reset()
+        foreign = (1 % world + 1) % world if world > 1 else 0
+        e.push(foreign, 0, 1000, b"k", 5)
+        with pytest.raises(KtaError) as ei:
+            e.finalize()
+        assert ei.value.code == 4 and e.bad_partition_records() == 1 and e.message_metrics.overall_count() == 0
+    finally:
+        for e in engines:
+            e.close()

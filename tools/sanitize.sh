@@ -5,7 +5,7 @@ set -u
 tag=${1:-r02}; out=gpurun_out; mkdir -p $out
 export KTA_NO_BUILD=1
 for tool in memcheck racecheck synccheck initcheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 77 python tools/sanitize_driver.py \
+  timeout 900 compute-sanitizer --tool $tool --num-cuda-barriers 32768 --print-limit 20 --error-exitcode 77 python tools/sanitize_driver.py \
       > $out/${tag}_sanitizer_$tool.log 2>&1
   echo "$tool rc=$?" | tee -a $out/${tag}_sanitizer_summary.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard|Error" $out/${tag}_sanitizer_$tool.log | head -5 | tee -a $out/${tag}_sanitizer_summary.log
