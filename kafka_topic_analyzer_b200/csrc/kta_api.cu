@@ -168,12 +168,12 @@ static int set_device(const kta_handle *h) {
     return KTA_OK;
 }
 
-static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf) {
-    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf);
+static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf, bool exact) {
+    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf, exact);
 }
 
 // Launch shape for one scan: key-stage bytes from the batch's mean key length, then as many warps as fit.
-static void scan_shape(const kta_handle *h, bool hash, int64_t n, int64_t key_bytes, int &threads, int &keybuf, size_t &smem) {
+static void scan_shape(const kta_handle *h, bool hash, bool exact, int64_t n, int64_t key_bytes, int &threads, int &keybuf, size_t &smem) {
     keybuf = KEYBUF_MIN;
     if (hash && n > 0) {
         const int64_t per_tile = (key_bytes * TILE + n - 1) / n;           // mean key bytes per 128-record tile
@@ -188,13 +188,13 @@ static void scan_shape(const kta_handle *h, bool hash, int64_t n, int64_t key_by
     static const size_t l1_reserve = [] { const char *e = getenv("KTA_SCAN_L1_RESERVE"); return e ? (size_t)atoll(e) : (size_t)0; }();
     const size_t budget = h->smem_optin > l1_reserve ? h->smem_optin - l1_reserve : h->smem_optin;
     for (threads = MAX_THREADS;; threads -= 128) {
-        smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf);
+        smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf, exact);
         if (smem <= budget || threads <= 256) break;
     }
     if (smem > h->smem_optin) {   // still too big with 8 warps: fall back to the smallest stage (long keys go through global)
         keybuf = KEYBUF_MIN;
         for (threads = MAX_THREADS;; threads -= 128) {
-            smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf);
+            smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf, exact);
             if (smem <= h->smem_optin || threads <= 128) break;
         }
     }
@@ -301,6 +301,7 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     h->sm_count = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->need_hash = cfg->count_alive_keys == 1 || cfg->hll_precision != 0;
+    h->pc.hash = h->need_hash;   // kta_push reads it before its first (slow-path) call has bound the ring
     if (cfg->now_s == INT64_MIN) {
         const auto now = std::chrono::system_clock::now().time_since_epoch();
         const int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(now).count();
@@ -340,7 +341,7 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
     }
     h->columns = (P - h->shard_rank + h->shard_world - 1) / h->shard_world;   // partitions p < P with p % world == rank
     // counters in shared memory as long as at least 8 warps still fit beside them
-    h->smem_counters = smem_counter_bytes(h->columns) + 8 * warp_smem_bytes(true, KEYBUF_MIN) <= h->smem_optin;
+    h->smem_counters = smem_counter_bytes(h->columns) + 8 * warp_smem_bytes(true, KEYBUF_MIN, true) <= h->smem_optin;
     int rc;
     if ((rc = h->smem_counters ? prepare_all<true>(h) : prepare_all<false>(h))) return rc;
     if ((rc = state_reset_device(h))) return rc;
@@ -432,7 +433,7 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     const int variant = h->shard_world > 1 ? 5 + mode : mode + (capture ? 2 : 0);
     int threads = 0, keybuf = 0;
     size_t sm = 0;
-    scan_shape(h, mode != MODE_COUNTERS, prm.n, key_bytes, threads, keybuf, sm);
+    scan_shape(h, mode != MODE_COUNTERS, mode == MODE_EXACT, prm.n, key_bytes, threads, keybuf, sm);
     if (sm > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", sm);
     prm.keybuf = keybuf;
     const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
@@ -1334,7 +1335,11 @@ extern "C" int kta_fnv32_host(kta_handle *h, int64_t n, const int32_t *key_len, 
 // test hook: capture the per-record hash computed inside the fused scan (device buffer of n u32, or NULL)
 extern "C" int kta_set_hash_capture(kta_handle *h, uint32_t *dev_out) {
     if (!h) return fail(KTA_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = set_device(h))) return rc;
+    if ((rc = ring_flush(h))) return rc;   // records already landed were taken with the old setting
     h->d_hash_out = dev_out;
+    h->pc.hash = h->need_hash || h->d_hash_out;
     return KTA_OK;
 }
 

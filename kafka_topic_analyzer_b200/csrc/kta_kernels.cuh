@@ -33,7 +33,11 @@ constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
 // for long keys, trading warps per SM for stage bytes when shared memory runs out.  A stage has 32 bytes of slack for
 // the (harmless, <= 23 byte) over-read of the last words.
 constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_SLACK = 32;
-__host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf) { return hash ? 128 + 2 * (size_t)keybuf : 128; }
+// MODE_EXACT adds a 32-entry queue of 16-byte items (records on their way to the alive-key table, see scan_kernel)
+constexpr int ALIVE_QUEUE = 32;
+__host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf, bool exact = false) {
+    return hash ? 128 + 2 * (size_t)keybuf + (exact ? (size_t)ALIVE_QUEUE * 16 : 0) : 128;
+}
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int FOLD_TILES = 8;             // every warp checks the CTA's 16-bit-split sums after every 8th tile of its own
@@ -707,7 +711,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t *scnt = reinterpret_cast<uint32_t *>(smem_raw);
     const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : CTA_SCRATCH;
     const uint32_t KEYBUF = (uint32_t)prm.keybuf;
-    const size_t warp_bytes = warp_smem_bytes(HASH, prm.keybuf);
+    const size_t warp_bytes = warp_smem_bytes(HASH, prm.keybuf, MODE == MODE_EXACT);
     unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * warp_bytes;
     const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
@@ -751,6 +755,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
+    uint32_t q_pending = 0;   // MODE_EXACT: records of the previous tile waiting in the warp's queue for the table (warp-uniform)
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     // MODE_HLL: the warp's copy of the sketch floor (a lower bound of every register: monotone, so a stale copy only
     // filters less).  Re-read from its global word after the first tiles and then every 16th tile — one global word read by
@@ -1065,8 +1070,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
             // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
             // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
-            // Step 1: the seen-cache probes (one L2 word per record) go out, and the records are COUNTED while they fly.
-            uint4 *queue = reinterpret_cast<uint4 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (x, low word, wave, set word) x 128 <= stage
+            // What limits this mode is not DRAM but the L1 pipe — a divergent 32-lane global access costs it ~2 cycles per
+            // lane — and latency.  So: exactly one random access per record (the seen cache), everything else only for
+            // the ~12 % that survive it, and every wait is filled with work:
+            //   1. the seen-cache probes of this tile go out;
+            //   2. the survivors of the PREVIOUS tile (parked in the warp's queue, their table lines prefetched into L2 a
+            //      whole tile ago) load their home pairs;
+            //   3. this tile's records are counted (~250 instructions) while 1 and 2 are in flight;
+            //   4. the previous survivors are stamped (RED.MAX / CAS on an L2-resident line) and written back to the cache;
+            //   5. this tile's probes are read; survivors are compacted into the queue and their pairs prefetched.
+            uint4 *pq = reinterpret_cast<uint4 *>(wsm + 128 + 2 * (size_t)KEYBUF);   // (x, low word, wave, set word) x ALIVE_QUEUE
             const bool cached = prm.alive_cache != nullptr;
             const uint32_t r32 = (uint32_t)rbase;   // index in the batch (< 2^31: host-checked)
             uint32_t x[ROWS], low[ROWS], cw[ROWS];
@@ -1091,45 +1104,57 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 cw[k] = 0;
                 if (cached && live[k]) cw[k] = alive_cache_ld(prm.alive_cache + (x[k] >> ALIVE_CACHE_TAG_BITS), AT.pol);
             }
+            // the table pass of one queued record: stamp it, then tell the cache what the table knows now
+            auto finish = [&](const uint4 item, uint32_t pr, const ulonglong2 e) {
+                const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
+                if (cached) {
+                    // as a wave of THIS batch: the record's own wave, or — when the stamp that beat it is from this batch and
+                    // seq is implicit (field - fbase = batch index) — that stamp's.  Stamps of earlier batches and rebased
+                    // ones are older than every record here: they say nothing.
+                    uint32_t wv = item.z;
+                    const uint32_t idx = (newest >> 1) - (uint32_t)prm.alive_fbase;
+                    if (!prm.seq && idx < (uint32_t)prm.n) wv = max(wv, 1u + (idx >> prm.alive_wave_shift));
+                    alive_cache_put(prm.alive_cache + (item.x >> ALIVE_CACHE_TAG_BITS), item.w, item.x, wv, newest >> 1);
+                }
+            };
+            const bool pon = lane < q_pending;
+            uint4 pit = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t ppr = 0;
+            ulonglong2 pe = make_ulonglong2(0ull, 0ull);
+            if (pon) {
+                pit = pq[lane];
+                ppr = alive_home(pit.x, AT.npairs);
+                pe = alive_ld_pair(AT.slots + 2 * (size_t)ppr, AT.pol);
+            }
             count_records();
+#if KTA_EXP_ALIVE_STAGE >= 2
+            if (pon) finish(pit, ppr, pe);
+#endif
+            __syncwarp();      // every lane has taken its queued record before the queue is refilled
 #if KTA_EXP_ALIVE_STAGE >= 1
-            // A record superseded by a newer wave of its own hash is done.  The others are compacted across the tile into
-            // one dense queue in the warp's spent key stage.
-            __syncwarp();      // every lane is done reading its keys from this stage before any lane overwrites it
             uint32_t qn = 0;   // warp-uniform
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
                 const uint32_t wv = 1u + ((r32 + 32u * k) >> prm.alive_wave_shift);
                 const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], wv));
                 const unsigned m = __ballot_sync(full, go);
-                if (go) queue[qn + __popc(m & lt_mask)] = make_uint4(x[k], low[k], wv, cw[k]);
-                qn += __popc(m);
-            }
-            __syncwarp();
+                if (go) {
+                    const uint32_t qi = qn + __popc(m & lt_mask);
+                    const uint4 item = make_uint4(x[k], low[k], wv, cw[k]);
+                    const uint32_t pr = alive_home(x[k], AT.npairs);
+                    if (qi < (uint32_t)ALIVE_QUEUE) {
+                        pq[qi] = item;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(AT.slots + 2 * (size_t)pr));
+                    } else {
 #if KTA_EXP_ALIVE_STAGE >= 2
-            // Step 2, dense: the exact path through the table, then tell the cache what the table knows now
-            for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
-                if (q0 + lane < qn) {
-                    const uint4 item = queue[q0 + lane];
-                    const uint32_t pr = alive_home(item.x, AT.npairs);
-                    const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
-                    const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
-                    if (cached) {
-                        // what the table knows now, as a wave of THIS batch: the record's own wave, or — when the stamp
-                        // that beat it is from this batch and seq is implicit (field - fbase = batch index) — that
-                        // stamp's.  Stamps of earlier batches and rebased ones are older than every record here.
-                        uint32_t wv = item.z;
-                        const uint32_t idx = (newest >> 1) - (uint32_t)prm.alive_fbase;
-                        if (!prm.seq && idx < (uint32_t)prm.n) wv = max(wv, 1u + (idx >> prm.alive_wave_shift));
-                        alive_cache_put(prm.alive_cache + (item.x >> ALIVE_CACHE_TAG_BITS), item.w, item.x, wv, newest >> 1);
+                        finish(item, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol));   // queue full: take the table now
+#endif
                     }
                 }
+                qn += __popc(m);
             }
-#endif
-            // the queue lives in a key stage that the TMA engine refills next iteration: order these generic-proxy
-            // accesses before that async-proxy write
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
+            q_pending = min(qn, (uint32_t)ALIVE_QUEUE);
+            __syncwarp();      // the queue is complete before the next iteration reads it
 #endif
         }
 #ifndef KTA_EXP_NO_HLL
@@ -1172,6 +1197,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 hll_refresh_slice(prm.hll, prm.hll_p, prm.hll_floor, (blockIdx.x + (uint32_t)(it >> 2) * 37u) & (HLL_SLICES - 1), lane);
             if (it < 4 || (it & 15) == 15) floor_reg = ld_cg_u32(prm.hll_floor);
         }
+    }
+
+    if (MODE == MODE_EXACT && KTA_EXP_ALIVE_STAGE >= 2 && lane < q_pending) {
+        // the survivors of the warp's last tile
+        const uint4 item = reinterpret_cast<const uint4 *>(wsm + 128 + 2 * (size_t)KEYBUF)[lane];
+        const uint32_t pr = alive_home(item.x, AT.npairs);
+        const uint32_t newest = alive_stamp(AT, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol), item.x, item.y);
+        (void)newest;   // the batch is over: nothing left for the cache to filter
     }
 
     // ---- flush CTA-private state ----
