@@ -168,8 +168,16 @@ static int set_device(const kta_handle *h) {
     return KTA_OK;
 }
 
+// MODE_EXACT: how many of a CTA's warps do the alive-key work (the rest scan); KTA_EXACT_CONSUMERS is a tuning knob
+static int exact_consumers(int warps) {
+    static const int want = [] { const char *e = getenv("KTA_EXACT_CONSUMERS"); return e ? atoi(e) : 8; }();
+    return std::max(1, std::min(want, warps / 2));
+}
+
 static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf, bool exact) {
-    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf, exact);
+    const int warps = threads / 32, ncons = exact ? exact_consumers(warps) : 0;
+    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(warps - ncons) * warp_smem_bytes(hash, keybuf, exact) +
+           (size_t)ncons * CONSUMER_SMEM;
 }
 
 // Launch shape for one scan: key-stage bytes from the batch's mean key length, then as many warps as fit.
@@ -412,7 +420,7 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     prm.alive_count = h->d_scalar;
     prm.alive_status = h->d_alive_status;
     prm.alive_cache = nullptr;
-    if (exact && prm.n >= ALIVE_CACHE_MIN_RECORDS) {
+    if (exact && prm.n >= ALIVE_CACHE_MIN_RECORDS && !prm.seq) {   // (waves are batch positions: not known from an explicit seq)
         // the seen cache pays for its clearing (32 MiB, ~10 µs) on batches of a million records and more
         static const bool off = getenv("KTA_ALIVE_NO_CACHE") != nullptr;   // tuning / ablation knob
         if (!off) {
@@ -436,7 +444,9 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     scan_shape(h, mode != MODE_COUNTERS, mode == MODE_EXACT, prm.n, key_bytes, threads, keybuf, sm);
     if (sm > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", sm);
     prm.keybuf = keybuf;
-    const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
+    prm.consumers = mode == MODE_EXACT ? exact_consumers(threads / 32) : 0;
+    const int scanners = threads / 32 - prm.consumers;
+    const int grid = (int)std::min<int64_t>((prm.ntiles + scanners - 1) / scanners, h->sm_count);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         if (h->ev_used == h->ev_pool.size()) {

@@ -6,8 +6,7 @@ variants = {
  'nohints': ['KTA_L2_HINTS=0'],
  'stage0': ['KTA_EXP_ALIVE_STAGE=0'],
  'stage1': ['KTA_EXP_ALIVE_STAGE=1'],
- 't768': ['KTA_SCAN_THREADS=768'],
- 't512': ['KTA_SCAN_THREADS=512'],
+
 }
 for f in glob.glob(N.LIB_PATH.replace('.so','_exp_*.so')): os.remove(f)
 import concurrent.futures as cf
