@@ -61,7 +61,7 @@ extern "C" int kta_device_count(void) {
 // handle
 // ------------------------------------------------------------------------------------------------
 static constexpr int NCHUNK = 3;
-static constexpr int32_t ALIVE_DEFAULT_KIB = 128 * 1024;       // initial alive-key table: 128 MiB
+static constexpr int32_t ALIVE_DEFAULT_KIB = 128 * 1024;       // initial alive-key table: 128 MiB (KTA_ALIVE_TABLE_KIB overrides: tuning)
 static constexpr int32_t ALIVE_MAX_KIB = 32 * 1024 * 1024;     // 32 GiB = one slot per possible 32-bit hash
 static constexpr int64_t ALIVE_CACHE_MIN_RECORDS = 1 << 20;    // smaller batches go straight to the table
 static constexpr int64_t DEFAULT_RING_RECORDS = 1 << 22;  // 4 Mi records per chunk
@@ -168,16 +168,8 @@ static int set_device(const kta_handle *h) {
     return KTA_OK;
 }
 
-// MODE_EXACT: how many of a CTA's warps do the alive-key work (the rest scan); KTA_EXACT_CONSUMERS is a tuning knob
-static int exact_consumers(int warps) {
-    static const int want = [] { const char *e = getenv("KTA_EXACT_CONSUMERS"); return e ? atoi(e) : 8; }();
-    return std::max(1, std::min(want, warps / 2));
-}
-
 static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf, bool exact) {
-    const int warps = threads / 32, ncons = exact ? exact_consumers(warps) : 0;
-    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(warps - ncons) * warp_smem_bytes(hash, keybuf, exact) +
-           (size_t)ncons * CONSUMER_SMEM;
+    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf, exact);
 }
 
 // Launch shape for one scan: key-stage bytes from the batch's mean key length, then as many warps as fit.
@@ -333,7 +325,8 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
         // on demand (alive_check): 128 MiB = 2^24 slots holds the 1e7 keys of BASELINE configs[2] at load 0.6
         if (cfg->alive_table_kib < 0 || cfg->alive_table_kib > ALIVE_MAX_KIB)
             return fail(KTA_ERR_INVALID, "alive_table_kib %d out of range [0, %d]", cfg->alive_table_kib, ALIVE_MAX_KIB);
-        const int64_t kib = cfg->alive_table_kib ? cfg->alive_table_kib : ALIVE_DEFAULT_KIB;
+        static const int64_t env_kib = [] { const char *e = getenv("KTA_ALIVE_TABLE_KIB"); return e ? atoll(e) : 0ll; }();   // tuning knob
+        const int64_t kib = cfg->alive_table_kib ? cfg->alive_table_kib : env_kib > 0 ? env_kib : ALIVE_DEFAULT_KIB;
         h->alive_pairs = (uint32_t)std::max<int64_t>(kib * 64, 16);   // 16 bytes per pair
         CU(cudaMalloc(&h->d_alive_table, (size_t)h->alive_pairs * 16));
         CU(cudaMalloc(&h->d_alive_status, 8));
@@ -393,7 +386,7 @@ extern "C" int kta_set_stream(kta_handle *h, void *stream) {
 // scan launch
 // ------------------------------------------------------------------------------------------------
 // one launch of the fused scan; prm is complete apart from the state pointers filled in here
-static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes) {
+static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes, const uint64_t *seq_ends = nullptr) {
     const int P = h->cfg.num_partitions;
     const bool exact = h->cfg.count_alive_keys == 1;
     const bool capture = h->d_hash_out != nullptr && !prm.alive_only;
@@ -420,15 +413,33 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     prm.alive_count = h->d_scalar;
     prm.alive_status = h->d_alive_status;
     prm.alive_cache = nullptr;
-    if (exact && prm.n >= ALIVE_CACHE_MIN_RECORDS && !prm.seq) {   // (waves are batch positions: not known from an explicit seq)
-        // the seen cache pays for its clearing (32 MiB, ~10 µs) on batches of a million records and more
+    if (exact && prm.n >= ALIVE_CACHE_MIN_RECORDS) {
+        // the seen cache pays for its clearing (32 MiB, ~10 µs) on batches of a million records and more.
+        // Waves cut the batch's seq range [lo, hi] into <= 127 equal slices (any monotone function of seq will do).
         static const bool off = getenv("KTA_ALIVE_NO_CACHE") != nullptr;   // tuning / ablation knob
-        if (!off) {
+        uint64_t lo = prm.seq_base, hi = prm.seq_base + (uint64_t)prm.n - 1;
+        bool ok = !off;
+        if (ok && prm.seq) {
+            // explicit sequence numbers: the range is read off the column's ends (records of a batch are in seq order; a
+            // record outside the range just lands in the first or last wave)
+            uint64_t ends[2];
+            if (seq_ends) { ends[0] = seq_ends[0]; ends[1] = seq_ends[1]; }
+            else {
+                CU(cudaMemcpyAsync(&ends[0], prm.seq, 8, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaMemcpyAsync(&ends[1], prm.seq + (prm.n - 1), 8, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+            }
+            lo = std::min(ends[0], ends[1]);
+            hi = std::max(ends[0], ends[1]);
+            ok = lo >= h->alive_origin && hi - h->alive_origin < (uint64_t)ALIVE_FIELD_MAX;
+        }
+        if (ok) {
             CU(cudaMemsetAsync(h->d_alive_cache, 0, (size_t)4 << ALIVE_CACHE_SET_BITS, h->stream));
             prm.alive_cache = h->d_alive_cache;
             int sh = 0;
-            while (((prm.n - 1) >> sh) + 1 > (int64_t)ALIVE_CACHE_WAVES) sh++;
+            while (((hi - lo) >> sh) + 1 > (uint64_t)ALIVE_CACHE_WAVES) sh++;
             prm.alive_wave_shift = sh;
+            prm.alive_wave_base = (uint32_t)(lo - h->alive_origin + 1ull);   // the stamp field of seq lo
         }
     }
     prm.hash_out = capture ? h->d_hash_out : nullptr;
@@ -444,9 +455,7 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     scan_shape(h, mode != MODE_COUNTERS, mode == MODE_EXACT, prm.n, key_bytes, threads, keybuf, sm);
     if (sm > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", sm);
     prm.keybuf = keybuf;
-    prm.consumers = mode == MODE_EXACT ? exact_consumers(threads / 32) : 0;
-    const int scanners = threads / 32 - prm.consumers;
-    const int grid = (int)std::min<int64_t>((prm.ntiles + scanners - 1) / scanners, h->sm_count);
+    const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         if (h->ev_used == h->ev_pool.size()) {
@@ -535,7 +544,8 @@ static int alive_check(kta_handle *h) {
     return KTA_OK;
 }
 
-static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes, int chunk = -1) {
+static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int64_t key_bytes, int chunk = -1,
+                       const uint64_t *seq_ends = nullptr /* host copy of seq[0], seq[n-1] when the column came from the host */) {
     if (prm.n <= 0) return KTA_OK;
     int rc;
     if (h->cfg.count_alive_keys == 1) {
@@ -558,7 +568,7 @@ static int launch_scan(kta_handle *h, ScanParams prm, int64_t key_readable, int6
         prm.alive_fbase = prm.seq_base - h->alive_origin + 1ull;
         prm.alive_only = 0;
     }
-    if ((rc = launch_scan_raw(h, prm, key_readable, key_bytes))) return rc;
+    if ((rc = launch_scan_raw(h, prm, key_readable, key_bytes, seq_ends))) return rc;
     if (h->cfg.count_alive_keys == 1) h->pending.push_back(PendingScan{prm, key_readable, key_bytes, chunk});
     h->records += (uint64_t)prm.n;
     h->finalized = false;
@@ -1037,7 +1047,8 @@ extern "C" int kta_push_batch_host(kta_handle *h, const kta_batch *b) {
         prm.key_len = c.d_klen;
         prm.value_len = c.d_vlen;
         prm.seq = use_seq ? c.d_seq : nullptr;
-        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull), (int64_t)(k1 - k0), ci))) return rc;
+        const uint64_t seq_ends[2] = {use_seq ? b->seq[r0] : 0, use_seq ? b->seq[r0 + cn - 1] : 0};
+        if ((rc = launch_scan(h, prm, (int64_t)((k1 + 15) & ~15ull), (int64_t)(k1 - k0), ci, use_seq ? seq_ends : nullptr))) return rc;
         if (h->d_alive_table) CU(cudaMemcpyAsync(c.h_status, h->d_alive_status, 8, cudaMemcpyDeviceToHost, s));
         CU(cudaEventRecord(c.free_ev, s));
         h->cur = (h->cur + 1) % NCHUNK;

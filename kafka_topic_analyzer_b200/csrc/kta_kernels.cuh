@@ -33,16 +33,11 @@ constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
 // for long keys, trading warps per SM for stage bytes when shared memory runs out.  A stage has 32 bytes of slack for
 // the (harmless, <= 23 byte) over-read of the last words.
 constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_SLACK = 32;
-// MODE_EXACT splits the CTA's warps into PRODUCERS (everything the other modes do, plus the hash of every key) and
-// CONSUMERS (the alive-key work: seen cache, table).  A producer owns a ring of two 128-item buffers (8 bytes per record:
-// mixed hash, stamp low word) next to its key stages; a consumer owns a 32-entry queue of 16-byte items (records on their
-// way to the table).
-constexpr int ALIVE_QUEUE = 32;
-constexpr int RING_BYTES = TILE * 8;                       // one ring buffer
-constexpr uint32_t ITEM_SKIP = 0xffffffffu, ITEM_END = 0xfffffffeu;   // low words no stamp can have (see ALIVE_FIELD_MAX)
-constexpr int CONSUMER_SMEM = 128 + ALIVE_QUEUE * 16;
+// MODE_EXACT adds a queue of 16-byte items (records on their way to the alive-key table, see scan_kernel): it is drained
+// 32 at a time as soon as it holds 32, and a row of the tile adds at most 32
+constexpr int ALIVE_QUEUE = 64;
 __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf, bool exact = false) {
-    return hash ? 128 + 2 * (size_t)keybuf + (exact ? 2 * (size_t)RING_BYTES : 0) : 128;
+    return hash ? 128 + 2 * (size_t)keybuf + (exact ? (size_t)ALIVE_QUEUE * 16 : 0) : 128;
 }
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
@@ -93,11 +88,9 @@ struct ScanParams {
     uint64_t alive_origin;           // seq that field value 1 stands for (moved forward by a rebase)
     uint64_t alive_fbase;            // seq_base - alive_origin + 1: the field of record 0 when seq is implicit
     unsigned long long *alive_count; // scratch u64 words: [0] alive entries, [1] export cursor, [2] occupied slots (count kernels)
-    int32_t consumers;               // MODE_EXACT: warps of every CTA that do the alive-key work (the others scan)
-    int32_t pad2;
     uint32_t *alive_cache;           // [2^ALIVE_CACHE_SET_BITS] seen cache of this batch (cleared by the host before the launch), or NULL
-    int32_t alive_wave_shift;        // wave of the record at batch index r = 1 + (r >> alive_wave_shift)
-    int32_t pad1;
+    int32_t alive_wave_shift;        // wave of a record = 1 + min((field - alive_wave_base) >> alive_wave_shift, 126): a monotone
+    uint32_t alive_wave_base;        //   function of seq (field = seq - origin + 1); base = the field of the batch's first record
     uint32_t *alive_status;          // [0] stamps that found no slot (table too full: host grows it and re-runs the
                                      //     batch), [1] records whose seq lies outside the 31-bit window of the table
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
@@ -122,9 +115,6 @@ __device__ __forceinline__ void fence_mbar_init() {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -514,6 +504,9 @@ constexpr int ALIVE_MAX_PROBES = 96;                // pairs examined before a s
 #ifndef KTA_EXP_ALIVE_STAGE   // ablation knob: 0 = hashes only, 1 = + seen-cache probe and queue, 2 = everything (the product)
 #define KTA_EXP_ALIVE_STAGE 2
 #endif
+#ifndef KTA_EXP_ALIVE_PREFETCH   // prefetch a survivor's table line into L2 when it is queued
+#define KTA_EXP_ALIVE_PREFETCH 1
+#endif
 // L2 residency control for MODE_EXACT: the table should stay in L2, the record stream should leave it at once.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t pol;
@@ -694,6 +687,46 @@ __device__ __noinline__ void wide_tile_hashes(const int32_t *key_len, int64_t n,
     __syncwarp();
 }
 
+// wave of a stamp field (seq - origin + 1) within the batch being scanned: 0 = older than the batch, else 1..127, a monotone
+// function of seq
+struct AliveWaves {
+    uint32_t *cache;   // the seen cache, or NULL
+    uint32_t base;     // field of the batch's first record
+    int shift;
+};
+__device__ __forceinline__ uint32_t alive_wave(uint32_t field, const AliveWaves w) {
+    const uint32_t d = field - w.base;
+    return (int32_t)d < 0 ? 0u : 1u + min(d >> w.shift, ALIVE_CACHE_WAVES - 1u);
+}
+
+// One dense pass of (up to) 32 queued records through the alive-key table: the OLDEST min(count, 32) entries of the queue
+// (their table lines were prefetched longest ago).  Stamp each, then tell the seen cache what the table knows now; the
+// rest of the queue moves to the front.  Out of line: one copy of the table code per kernel.  Returns the entries left.
+__device__ __noinline__ uint32_t alive_drain(const AliveTable t, const AliveWaves w, uint4 *pq, uint32_t count, int lane) {
+    const uint32_t take = min(count, 32u);
+    uint4 moved = make_uint4(0u, 0u, 0u, 0u);
+    const bool move = 32u + (uint32_t)lane < count;
+    if (move) moved = pq[32 + lane];
+#if KTA_EXP_ALIVE_STAGE >= 2
+    if ((uint32_t)lane < take) {
+        const uint4 item = pq[lane];
+        const uint32_t pr = alive_home(item.x, t.npairs);
+        const ulonglong2 e = alive_ld_pair(t.slots + 2 * (size_t)pr, t.pol);
+        const uint32_t newest = alive_stamp(t, pr, e, item.x, item.y);
+        if (w.cache) {
+            // the newest stamp known for this hash as a wave of THIS batch (0 = it is older than the batch and says
+            // nothing), or the record's own wave
+            const uint32_t wv = max(item.z, alive_wave(newest >> 1, w));
+            alive_cache_put(w.cache + (item.x >> ALIVE_CACHE_TAG_BITS), item.w, item.x, wv, newest >> 1);
+        }
+    }
+#endif
+    __syncwarp();
+    if (move) pq[lane] = moved;
+    __syncwarp();
+    return count - take;
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused scan kernel.
 //   MODE_COUNTERS: counters + histograms + extrema only (20 B/record, no key bytes touched — the reference
@@ -723,36 +756,24 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     const size_t cta_bytes = SMEM ? smem_counter_bytes(P) : CTA_SCRATCH;
     const uint32_t KEYBUF = (uint32_t)prm.keybuf;
     const size_t warp_bytes = warp_smem_bytes(HASH, prm.keybuf, MODE == MODE_EXACT);
-    // MODE_EXACT: the last `consumers` warps of the CTA do the alive-key work for the others (see below)
-    const int ncons = MODE == MODE_EXACT ? prm.consumers : 0;
-    const int nprod = nwarps - ncons;
-    const bool consumer = MODE == MODE_EXACT && warp >= nprod;
-    auto warp_base = [&](int w) -> unsigned char * {
-        return smem_raw + cta_bytes + (w < nprod ? (size_t)w * warp_bytes : (size_t)nprod * warp_bytes + (size_t)(w - nprod) * CONSUMER_SMEM);
-    };
-    unsigned char *wsm = warp_base(warp);
-    // per-warp header: +0, +8 mbarriers of the two key stages | +16, +24 ring buffer "full" | +32, +40 ring buffer "empty" |
-    // +64 scratch for the final reduction
-    const uint32_t mbar = smem_u32(wsm);
+    unsigned char *wsm = smem_raw + cta_bytes + (size_t)warp * warp_bytes;
+    const uint32_t mbar = smem_u32(wsm);            // two 8-byte mbarriers at +0, +8
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
     const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P, prm.P, SHARD ? prm.shard_world : 1, SHARD ? prm.shard_rank : 0};
     // MODE_EXACT: the alive table's lines are asked to stay in L2 (evict_last), the record stream to leave first
     constexpr bool HINTS = MODE == MODE_EXACT && KTA_L2_HINTS;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
     const AliveTable AT{prm.alive_table, prm.alive_pairs, prm.alive_status, HINTS ? l2_policy_evict_last() : 0};
+    const AliveWaves AW{prm.alive_cache, prm.alive_wave_base, prm.alive_wave_shift};
     const bool count_it = !(MODE == MODE_EXACT && prm.alive_only);   // false: a stamps-only re-run after the table grew
 
     if (SMEM) {
         const int nw = P * SMEM_ROWS;
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
     }
-    if (HASH && lane == 0 && !consumer) {
+    if (HASH && lane == 0) {
         mbar_init(mbar, 1);
         mbar_init(mbar + 8, 1);
-        if (MODE == MODE_EXACT) {
-#pragma unroll
-            for (int i = 2; i < 6; i++) mbar_init(mbar + 8u * i, 1);
-        }
         fence_mbar_init();
     }
     __syncthreads();
@@ -779,7 +800,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
-    uint32_t ring_it = 0;     // MODE_EXACT producer: ring buffers filled so far
+    uint32_t q_pending = 0;   // MODE_EXACT: records waiting in the warp's queue for the alive-key table (warp-uniform)
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     // MODE_HLL: the warp's copy of the sketch floor (a lower bound of every register: monotone, so a stale copy only
     // filters less).  Re-read from its global word after the first tiles and then every 16th tile — one global word read by
@@ -792,8 +813,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     // 64-bit arithmetic and out of local memory
     const int ntiles = (int)prm.ntiles;
     auto phys = [&](int t) { return MODE == MODE_EXACT ? ntiles - 1 - t : t; };
-    const int gstride = (int)gridDim.x * nprod;
-    int tile = consumer ? ntiles : (int)blockIdx.x * nprod + warp;   // consumers take no tiles
+    const int gstride = (int)gridDim.x * nwarps;
+    int tile = (int)blockIdx.x * nwarps + warp;
     if (HASH && lane == 0 && tile < ntiles) nxt_info = issue(phys(tile), 0);
 
     // the body of one tile; FULL = every record of the tile exists (no tail predicates)
@@ -1091,36 +1112,60 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         if (MODE != MODE_EXACT) count_records();
         if (HASH) hash_keys();
         if (MODE == MODE_EXACT) {
-            // LogCompactionInMemoryMetrics::handle_message, producer half: every keyed record's (mixed hash, stamp low word)
-            // goes to this warp's ring for a consumer warp (alive_consume below); then the records are counted.
+            // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
+            // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
+            // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
+            // What limits this mode is the L1 pipe — a divergent 32-lane global access costs it ~2 cycles per lane — and
+            // latency, not DRAM.  So: exactly ONE random access per record (the seen cache, read while the records are
+            // counted), and the ~12 % that survive it wait in the warp's queue — their table lines prefetched into L2 —
+            // until 32 of them make a dense pass through the table worth its two round trips.
+            uint4 *pq = reinterpret_cast<uint4 *>(wsm + 128 + 2 * (size_t)KEYBUF);   // (x, low word, wave, set word) x ALIVE_QUEUE
+            const bool cached = AW.cache != nullptr;
             const uint32_t r32 = (uint32_t)rbase;   // index in the batch (< 2^31: host-checked)
-            uint2 item[ROWS];
+            uint32_t x[ROWS], low[ROWS], cw[ROWS];
+            bool live[ROWS];
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                bool live = (clean || use[k]) && kl[k] >= 0;
+                live[k] = (clean || use[k]) && kl[k] >= 0;
                 uint32_t field;
                 if (prm.seq) {
                     // explicit global sequence numbers (partition-sharded scans): must fall into the table's window
-                    const uint64_t f = live ? ld_stream_u64(prm.seq + rbase + 32 * k) - prm.alive_origin + 1ull : 1ull;
+                    const uint64_t f = live[k] ? ld_stream_u64(prm.seq + rbase + 32 * k) - prm.alive_origin + 1ull : 1ull;
                     if (f - 1ull >= (uint64_t)ALIVE_FIELD_MAX) {
                         atomicAdd(prm.alive_status + 1, 1u);
-                        live = false;
+                        live[k] = false;
                     }
                     field = (uint32_t)f;
                 } else {
                     field = (uint32_t)prm.alive_fbase + r32 + 32u * k;   // host-checked: seq_base + n fits the window
                 }
-                item[k] = make_uint2(hll_mix(h[k]), live ? (field << 1) | (vl[k] >= 0 ? 1u : 0u) : ITEM_SKIP);
+                low[k] = (field << 1) | (vl[k] >= 0 ? 1u : 0u);
+                x[k] = hll_mix(h[k]);
+                cw[k] = 0;
+                if (cached && live[k]) cw[k] = alive_cache_ld(AW.cache + (x[k] >> ALIVE_CACHE_TAG_BITS), AT.pol);
             }
-            const uint32_t rb = ring_it & 1u, use_no = ring_it >> 1;
-            if (use_no) mbar_wait(mbar + 32u + 8u * rb, (use_no - 1u) & 1u);   // the consumer has taken this buffer's last load
-            uint2 *ring = reinterpret_cast<uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF + (size_t)rb * RING_BYTES);
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) ring[32 * k + lane] = item[k];
+            count_records();   // ~250 instructions while the probes are in flight
+#if KTA_EXP_ALIVE_STAGE >= 1
             __syncwarp();
-            if (lane == 0) mbar_arrive(mbar + 16u + 8u * rb);
-            ring_it++;
-            count_records();
+#pragma unroll
+            for (int k = 0; k < ROWS; k++) {
+                const uint32_t wv = alive_wave(low[k] >> 1, AW);
+                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], wv));
+                const unsigned m = __ballot_sync(full, go);
+                if (go) {
+                    pq[q_pending + __popc(m & lt_mask)] = make_uint4(x[k], low[k], wv, cw[k]);
+#if KTA_EXP_ALIVE_PREFETCH
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(AT.slots + 2 * (size_t)alive_home(x[k], AT.npairs)));
+#endif
+                }
+                q_pending += __popc(m);
+                if (q_pending >= 32u) {
+                    __syncwarp();
+                    q_pending = alive_drain(AT, AW, pq, q_pending, lane);
+                }
+            }
+            __syncwarp();
+#endif
         }
 #ifndef KTA_EXP_NO_HLL
         if (MODE == MODE_HLL) {
@@ -1164,113 +1209,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         }
     }
 
-    if (MODE == MODE_EXACT && !consumer) {
-        // tell the consumer that this producer is done
-        const uint32_t rb = ring_it & 1u, use_no = ring_it >> 1;
-        if (use_no) mbar_wait(mbar + 32u + 8u * rb, (use_no - 1u) & 1u);
-        uint2 *ring = reinterpret_cast<uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF + (size_t)rb * RING_BYTES);
-        if (lane == 0) ring[0] = make_uint2(0u, ITEM_END);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(mbar + 16u + 8u * rb);
-    }
-    if (MODE == MODE_EXACT && consumer) {
-        // ---- LogCompactionInMemoryMetrics::handle_message, consumer half (metric.rs:288-305) ----
-        // Some(key) → insert (value) / remove (tombstone), last writer in seq order wins (:295, :298).
-        // What limits this work is not DRAM but the L1 pipe — a divergent 32-lane global access costs it ~2 cycles per
-        // lane — and latency.  So: exactly ONE random access per record (the seen cache), everything else only for the
-        // ~12 % that survive it; and the consumer warps do nothing else, so their waits cost no one anything:
-        //   1. the four seen-cache probes of each lane go out;
-        //   2. the survivors of the PREVIOUS buffer (parked in the warp's queue, their table lines prefetched into L2 a
-        //      whole buffer ago) load their home pairs, are stamped (RED.MAX / CAS) and written back to the cache;
-        //   3. this buffer's probes are read; survivors are compacted into the queue and their pairs prefetched.
-        const int cidx = warp - nprod;
-        uint4 *pq = reinterpret_cast<uint4 *>(wsm + 128);   // (x, low word, wave, set word) x ALIVE_QUEUE
-        const bool cached = prm.alive_cache != nullptr;
-        uint32_t q_pending = 0;
-        auto finish = [&](const uint4 it4, uint32_t pr, const ulonglong2 e) {
-#if KTA_EXP_ALIVE_STAGE < 2
-            return;
-#endif
-            const uint32_t newest = alive_stamp(AT, pr, e, it4.x, it4.y);
-            if (cached) {
-                // what the table knows now, as a wave of THIS batch: the record's own wave, or that of the stamp that beat
-                // it when that one is from this batch (field - fbase = batch index).  Stamps of earlier batches and
-                // rebased ones are older than every record here: they say nothing.
-                const uint32_t idx = (newest >> 1) - (uint32_t)prm.alive_fbase;
-                uint32_t wv = it4.z;
-                if (idx < (uint32_t)prm.n) wv = max(wv, 1u + (idx >> prm.alive_wave_shift));
-                alive_cache_put(prm.alive_cache + (it4.x >> ALIVE_CACHE_TAG_BITS), it4.w, it4.x, wv, newest >> 1);
-            }
-        };
-        auto drain = [&]() {
-            if (lane < q_pending) {
-                const uint4 it4 = pq[lane];
-                const uint32_t pr = alive_home(it4.x, AT.npairs);
-                finish(it4, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol));
-            }
-            __syncwarp();
-            q_pending = 0;
-        };
-        uint32_t done = 0;   // bit j: my j-th producer has sent its end marker
-        int mine = 0;
-        for (int pw = cidx; pw < nprod; pw += ncons) mine++;
-        for (uint32_t round = 0; done != (1u << mine) - 1u; round++) {
-            const uint32_t rb = round & 1u, par = (round >> 1) & 1u;
-            for (int j = 0; j < mine; j++) {
-                if ((done >> j) & 1u) continue;
-                unsigned char *pbase = warp_base(cidx + j * ncons);
-                const uint32_t pbar = smem_u32(pbase);
-                mbar_wait(pbar + 16u + 8u * rb, par);
-                const uint2 *ring = reinterpret_cast<const uint2 *>(pbase + 128 + 2 * (size_t)KEYBUF + (size_t)rb * RING_BYTES);
-                if (ring[0].y == ITEM_END) {   // uniform: every lane reads the same word
-                    done |= 1u << j;
-                    continue;
-                }
-                uint2 item[ROWS];
-#pragma unroll
-                for (int k = 0; k < ROWS; k++) item[k] = ring[32 * k + lane];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(pbar + 32u + 8u * rb);   // the producer may refill the buffer
-#if KTA_EXP_ALIVE_STAGE == 0
-                continue;
-#endif
-                // 1. probes
-                uint32_t cw[ROWS];
-#pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    cw[k] = 0;
-                    if (cached && item[k].y != ITEM_SKIP)
-                        cw[k] = alive_cache_ld(prm.alive_cache + (item[k].x >> ALIVE_CACHE_TAG_BITS), AT.pol);
-                }
-                // 2. the previous buffer's survivors
-                drain();
-                // 3. this buffer's survivors
-                uint32_t qn = 0;   // warp-uniform
-#pragma unroll
-                for (int k = 0; k < ROWS; k++) {
-                    // the wave of a record = its index in the batch >> shift; with an explicit seq column the index is not
-                    // known here and the cache is off (host)
-                    const uint32_t wv = 1u + (((item[k].y >> 1) - (uint32_t)prm.alive_fbase) >> prm.alive_wave_shift);
-                    const bool go = item[k].y != ITEM_SKIP && !(cached && alive_cache_newer(cw[k], item[k].x, wv));
-                    const unsigned m = __ballot_sync(full, go);
-                    if (go) {
-                        const uint32_t qi = qn + __popc(m & lt_mask);
-                        const uint4 it4 = make_uint4(item[k].x, item[k].y, wv, cw[k]);
-                        const uint32_t pr = alive_home(item[k].x, AT.npairs);
-                        if (qi < (uint32_t)ALIVE_QUEUE) {
-                            pq[qi] = it4;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(AT.slots + 2 * (size_t)pr));
-                        } else {
-                            finish(it4, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol));   // queue full: take the table now
-                        }
-                    }
-                    qn += __popc(m);
-                }
-                q_pending = min(qn, (uint32_t)ALIVE_QUEUE);
-                __syncwarp();
-            }
-        }
-        drain();
+    if (MODE == MODE_EXACT) {
+        uint4 *pq = reinterpret_cast<uint4 *>(wsm + 128 + 2 * (size_t)KEYBUF);
+        while (q_pending) q_pending = alive_drain(AT, AW, pq, q_pending, lane);   // the warp's last survivors
     }
 
     // ---- flush CTA-private state ----
@@ -1310,7 +1251,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     __syncthreads();
     if (tid == 0) {
         for (int w = 1; w < nwarps; w++) {
-            const long long *rw = reinterpret_cast<const long long *>(warp_base(w) + 64);
+            const long long *rw = reinterpret_cast<const long long *>(wsm + (size_t)w * warp_bytes + 64);
             tmin = rw[0] < tmin ? rw[0] : tmin;
             tmax = rw[1] > tmax ? rw[1] : tmax;
             smin64 = rw[2] < smin64 ? rw[2] : smin64;

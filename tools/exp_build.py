@@ -6,6 +6,8 @@ variants = {
  'nohints': ['KTA_L2_HINTS=0'],
  'stage0': ['KTA_EXP_ALIVE_STAGE=0'],
  'stage1': ['KTA_EXP_ALIVE_STAGE=1'],
+ 'noprefetch': ['KTA_EXP_ALIVE_PREFETCH=0'],
+ 't768': ['KTA_SCAN_THREADS=768'],
 
 }
 for f in glob.glob(N.LIB_PATH.replace('.so','_exp_*.so')): os.remove(f)
