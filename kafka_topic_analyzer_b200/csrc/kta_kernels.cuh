@@ -33,11 +33,11 @@ constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
 // for long keys, trading warps per SM for stage bytes when shared memory runs out.  A stage has 32 bytes of slack for
 // the (harmless, <= 23 byte) over-read of the last words.
 constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_SLACK = 32;
-// MODE_EXACT adds a queue of 16-byte items (records on their way to the alive-key table, see scan_kernel): it is drained
-// 32 at a time as soon as it holds 32, and a row of the tile adds at most 32
-constexpr int ALIVE_QUEUE = 64;
+// MODE_EXACT adds a queue of 8-byte items (mixed hash, stamp low word: records on their way to the alive-key table, see
+// scan_kernel): it is drained 32 at a time once it holds 32, and a tile adds at most 128
+constexpr int ALIVE_QUEUE = 32 + TILE;
 __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf, bool exact = false) {
-    return hash ? 128 + 2 * (size_t)keybuf + (exact ? (size_t)ALIVE_QUEUE * 16 : 0) : 128;
+    return hash ? 128 + 2 * (size_t)keybuf + (exact ? (size_t)ALIVE_QUEUE * 8 : 0) : 128;
 }
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
@@ -641,16 +641,12 @@ __device__ __forceinline__ bool alive_cache_newer(uint32_t c, uint32_t x, uint32
     const uint32_t lo = (tag << ALIVE_CACHE_WAVE_BITS) | wv;
     return (w0 - lo - 1u < ALIVE_CACHE_WAVES - wv) || (w1 - lo - 1u < ALIVE_CACHE_WAVES - wv);
 }
-// record the fact "hash x has a record of wave wv" (wv >= 1) in its set; c = the set word as last read
-__device__ __forceinline__ void alive_cache_put(uint32_t *set, uint32_t c, uint32_t x, uint32_t wv, uint32_t pick) {
+// record the fact "hash x has a record of wave wv" (wv >= 1).  The way is chosen by a bit of the hash (a key always lives in
+// the same way: nothing to read before the write; lookups still look at both halves of the word at once).
+__device__ __forceinline__ void alive_cache_put(uint32_t *cache, uint32_t x, uint32_t wv) {
     const uint32_t tag = x & ((1u << ALIVE_CACHE_TAG_BITS) - 1u);
-    const uint32_t mine = (tag << ALIVE_CACHE_WAVE_BITS) | wv;
-    const uint32_t w0 = c & 0xffffu, w1 = c >> 16;
-    int way;
-    if ((w0 >> ALIVE_CACHE_WAVE_BITS) == tag && w0) way = w0 >= mine ? -1 : 0;          // already known at least as new
-    else if ((w1 >> ALIVE_CACHE_WAVE_BITS) == tag && w1) way = w1 >= mine ? -1 : 1;
-    else way = w0 == 0 ? 0 : w1 == 0 ? 1 : (int)(pick & 1u);
-    if (way >= 0) reinterpret_cast<unsigned short *>(set)[way] = (unsigned short)mine;   // little-endian: way 0 = low half
+    unsigned short *set = reinterpret_cast<unsigned short *>(cache + (x >> ALIVE_CACHE_TAG_BITS));
+    set[(x >> (ALIVE_CACHE_TAG_BITS - 1)) & 1u] = (unsigned short)((tag << ALIVE_CACHE_WAVE_BITS) | wv);   // top tag bit picks the way
 }
 
 // plain insert of an entry whose hash is known to be absent (rehash into a fresh table)
@@ -697,34 +693,6 @@ struct AliveWaves {
 __device__ __forceinline__ uint32_t alive_wave(uint32_t field, const AliveWaves w) {
     const uint32_t d = field - w.base;
     return (int32_t)d < 0 ? 0u : 1u + min(d >> w.shift, ALIVE_CACHE_WAVES - 1u);
-}
-
-// One dense pass of (up to) 32 queued records through the alive-key table: the OLDEST min(count, 32) entries of the queue
-// (their table lines were prefetched longest ago).  Stamp each, then tell the seen cache what the table knows now; the
-// rest of the queue moves to the front.  Out of line: one copy of the table code per kernel.  Returns the entries left.
-__device__ __noinline__ uint32_t alive_drain(const AliveTable t, const AliveWaves w, uint4 *pq, uint32_t count, int lane) {
-    const uint32_t take = min(count, 32u);
-    uint4 moved = make_uint4(0u, 0u, 0u, 0u);
-    const bool move = 32u + (uint32_t)lane < count;
-    if (move) moved = pq[32 + lane];
-#if KTA_EXP_ALIVE_STAGE >= 2
-    if ((uint32_t)lane < take) {
-        const uint4 item = pq[lane];
-        const uint32_t pr = alive_home(item.x, t.npairs);
-        const ulonglong2 e = alive_ld_pair(t.slots + 2 * (size_t)pr, t.pol);
-        const uint32_t newest = alive_stamp(t, pr, e, item.x, item.y);
-        if (w.cache) {
-            // the newest stamp known for this hash as a wave of THIS batch (0 = it is older than the batch and says
-            // nothing), or the record's own wave
-            const uint32_t wv = max(item.z, alive_wave(newest >> 1, w));
-            alive_cache_put(w.cache + (item.x >> ALIVE_CACHE_TAG_BITS), item.w, item.x, wv, newest >> 1);
-        }
-    }
-#endif
-    __syncwarp();
-    if (move) pq[lane] = moved;
-    __syncwarp();
-    return count - take;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1119,7 +1087,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // latency, not DRAM.  So: exactly ONE random access per record (the seen cache, read while the records are
             // counted), and the ~12 % that survive it wait in the warp's queue — their table lines prefetched into L2 —
             // until 32 of them make a dense pass through the table worth its two round trips.
-            uint4 *pq = reinterpret_cast<uint4 *>(wsm + 128 + 2 * (size_t)KEYBUF);   // (x, low word, wave, set word) x ALIVE_QUEUE
+            uint2 *pq = reinterpret_cast<uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF);   // (x, low word) x ALIVE_QUEUE
             const bool cached = AW.cache != nullptr;
             const uint32_t r32 = (uint32_t)rbase;   // index in the batch (< 2^31: host-checked)
             uint32_t x[ROWS], low[ROWS], cw[ROWS];
@@ -1149,22 +1117,37 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                const uint32_t wv = alive_wave(low[k] >> 1, AW);
-                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], wv));
+                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], alive_wave(low[k] >> 1, AW)));
                 const unsigned m = __ballot_sync(full, go);
                 if (go) {
-                    pq[q_pending + __popc(m & lt_mask)] = make_uint4(x[k], low[k], wv, cw[k]);
+                    pq[q_pending + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
 #if KTA_EXP_ALIVE_PREFETCH
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(AT.slots + 2 * (size_t)alive_home(x[k], AT.npairs)));
 #endif
                 }
                 q_pending += __popc(m);
-                if (q_pending >= 32u) {
-                    __syncwarp();
-                    q_pending = alive_drain(AT, AW, pq, q_pending, lane);
-                }
             }
             __syncwarp();
+            // a dense pass of the 32 OLDEST queued records through the table (their lines were prefetched a tile or two
+            // ago): stamp, tell the seen cache what the table knows now, move the rest of the queue to the front
+            while (q_pending >= 32u) {
+                const uint2 moved = pq[32u + lane < q_pending ? 32 + lane : lane];
+#if KTA_EXP_ALIVE_STAGE >= 2
+                {
+                    const uint2 item = pq[lane];
+                    const uint32_t pr = alive_home(item.x, AT.npairs);
+                    const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
+                    const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
+                    // the newest stamp known for this hash as a wave of THIS batch (0 = it is older than the batch and says
+                    // nothing), or the record's own wave
+                    if (cached) alive_cache_put(AW.cache, item.x, max(alive_wave(item.y >> 1, AW), alive_wave(newest >> 1, AW)));
+                }
+#endif
+                __syncwarp();
+                if (32u + lane < q_pending) pq[lane] = moved;
+                __syncwarp();
+                q_pending -= 32u;
+            }
 #endif
         }
 #ifndef KTA_EXP_NO_HLL
@@ -1209,9 +1192,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         }
     }
 
-    if (MODE == MODE_EXACT) {
-        uint4 *pq = reinterpret_cast<uint4 *>(wsm + 128 + 2 * (size_t)KEYBUF);
-        while (q_pending) q_pending = alive_drain(AT, AW, pq, q_pending, lane);   // the warp's last survivors
+    if (MODE == MODE_EXACT && KTA_EXP_ALIVE_STAGE >= 2 && (uint32_t)lane < q_pending) {
+        // the warp's last survivors (fewer than 32; the batch is over: nothing left for the cache to filter)
+        const uint2 item = reinterpret_cast<const uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF)[lane];
+        const uint32_t pr = alive_home(item.x, AT.npairs);
+        alive_stamp(AT, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol), item.x, item.y);
     }
 
     // ---- flush CTA-private state ----
