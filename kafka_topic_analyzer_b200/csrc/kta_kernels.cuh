@@ -1131,7 +1131,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // a dense pass of the 32 OLDEST queued records through the table (their lines were prefetched a tile or two
             // ago): stamp, tell the seen cache what the table knows now, move the rest of the queue to the front
             while (q_pending >= 32u) {
-                const uint2 moved = pq[32u + lane < q_pending ? 32 + lane : lane];
 #if KTA_EXP_ALIVE_STAGE >= 2
                 {
                     const uint2 item = pq[lane];
@@ -1144,8 +1143,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
                 }
 #endif
                 __syncwarp();
-                if (32u + lane < q_pending) pq[lane] = moved;
-                __syncwarp();
+                for (uint32_t from = 32u; from < q_pending; from += 32u) {   // the rest moves up by 32, oldest first
+                    const uint2 v = pq[min(from + lane, (uint32_t)ALIVE_QUEUE - 1u)];
+                    __syncwarp();
+                    if (from + lane < q_pending) pq[from - 32u + lane] = v;
+                    __syncwarp();
+                }
                 q_pending -= 32u;
             }
 #endif

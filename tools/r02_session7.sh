@@ -3,7 +3,7 @@
 set -u
 out=gpurun_out; mkdir -p $out
 export KTA_NO_BUILD=1
-timeout 180 python tools/sanitize_driver.py exact ragged ring log 2>&1 | tail -5 | tee $out/r02s7_quick.log
+timeout 180 python tools/sanitize_driver.py exact ragged ring log 2>&1 | tail -30 | tee $out/r02s7_quick.log
 rc=${PIPESTATUS[0]}; if [ $rc -ne 0 ]; then echo "quick check failed rc=$rc: stopping" | tee -a $out/r02s7_quick.log; exit 1; fi
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee $out/r02s7_tests.log
 run() { timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e --no-extra --no-verify "$@" 2>$out/r02s7_last.err | python -c "
