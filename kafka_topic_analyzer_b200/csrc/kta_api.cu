@@ -177,7 +177,7 @@ static void scan_shape(const kta_handle *h, bool hash, bool exact, int64_t n, in
     keybuf = KEYBUF_MIN;
     if (hash && n > 0) {
         const int64_t per_tile = (key_bytes * TILE + n - 1) / n;           // mean key bytes per 128-record tile
-        int64_t want = per_tile + per_tile / 4 + 64 + KEYBUF_SLACK;       // 25 % headroom for ragged tiles
+        int64_t want = per_tile + per_tile / 8 + 64 + KEYBUF_SLACK;       // 12.5 % headroom for ragged tiles (~2.4 sigma for 0..40 B keys)
         want = (want + 127) / 128 * 128;
         keybuf = (int)std::min<int64_t>(std::max<int64_t>(want, KEYBUF_MIN), KEYBUF_MAX);
         keybuf = (keybuf + 15) / 16 * 16;

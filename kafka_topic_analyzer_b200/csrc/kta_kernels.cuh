@@ -34,8 +34,10 @@ constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
 // the (harmless, <= 23 byte) over-read of the last words.
 constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_SLACK = 32;
 // MODE_EXACT adds a queue of 8-byte items (mixed hash, stamp low word: records on their way to the alive-key table, see
-// scan_kernel): it is drained 32 at a time once it holds 32, and a tile adds at most 128
-constexpr int ALIVE_QUEUE = 32 + TILE;
+// scan_kernel): it is drained 128 at a time (four per lane, all four table lines in flight at once) as soon as it holds
+// 128, and a row of the tile adds at most 32
+constexpr int ALIVE_DRAIN = 128;
+constexpr int ALIVE_QUEUE = ALIVE_DRAIN + 32;
 __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf, bool exact = false) {
     return hash ? 128 + 2 * (size_t)keybuf + (exact ? (size_t)ALIVE_QUEUE * 8 : 0) : 128;
 }
@@ -1119,38 +1121,41 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             for (int k = 0; k < ROWS; k++) {
                 const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], alive_wave(low[k] >> 1, AW)));
                 const unsigned m = __ballot_sync(full, go);
-                if (go) {
-                    pq[q_pending + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
-#if KTA_EXP_ALIVE_PREFETCH
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(AT.slots + 2 * (size_t)alive_home(x[k], AT.npairs)));
-#endif
-                }
+                if (go) pq[q_pending + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
                 q_pending += __popc(m);
+                if (q_pending >= (uint32_t)ALIVE_DRAIN) {
+                    // A dense pass of the 128 oldest queued records through the table, four per lane: the four home pairs
+                    // are loaded together (these are DRAM misses: the table does not fit L2), then each record is stamped
+                    // and the seen cache is told what the table knows now.  Amortised over the ~9 tiles it takes 12 %
+                    // survivors to fill the queue, the two or three round trips of a table access cost little.
+                    __syncwarp();
+#if KTA_EXP_ALIVE_STAGE >= 2
+                    uint2 it[4];
+                    uint32_t pr[4];
+                    ulonglong2 e[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        it[j] = pq[32 * j + lane];
+                        pr[j] = alive_home(it[j].x, AT.npairs);
+                        e[j] = alive_ld_pair(AT.slots + 2 * (size_t)pr[j], AT.pol);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t newest = alive_stamp(AT, pr[j], e[j], it[j].x, it[j].y);
+                        // the newest stamp known for this hash as a wave of THIS batch (0 = older than the batch: says
+                        // nothing), or the record's own wave
+                        if (cached) alive_cache_put(AW.cache, it[j].x, max(alive_wave(it[j].y >> 1, AW), alive_wave(newest >> 1, AW)));
+                    }
+                    __syncwarp();
+#endif
+                    const uint2 rest = pq[min((uint32_t)ALIVE_DRAIN + lane, (uint32_t)ALIVE_QUEUE - 1u)];   // < 32 entries are left
+                    __syncwarp();
+                    if ((uint32_t)ALIVE_DRAIN + lane < q_pending) pq[lane] = rest;
+                    q_pending -= (uint32_t)ALIVE_DRAIN;
+                    __syncwarp();
+                }
             }
             __syncwarp();
-            // a dense pass of the 32 OLDEST queued records through the table (their lines were prefetched a tile or two
-            // ago): stamp, tell the seen cache what the table knows now, move the rest of the queue to the front
-            while (q_pending >= 32u) {
-#if KTA_EXP_ALIVE_STAGE >= 2
-                {
-                    const uint2 item = pq[lane];
-                    const uint32_t pr = alive_home(item.x, AT.npairs);
-                    const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
-                    const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
-                    // the newest stamp known for this hash as a wave of THIS batch (0 = it is older than the batch and says
-                    // nothing), or the record's own wave
-                    if (cached) alive_cache_put(AW.cache, item.x, max(alive_wave(item.y >> 1, AW), alive_wave(newest >> 1, AW)));
-                }
-#endif
-                __syncwarp();
-                for (uint32_t from = 32u; from < q_pending; from += 32u) {   // the rest moves up by 32, oldest first
-                    const uint2 v = pq[min(from + lane, (uint32_t)ALIVE_QUEUE - 1u)];
-                    __syncwarp();
-                    if (from + lane < q_pending) pq[from - 32u + lane] = v;
-                    __syncwarp();
-                }
-                q_pending -= 32u;
-            }
 #endif
         }
 #ifndef KTA_EXP_NO_HLL
@@ -1195,11 +1200,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
         }
     }
 
-    if (MODE == MODE_EXACT && KTA_EXP_ALIVE_STAGE >= 2 && (uint32_t)lane < q_pending) {
-        // the warp's last survivors (fewer than 32; the batch is over: nothing left for the cache to filter)
-        const uint2 item = reinterpret_cast<const uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF)[lane];
-        const uint32_t pr = alive_home(item.x, AT.npairs);
-        alive_stamp(AT, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol), item.x, item.y);
+    if (MODE == MODE_EXACT && KTA_EXP_ALIVE_STAGE >= 2) {
+        // the warp's last survivors (the batch is over: nothing left for the cache to filter)
+        const uint2 *pq = reinterpret_cast<const uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF);
+        for (uint32_t i = lane; i < q_pending; i += 32) {
+            const uint2 item = pq[i];
+            const uint32_t pr = alive_home(item.x, AT.npairs);
+            alive_stamp(AT, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol), item.x, item.y);
+        }
     }
 
     // ---- flush CTA-private state ----
