@@ -1119,9 +1119,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], alive_wave(low[k] >> 1, AW)));
+                const uint32_t wv = alive_wave(low[k] >> 1, AW);
+                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], wv));
                 const unsigned m = __ballot_sync(full, go);
-                if (go) pq[q_pending + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
+                if (go) {
+                    pq[q_pending + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
+                    // The cache learns of the record NOW, not when it reaches the table: "a record of this hash with this
+                    // wave exists and is on its way" is already true, and every tile it stays unknown lets older siblings
+                    // through (measured: telling the cache only at drain time made every deferred variant slower).
+                    if (cached) alive_cache_put(AW.cache, x[k], wv);
+                }
                 q_pending += __popc(m);
                 if (q_pending >= (uint32_t)ALIVE_DRAIN) {
                     // A dense pass of the 128 oldest queued records through the table, four per lane: the four home pairs
@@ -1142,9 +1149,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const uint32_t newest = alive_stamp(AT, pr[j], e[j], it[j].x, it[j].y);
-                        // the newest stamp known for this hash as a wave of THIS batch (0 = older than the batch: says
-                        // nothing), or the record's own wave
-                        if (cached) alive_cache_put(AW.cache, it[j].x, max(alive_wave(it[j].y >> 1, AW), alive_wave(newest >> 1, AW)));
+                        // if the table knows a newer record of this hash than the one the cache was told about at enqueue
+                        // time, pass that on
+                        if (cached && newest != it[j].y) {
+                            const uint32_t wt = alive_wave(newest >> 1, AW);
+                            if (wt > alive_wave(it[j].y >> 1, AW)) alive_cache_put(AW.cache, it[j].x, wt);
+                        }
                     }
                     __syncwarp();
 #endif
