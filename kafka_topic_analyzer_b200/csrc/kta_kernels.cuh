@@ -636,12 +636,19 @@ __device__ __forceinline__ bool alive_cache_newer(uint32_t c, uint32_t x, uint32
     const uint32_t lo = (tag << ALIVE_CACHE_WAVE_BITS) | wv;
     return (w0 - lo - 1u < ALIVE_CACHE_WAVES - wv) || (w1 - lo - 1u < ALIVE_CACHE_WAVES - wv);
 }
-// record the fact "hash x has a record of wave wv" (wv >= 1).  The way is chosen by a bit of the hash (a key always lives in
-// the same way: nothing to read before the write; lookups still look at both halves of the word at once).
-__device__ __forceinline__ void alive_cache_put(uint32_t *cache, uint32_t x, uint32_t wv) {
+// record the fact "hash x has a record of wave wv" (wv >= 1) in its set; c = the set word as read by the probe.
+// The tag's own way if it has one (and only if that improves on it), else an empty way, else either.  (Picking the way by
+// a bit of the hash instead — nothing to carry from the probe — was measured: two keys that share a set then evict each
+// other for ever, 1.4 GB more table traffic per 1e8 records.)
+__device__ __forceinline__ void alive_cache_put(uint32_t *cache, uint32_t c, uint32_t x, uint32_t wv, uint32_t pick) {
     const uint32_t tag = x & ((1u << ALIVE_CACHE_TAG_BITS) - 1u);
-    unsigned short *set = reinterpret_cast<unsigned short *>(cache + (x >> ALIVE_CACHE_TAG_BITS));
-    set[(x >> (ALIVE_CACHE_TAG_BITS - 1)) & 1u] = (unsigned short)((tag << ALIVE_CACHE_WAVE_BITS) | wv);   // top tag bit picks the way
+    const uint32_t mine = (tag << ALIVE_CACHE_WAVE_BITS) | wv;
+    const uint32_t w0 = c & 0xffffu, w1 = c >> 16;
+    int way;
+    if ((w0 >> ALIVE_CACHE_WAVE_BITS) == tag && w0) way = w0 >= mine ? -1 : 0;          // already known at least as new
+    else if ((w1 >> ALIVE_CACHE_WAVE_BITS) == tag && w1) way = w1 >= mine ? -1 : 1;
+    else way = w0 == 0 ? 0 : w1 == 0 ? 1 : (int)(pick & 1u);
+    if (way >= 0) reinterpret_cast<unsigned short *>(cache + (x >> ALIVE_CACHE_TAG_BITS))[way] = (unsigned short)mine;   // way 0 = low half
 }
 
 // plain insert of an entry whose hash is known to be absent (rehash into a fresh table)
@@ -1083,7 +1090,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             // the tile has just finished with) and take the exact path through the table, usually in a single pass.
             // (Measured dead ends, profiles/r02_exact_experiments.md: deferring the table pass by a tile or batching it
             // over several, with or without L2 prefetch, and giving it to dedicated consumer warps were all slower.)
-            uint2 *queue = reinterpret_cast<uint2 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (x, low word) x TILE <= stage
+            uint4 *queue = reinterpret_cast<uint4 *>(wsm + 128 + (size_t)buf * KEYBUF);   // (x, low word, set word, -) x TILE <= stage
             const bool cached = AW.cache != nullptr;
             const uint32_t r32 = (uint32_t)rbase;   // index in the batch (< 2^31: host-checked)
             uint32_t x[ROWS], low[ROWS], cw[ROWS];
@@ -1116,20 +1123,21 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             for (int k = 0; k < ROWS; k++) {
                 const bool go = live[k] && !(cached && alive_cache_newer(cw[k], x[k], alive_wave(low[k] >> 1, AW)));
                 const unsigned m = __ballot_sync(full, go);
-                if (go) queue[qn + __popc(m & lt_mask)] = make_uint2(x[k], low[k]);
+                if (go) queue[qn + __popc(m & lt_mask)] = make_uint4(x[k], low[k], cw[k], 0u);
                 qn += __popc(m);
             }
             __syncwarp();
 #if KTA_EXP_ALIVE_STAGE >= 2
             for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
                 if (q0 + lane < qn) {
-                    const uint2 item = queue[q0 + lane];
+                    const uint4 item = queue[q0 + lane];
                     const uint32_t pr = alive_home(item.x, AT.npairs);
                     const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
                     const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
                     // tell the cache what the table knows now: the newest stamp of this hash as a wave of THIS batch (0 =
                     // older than the batch: says nothing), or the record's own wave
-                    if (cached) alive_cache_put(AW.cache, item.x, max(alive_wave(item.y >> 1, AW), alive_wave(newest >> 1, AW)));
+                    if (cached)
+                        alive_cache_put(AW.cache, item.z, item.x, max(alive_wave(item.y >> 1, AW), alive_wave(newest >> 1, AW)), newest >> 1);
                 }
             }
 #endif
