@@ -343,7 +343,9 @@ def measure(a, ctx, full):
     assert n == a.n
     alg_bytes = 20 * n + (topic.key_bytes_len if a.mode != "counters" else 0)
 
-    eng = make_engine(kta, a, a.mode, local, shard=(rank, vw))
+    # a sharded handle carves counter columns for its own partitions only: worth its few instructions per record when the
+    # topic has many partitions (C3: 256 -> 32 columns per rank), not for C1's 64
+    eng = make_engine(kta, a, a.mode, local, shard=(rank, vw) if a.partitions > 64 else None)
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
 
