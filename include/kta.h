@@ -212,6 +212,10 @@ int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, const uint6
 /* raw bytes already in device memory; batch_off[nbatches] = byte offset of every batch header (device memory) */
 int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
                                 const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out);
+/* the same for batches of SEVERAL partitions lying in one device buffer (e.g. a whole fetch response, or many segments
+ * staged back to back): dev_batch_partition[nbatches] names each batch's partition.  One decode and one scan. */
+int kta_scan_log_batches_device(kta_handle *h, const uint8_t *dev_bytes, int64_t len, const uint64_t *dev_batch_off,
+                                const int32_t *dev_batch_partition, int64_t nbatches, int64_t *records_out);
 /* raw bytes in host memory (e.g. an mmap of a .log file); returns when `bytes` may be reused */
 int kta_push_log_segment_host(kta_handle *h, int32_t partition, const uint8_t *bytes, int64_t len, int64_t *records_out);
 /* several segments (any partitions) in one go: one staging copy per segment, ONE decode and ONE scan for all of them */

@@ -134,6 +134,7 @@ SYMBOLS = {
     "kta_alive_export_device": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "kta_alive_import_device": (C.c_int, [_P, _P, _P, C.c_int64]),
     "kta_scan_log_segment_device": (C.c_int, [_P, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "kta_scan_log_batches_device": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "kta_push_log_segment_host": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "kta_push_log_segments_host": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(C.c_int64)]),
     "kta_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -39,6 +39,15 @@ static void die(const char *what) {
 }
 #define KTA(call) do { if ((call) != KTA_OK) die(#call); } while (0)
 
+// kta_finalize reports records whose partition lies outside the topic's metadata with KTA_ERR_PARTITION; the state is
+// valid (those records were left out of every metric), so the report is still printed — with a warning, like the
+// reference's warn!() for a failed poll (src/kafka.rs:95-97).
+static void finalize_or_warn(kta_handle *h) {
+    const int rc = kta_finalize(h);
+    if (rc == KTA_ERR_PARTITION) fprintf(stderr, "warning: %s\n", kta_last_error());
+    else if (rc != KTA_OK) die("kta_finalize");
+}
+
 
 // ---- --log-dir: a broker's data directory instead of a live cluster ------------------------------------------------
 static bool read_file(const std::string &path, std::vector<uint8_t> &out) {
@@ -131,7 +140,7 @@ static int analyze_log_dir(const std::string &topic, const std::string &dir, boo
         fprintf(stderr, "Given topic has no content, no analysis possible. Exiting.\n");  // main.rs:98-101
         return 254;
     }
-    KTA(kta_finalize(h));
+    finalize_or_warn(h);
     const uint64_t secs = (uint64_t)std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start_time).count();
     // the report has one row per partition of the topic's metadata (main.rs:103-106): the <topic>-<n> directories found
     std::vector<int> present;
@@ -274,7 +283,7 @@ int main(int argc, char **argv) {
     }
     {
         const double t0 = now();
-        KTA(kta_finalize(h));
+        finalize_or_warn(h);
         feed_s += now() - t0;
     }
     fprintf(stderr, "[kta] feed=%s: %lld records through the handlers in %.4f s = %.3e msg/s (generator excluded)\n", feed.c_str(),

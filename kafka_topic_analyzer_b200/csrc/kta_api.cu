@@ -122,9 +122,10 @@ struct kta_handle {
     // RecordBatch decoder scratch (kta_scan_log_segment_device / kta_push_log_segment_host)
     uint8_t *d_log_bytes = nullptr; int64_t log_bytes_cap = 0;       // raw segment staged from the host
     uint64_t *d_log_off = nullptr;                                    // batch offsets staged from the host
-    LogBatchInfo *d_log_info = nullptr; uint64_t *d_log_cnt = nullptr, *d_log_kb = nullptr; int64_t log_batch_cap = 0;
+    LogBatchInfo *d_log_info = nullptr; uint64_t *d_log_cnt = nullptr; int64_t log_batch_cap = 0;
     int32_t *d_dec_part = nullptr, *d_dec_klen = nullptr, *d_dec_vlen = nullptr; int64_t *d_dec_ts = nullptr; int64_t dec_rec_cap = 0;
     uint8_t *d_dec_keys = nullptr; int64_t dec_key_cap = 0;
+    uint64_t *d_dec_ksrc = nullptr;          // per decoded record: where its key bytes lie in the segment buffer
     uint32_t *d_log_err = nullptr;
     size_t nsums = 0, nhll = 0;
     // landing ring
@@ -271,8 +272,8 @@ extern "C" int kta_destroy(kta_handle *h) {
     for (auto &c : h->chunks) free_chunk(c);
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
     cudaFree(h->d_alive_status); cudaFree(h->d_alive_cache); cudaFreeHost(h->h_alive_status); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
-    cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt); cudaFree(h->d_log_kb);
-    cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys);
+    cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt);
+    cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys); cudaFree(h->d_dec_ksrc);
     cudaFree(h->d_log_err);
     for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -694,7 +695,8 @@ static int grow(T *&ptr, int64_t &cap, int64_t need, cudaStream_t s) {
 }
 
 static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev_batch_partition, const uint8_t *dev_bytes,
-                            int64_t len, const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
+                            int64_t len, int64_t readable /* bytes of dev_bytes that may be READ (>= len when the buffer has slack) */,
+                            const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
     if (!h || len < 0 || nbatches < 0 || (nbatches && (!dev_bytes || !dev_batch_off))) return fail(KTA_ERR_INVALID, "bad argument");
     if (records_out) *records_out = 0;
     if (nbatches == 0) return KTA_OK;
@@ -705,16 +707,15 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     cudaStream_t s = h->stream;
     if (nbatches + 1 > h->log_batch_cap) {
         CU(cudaStreamSynchronize(s));
-        cudaFree(h->d_log_info); cudaFree(h->d_log_cnt); cudaFree(h->d_log_kb);
-        h->d_log_info = nullptr; h->d_log_cnt = nullptr; h->d_log_kb = nullptr; h->log_batch_cap = 0;
+        cudaFree(h->d_log_info); cudaFree(h->d_log_cnt);
+        h->d_log_info = nullptr; h->d_log_cnt = nullptr; h->log_batch_cap = 0;
         const int64_t n = nbatches + nbatches / 4 + 64;
         CU(cudaMalloc(&h->d_log_info, (size_t)n * sizeof(LogBatchInfo)));
         CU(cudaMalloc(&h->d_log_cnt, (size_t)n * 8));
-        CU(cudaMalloc(&h->d_log_kb, (size_t)n * 8));
         h->log_batch_cap = n;
     }
-    if (!h->d_log_err) CU(cudaMalloc(&h->d_log_err, 4));
-    CU(cudaMemsetAsync(h->d_log_err, 0, 4, s));
+    if (!h->d_log_err) CU(cudaMalloc(&h->d_log_err, 8));   // [0] error flags, [1] longest batch
+    CU(cudaMemsetAsync(h->d_log_err, 0, 8, s));
     const int grid = (int)std::min<int64_t>((nbatches + 127) / 128, (int64_t)h->sm_count * 16);
     log_header_kernel<<<grid, 128, 0, s>>>(dev_bytes, len, dev_batch_off, nbatches, partition, dev_batch_partition, h->d_log_info,
                                             h->d_log_cnt, h->d_log_err);
@@ -722,43 +723,48 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     CU(cudaGetLastError());
     h->launches += 2;
     uint64_t nrec = 0;
-    uint32_t err = 0;
+    uint32_t err[2] = {0, 0};
     CU(cudaMemcpyAsync(&nrec, h->d_log_cnt + nbatches, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(&err, h->d_log_err, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(err, h->d_log_err, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    if (err & LOGB_COMPRESSED) return fail(KTA_ERR_INVALID, "compressed record batches are not supported (no decompressor on this path)");
-    if (err) return fail(KTA_ERR_INVALID, "malformed record batch header in partition %d", partition);
+    if (err[0] & LOGB_COMPRESSED) return fail(KTA_ERR_INVALID, "compressed record batches are not supported (no decompressor on this path)");
+    if (err[0]) return fail(KTA_ERR_INVALID, "malformed record batch header in partition %d", partition);
     if (nrec == 0) return KTA_OK;
+    if ((int64_t)nrec >= ((int64_t)1 << 31) - 2) return fail(KTA_ERR_INVALID, "%llu records in one call: split the segments", (unsigned long long)nrec);
+    const bool hash = h->need_hash || h->d_hash_out;
     if ((int64_t)nrec > h->dec_rec_cap) {
         CU(cudaStreamSynchronize(s));
-        cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts);
-        h->d_dec_part = h->d_dec_klen = h->d_dec_vlen = nullptr; h->d_dec_ts = nullptr; h->dec_rec_cap = 0;
+        cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_ksrc);
+        h->d_dec_part = h->d_dec_klen = h->d_dec_vlen = nullptr; h->d_dec_ts = nullptr; h->d_dec_ksrc = nullptr; h->dec_rec_cap = 0;
         const int64_t n = (int64_t)nrec + (int64_t)nrec / 4 + 1024;
         CU(cudaMalloc(&h->d_dec_part, (size_t)n * 4));
         CU(cudaMalloc(&h->d_dec_klen, (size_t)n * 4));
         CU(cudaMalloc(&h->d_dec_vlen, (size_t)n * 4));
         CU(cudaMalloc(&h->d_dec_ts, (size_t)n * 8));
+        CU(cudaMalloc(&h->d_dec_ksrc, (size_t)n * 8));
         h->dec_rec_cap = n;
     }
-    const int dgrid = (int)std::min<int64_t>((nbatches + 3) / 4, (int64_t)h->sm_count * 16);   // one warp per batch
-    log_decode_kernel<0><<<dgrid, LOG_DECODE_THREADS, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, h->d_dec_part, nullptr, h->d_dec_ts,
-                                              h->d_dec_klen, h->d_dec_vlen, h->d_log_kb, nullptr, h->d_log_err);
-    tile_base_scan_kernel<<<1, 1024, 0, s>>>(h->d_log_kb, nbatches);
-    CU(cudaGetLastError());
-    h->launches += 2;
-    uint64_t nkey = 0;
-    CU(cudaMemcpyAsync(&nkey, h->d_log_kb + nbatches, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(&err, h->d_log_err, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (err) return fail(KTA_ERR_INVALID, "malformed record inside a batch of partition %d", partition);
-    const bool hash = h->need_hash || h->d_hash_out;
-    if (hash) {
-        if ((rc = grow(h->d_dec_keys, h->dec_key_cap, (int64_t)nkey + 64, s))) return rc;
-        log_decode_kernel<1><<<dgrid, LOG_DECODE_THREADS, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_log_cnt, nullptr, nullptr, nullptr, nullptr,
-                                                  nullptr, h->d_log_kb, h->d_dec_keys, h->d_log_err);
-        CU(cudaGetLastError());
-        h->launches++;
+    // one warp per batch; the batch is staged in shared memory when the longest one fits a stage of <= 48 KiB
+    const uint32_t maxlen = err[1];
+    const uint32_t stage = (uint32_t)(((size_t)maxlen + 16 + 1023) / 1024 * 1024);
+    const bool staged = stage <= 48u * 1024u;
+    const size_t dsm = (size_t)(LOG_DECODE_THREADS / 32) * (LOG_WARP_HEADER + (staged ? stage : 0u));
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(log_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+        attr_set = true;
     }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, h->smem_optin / std::max<size_t>(dsm, 1)));
+    const int dgrid = (int)std::min<int64_t>((nbatches + 3) / 4, (int64_t)h->sm_count * per_sm);
+    uint64_t *ksrc = hash ? h->d_dec_ksrc : nullptr;
+    if (staged)
+        log_decode_kernel<true><<<dgrid, LOG_DECODE_THREADS, dsm, s>>>(dev_bytes, (uint64_t)readable, h->d_log_info, nbatches, h->d_log_cnt, h->d_dec_part,
+                                                                       nullptr, h->d_dec_ts, h->d_dec_klen, h->d_dec_vlen, ksrc, stage, h->d_log_err);
+    else
+        log_decode_kernel<false><<<dgrid, LOG_DECODE_THREADS, dsm, s>>>(dev_bytes, (uint64_t)readable, h->d_log_info, nbatches, h->d_log_cnt, h->d_dec_part,
+                                                                        nullptr, h->d_dec_ts, h->d_dec_klen, h->d_dec_vlen, ksrc, 0u, h->d_log_err);
+    CU(cudaGetLastError());
+    h->launches++;
     kta_batch b{};
     b.n = (int64_t)nrec;
     b.seq_base = KTA_SEQ_AUTO;
@@ -766,8 +772,36 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     b.ts_ms = h->d_dec_ts;
     b.key_len = h->d_dec_klen;
     b.value_len = h->d_dec_vlen;
-    b.key_bytes = hash ? h->d_dec_keys : nullptr;
-    b.key_bytes_len = hash ? (int64_t)nkey : 0;
+    if (hash) {
+        // pack the keys in record order: tile bases from the key_len column, then one gather pass (no second walk of the log)
+        const int64_t ntiles = ((int64_t)nrec + TILE - 1) / TILE;
+        if (ntiles + 1 > h->tb_scratch_tiles) {
+            CU(cudaStreamSynchronize(s));
+            cudaFree(h->d_tb_scratch);
+            h->d_tb_scratch = nullptr;
+            h->tb_scratch_tiles = 0;
+            CU(cudaMalloc(&h->d_tb_scratch, (size_t)(ntiles + 1) * 8));
+            h->tb_scratch_tiles = ntiles + 1;
+        }
+        if ((rc = derive_tile_base(h, h->d_dec_klen, (int64_t)nrec, h->d_tb_scratch))) return rc;
+        uint64_t nkey = 0;
+        CU(cudaMemcpyAsync(&nkey, h->d_tb_scratch + ntiles, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(err, h->d_log_err, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (err[0]) return fail(KTA_ERR_INVALID, "malformed record inside a batch of partition %d", partition);
+        if ((rc = grow(h->d_dec_keys, h->dec_key_cap, (int64_t)nkey + 64, s))) return rc;
+        log_gather_keys_kernel<<<(int)std::min<int64_t>((ntiles + 7) / 8, (int64_t)h->sm_count * 8), 256, 0, s>>>(
+            dev_bytes, h->d_dec_ksrc, h->d_dec_klen, (int64_t)nrec, h->d_tb_scratch, h->d_dec_keys);
+        CU(cudaGetLastError());
+        h->launches++;
+        b.key_bytes = h->d_dec_keys;
+        b.key_bytes_len = (int64_t)nkey;
+        b.key_tile_base = h->d_tb_scratch;
+    } else {
+        CU(cudaMemcpyAsync(err, h->d_log_err, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (err[0]) return fail(KTA_ERR_INVALID, "malformed record inside a batch of partition %d", partition);
+    }
     if ((rc = kta_scan_batch_device(h, &b))) return rc;
     if (records_out) *records_out = (int64_t)nrec;
     return KTA_OK;
@@ -775,7 +809,13 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
 
 extern "C" int kta_scan_log_segment_device(kta_handle *h, int32_t partition, const uint8_t *dev_bytes, int64_t len,
                                            const uint64_t *dev_batch_off, int64_t nbatches, int64_t *records_out) {
-    return scan_log_batches(h, partition, nullptr, dev_bytes, len, dev_batch_off, nbatches, records_out);
+    return scan_log_batches(h, partition, nullptr, dev_bytes, len, len, dev_batch_off, nbatches, records_out);
+}
+
+extern "C" int kta_scan_log_batches_device(kta_handle *h, const uint8_t *dev_bytes, int64_t len, const uint64_t *dev_batch_off,
+                                           const int32_t *dev_batch_partition, int64_t nbatches, int64_t *records_out) {
+    if (nbatches && !dev_batch_partition) return fail(KTA_ERR_INVALID, "dev_batch_partition is NULL");
+    return scan_log_batches(h, 0, dev_batch_partition, dev_bytes, len, len, dev_batch_off, nbatches, records_out);
 }
 
 extern "C" int kta_push_log_segments_host(kta_handle *h, int32_t nsegs, const int32_t *partitions, const uint8_t *const *bytes,
@@ -819,7 +859,8 @@ extern "C" int kta_push_log_segments_host(kta_handle *h, int32_t nsegs, const in
             CU(cudaMemcpyAsync(h->d_log_bytes + base[(size_t)sgi], bytes[sgi], (size_t)used[(size_t)sgi], cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(h->d_log_off, offs.data(), offs.size() * 8, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_parts, parts.data(), parts.size() * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = scan_log_batches(h, 0, d_parts, h->d_log_bytes, total, h->d_log_off, (int64_t)offs.size(), records_out))) return rc;
+    // the staging buffer has 64 bytes of slack behind `total`: 16-byte-granular bulk copies may run into it
+    if ((rc = scan_log_batches(h, 0, d_parts, h->d_log_bytes, total, total + 48, h->d_log_off, (int64_t)offs.size(), records_out))) return rc;
     CU(cudaStreamSynchronize(s));   // the caller may reuse its buffers, and the scratch may be reused by the next call
     return collect_timing(h);
 }

@@ -35,22 +35,6 @@ __device__ __forceinline__ uint32_t be_u32(const uint8_t *p) {
 }
 __device__ __forceinline__ uint32_t be_u16(const uint8_t *p) { return ((uint32_t)__ldg(p) << 8) | __ldg(p + 1); }
 
-// unsigned LEB128 at p (bounded by end); returns bytes consumed, 0 on malformed input
-__device__ __forceinline__ int uvarint(const uint8_t *p, const uint8_t *end, uint64_t &out) {
-    uint64_t v = 0;
-    int shift = 0, n = 0;
-    while (p + n < end && n < 10) {
-        const uint8_t b = __ldg(p + n);
-        n++;
-        v |= (uint64_t)(b & 0x7f) << shift;
-        if (!(b & 0x80)) {
-            out = v;
-            return n;
-        }
-        shift += 7;
-    }
-    return 0;
-}
 __device__ __forceinline__ int64_t unzigzag(uint64_t u) { return (int64_t)(u >> 1) ^ -(int64_t)(u & 1); }
 
 struct LogBatchInfo {      // one per record batch, filled by log_header_kernel
@@ -97,110 +81,183 @@ __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const ui
             }
         }
         if (bi.flags & (LOGB_BAD | LOGB_COMPRESSED)) atomicOr(error_flags, bi.flags);
+        else if (bi.flags == LOGB_OK) atomicMax(error_flags + 1, bi.len);   // [1]: the longest batch (sizes the decode stage)
         info[b] = bi;
         rec_count[b + 1] = (uint64_t)bi.records;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) rec_count[0] = 0;
 }
 
-// One WARP per batch.  Records are length-prefixed, so finding where record i starts is a serial chain — lane 0
-// hops through 32 record-length varints at a time (touching one or two bytes per record) and publishes the 32
-// start positions; then the 32 lanes parse their records in parallel and write the columns coalesced.
-// PASS 0: header columns + key-byte total of the batch; PASS 1: copy the keys (packed, in record order).
-constexpr int LOG_DECODE_THREADS = 128;
+// unsigned LEB128 at p (bounded by end); returns bytes consumed, 0 on malformed input.  Generic byte loads: the batch may
+// sit in shared memory or in global memory.
+__device__ __forceinline__ int uvarint_g(const uint8_t *p, const uint8_t *end, uint64_t &out) {
+    uint64_t v = 0;
+    int shift = 0, n = 0;
+    while (p + n < end && n < 10) {
+        const uint8_t b = p[n];
+        n++;
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) {
+            out = v;
+            return n;
+        }
+        shift += 7;
+    }
+    return 0;
+}
 
-template <int PASS>
+// One WARP per batch.  Records are length-prefixed, so finding where record i starts is a serial chain: lane 0 hops through
+// 32 record-length varints at a time and publishes the 32 start positions; then the 32 lanes parse their records in
+// parallel and write the columns coalesced.
+// STAGED: the whole batch (what a producer's batch.size bounds: 16 KiB by default) is first brought global→shared by ONE
+// bulk async copy per batch per warp (cp.async.bulk → UBLKCP, mbarrier completion), so every hop of the chain is a
+// 29-cycle shared-memory read instead of a dependent global access to a new line (measured: the chain of global hops was
+// the decoder's bottleneck).  Batches that do not fit the stage, or whose 16-byte-aligned copy would run past the readable
+// bytes, are read in place.
+// Output: the header columns and, per record, the position of its key bytes in the segment buffer (key_src, only when the
+// keys will be hashed) — the keys themselves are packed afterwards by log_gather_keys_kernel, without a second walk.
+constexpr int LOG_DECODE_THREADS = 128;
+constexpr int LOG_WARP_HEADER = 192;   // per warp: mbarrier (8 B) + 33 record starts (132 B), padded
+
+template <bool STAGED>
 __global__ void __launch_bounds__(LOG_DECODE_THREADS) log_decode_kernel(
-    const uint8_t *bytes, const LogBatchInfo *info, int64_t nbatches, const uint64_t *rec_base, int32_t *partition,
-    int64_t *offset, int64_t *ts_ms, int32_t *key_len, int32_t *value_len,
-    uint64_t *key_total /*[nbatches+1], PASS 0 out, PASS 1 in as exclusive bases*/, uint8_t *key_out, uint32_t *error_flags) {
-    __shared__ uint32_t s_start[LOG_DECODE_THREADS / 32][33];
+    const uint8_t *bytes, uint64_t readable /* bytes that may be read from `bytes` */, const LogBatchInfo *info, int64_t nbatches,
+    const uint64_t *rec_base, int32_t *partition, int64_t *offset, int64_t *ts_ms, int32_t *key_len, int32_t *value_len,
+    uint64_t *key_src, uint32_t stage_bytes /* per warp, multiple of 16 */, uint32_t *error_flags) {
+    extern __shared__ __align__(128) unsigned char log_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
+    unsigned char *wsm = log_smem + (size_t)wib * (LOG_WARP_HEADER + (STAGED ? stage_bytes : 0u));
+    uint32_t *s_start = reinterpret_cast<uint32_t *>(wsm + 16);
+    unsigned char *stage = wsm + LOG_WARP_HEADER;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(wsm);
+    uint32_t phase = 0;
+    if (STAGED && lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t b = gw; b < nbatches; b += gs) {
         const LogBatchInfo bi = info[b];
-        uint64_t kbytes = 0;
         if (bi.flags == LOGB_OK && bi.records > 0) {
             const uint8_t *base = bytes + bi.off;
+            if (STAGED) {
+                const uint32_t lead = (uint32_t)(bi.off & 15u), span = (lead + bi.len + 15u) & ~15u;
+                if (span <= stage_bytes && (bi.off - lead) + span <= readable) {
+                    if (lane == 0) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(span) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"((uint32_t)__cvta_generic_to_shared(stage)), "l"(bytes + (bi.off - lead)), "r"(span), "r"(bar)
+                                     : "memory");
+                    }
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "LOGW_%=:\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                        "@p bra LOGD_%=;\n\t"
+                        "bra LOGW_%=;\n\t"
+                        "LOGD_%=:\n\t}" ::"r"(bar), "r"(phase) : "memory");
+                    phase ^= 1u;
+                    base = stage + lead;
+                }
+            }
             const uint8_t *end = base + bi.len;
             uint32_t pos = LOG_HEADER_BYTES;          // offset of the next record inside the batch
             const uint64_t r0 = rec_base[b];
-            uint64_t kdst = PASS == 1 ? key_total[b] : 0;
             bool ok = true;
             for (int32_t i0 = 0; i0 < bi.records && ok; i0 += 32) {
                 const int cnt = min(32, bi.records - i0);
                 if (lane == 0) {
                     for (int j = 0; j < cnt; j++) {
-                        s_start[wib][j] = pos;
+                        s_start[j] = pos;
                         uint64_t u;
-                        const int n = uvarint(base + pos, end, u);
+                        const int n = uvarint_g(base + pos, end, u);
                         const int64_t rec_len = unzigzag(u);
                         if (n <= 0 || rec_len < 0 || (uint64_t)pos + n + rec_len > bi.len) { ok = false; break; }
                         pos += (uint32_t)n + (uint32_t)rec_len;
                     }
-                    s_start[wib][32] = ok ? pos : 0xffffffffu;
+                    s_start[32] = ok ? pos : 0xffffffffu;
                 }
                 __syncwarp();
-                pos = s_start[wib][32];
+                pos = s_start[32];
                 ok = pos != 0xffffffffu;
                 if (!ok) break;
                 int64_t klen = -1, vlen = -1, ts_delta = 0, off_delta = 0;
-                const uint8_t *key = nullptr;
+                uint32_t key_at = 0;
                 bool lane_ok = true;
                 if (lane < cnt) {
-                    const uint8_t *q = base + s_start[wib][lane];
-                    const uint8_t *rec_end = lane + 1 < cnt ? base + s_start[wib][lane + 1] : base + pos;
+                    const uint8_t *q = base + s_start[lane];
+                    const uint8_t *rec_end = lane + 1 < cnt ? base + s_start[lane + 1] : base + pos;
                     uint64_t u;
-                    int n = uvarint(q, rec_end, u); q += n;            // record length (validated by lane 0)
-                    q += 1;                                             // record attributes (unused)
-                    n = uvarint(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
+                    int n = uvarint_g(q, rec_end, u); q += n;            // record length (validated by lane 0)
+                    q += 1;                                               // record attributes (unused)
+                    n = uvarint_g(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
                     ts_delta = unzigzag(u);
-                    n = uvarint(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
+                    n = uvarint_g(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
                     off_delta = unzigzag(u);
-                    n = uvarint(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
+                    n = uvarint_g(q, rec_end, u); lane_ok = lane_ok && n > 0; q += n;
                     klen = unzigzag(u);
                     lane_ok = lane_ok && klen >= -1 && klen <= 0x7fffffff && (klen <= 0 || q + klen <= rec_end);
-                    key = q;
+                    key_at = (uint32_t)(q - base);
                     if (lane_ok && klen > 0) q += klen;
-                    n = lane_ok ? uvarint(q, rec_end, u) : 0; lane_ok = lane_ok && n > 0; q += n;
+                    n = lane_ok ? uvarint_g(q, rec_end, u) : 0; lane_ok = lane_ok && n > 0; q += n;
                     vlen = unzigzag(u);
                     lane_ok = lane_ok && vlen >= -1 && vlen <= 0x7fffffff && (vlen <= 0 || q + vlen <= rec_end);
                 }
                 __syncwarp();   // every lane has read its start before lane 0 overwrites them
                 ok = __all_sync(full, lane_ok);
                 if (!ok) break;
-                const uint64_t kl = (lane < cnt && klen > 0) ? (uint64_t)klen : 0;
-                if (PASS == 0) {
-                    if (lane < cnt) {
-                        const uint64_t r = r0 + (uint64_t)i0 + lane;
-                        partition[r] = bi.partition;
-                        if (offset) offset[r] = bi.base_offset + off_delta;
-                        ts_ms[r] = bi.log_append_time ? bi.max_ts : bi.base_ts + ts_delta;
-                        key_len[r] = (int32_t)klen;
-                        value_len[r] = (int32_t)vlen;
-                    }
-                    uint64_t t = kl;
-#pragma unroll
-                    for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(full, t, d);
-                    kbytes += t;
-                } else {
-                    uint64_t inc = kl;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint64_t t = __shfl_up_sync(full, inc, d);
-                        if (lane >= d) inc += t;
-                    }
-                    const uint64_t dst = kdst + inc - kl;
-                    for (uint64_t j = 0; j < kl; j++) key_out[dst + j] = __ldg(key + j);
-                    kdst += __shfl_sync(full, inc, 31);
+                if (lane < cnt) {
+                    const uint64_t r = r0 + (uint64_t)i0 + lane;
+                    partition[r] = bi.partition;
+                    if (offset) offset[r] = bi.base_offset + off_delta;
+                    ts_ms[r] = bi.log_append_time ? bi.max_ts : bi.base_ts + ts_delta;
+                    key_len[r] = (int32_t)klen;
+                    value_len[r] = (int32_t)vlen;
+                    if (key_src) key_src[r] = bi.off + key_at;
                 }
             }
             if (!ok && lane == 0) atomicOr(error_flags, (uint32_t)LOGB_BAD);
+            __syncwarp();   // the stage is free for the next batch's copy
         }
-        if (PASS == 0 && lane == 0) key_total[b + 1] = kbytes;
     }
-    if (PASS == 0 && blockIdx.x == 0 && threadIdx.x == 0) key_total[0] = 0;
+}
+
+// Packs the key bytes in record order (what the scan kernel hashes): one warp per 128-record tile, a lane owns four
+// consecutive records; byte offsets from the tile base (key_tile_base, derived from key_len beforehand) plus an in-tile scan.
+__global__ void __launch_bounds__(256) log_gather_keys_kernel(const uint8_t *bytes, const uint64_t *key_src, const int32_t *key_len,
+                                                              int64_t n, const uint64_t *tile_base, uint8_t *key_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ntiles = (n + 127) / 128;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t tile = gw; tile < ntiles; tile += gs) {
+        int32_t len[4];
+        uint64_t src[4];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int64_t r = tile * 128 + (int64_t)lane * 4 + k;
+            len[k] = r < n ? key_len[r] : -1;
+            src[k] = len[k] > 0 ? key_src[r] : 0;
+            mine += len[k] > 0 ? (uint32_t)len[k] : 0u;
+        }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        uint8_t *o = key_out + tile_base[tile] + (inc - mine);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (len[k] > 0) {
+                const uint8_t *sp = bytes + src[k];
+                for (int j = 0; j < len[k]; j++) o[j] = __ldg(sp + j);
+                o += len[k];
+            }
+        }
+    }
 }
 
 }  // namespace kta

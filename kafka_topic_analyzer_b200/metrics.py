@@ -154,6 +154,15 @@ class KtaEngine:
         check(lib().kta_push_log_segment_host(self._h, partition, buf.ctypes.data, buf.size, C.byref(n)))
         return n.value
 
+    def scan_log_batches_device(self, dev_bytes, length: int, dev_batch_off, dev_batch_partition, nbatches: int) -> int:
+        """RecordBatch v2 batches of any partitions lying in ONE device buffer (torch CUDA tensors / raw addresses): one
+        decode + one scan.  Returns the number of records delivered to the handlers."""
+        n = C.c_int64()
+        self._keep.append((dev_bytes, dev_batch_off, dev_batch_partition))
+        check(lib().kta_scan_log_batches_device(self._h, _ptr(dev_bytes), length, _ptr(dev_batch_off), _ptr(dev_batch_partition),
+                                                nbatches, C.byref(n)))
+        return n.value
+
     def push_log_segments(self, segments) -> int:
         """segments: iterable of (partition, bytes-like).  One decode + one scan for all of them."""
         segs = [(int(p), np.frombuffer(d, dtype=np.uint8) if not isinstance(d, np.ndarray) else d) for p, d in segments]
@@ -172,11 +181,18 @@ class KtaEngine:
     def reset(self) -> None:
         check(lib().kta_reset(self._h))
 
-    def finalize(self) -> None:
+    def finalize(self, strict: bool = True) -> int:
+        """kta_sync + state to the host.  Records whose partition lies outside [0, num_partitions) are left out of every
+        metric: with strict (default) that raises KtaError(ERR_PARTITION) — the getters are valid nevertheless —, without
+        it the number of such records is returned."""
         try:
-            check(lib().kta_finalize(self._h))
+            rc = lib().kta_finalize(self._h)
         finally:
             self._keep = []
+        if rc == N.ERR_PARTITION and not strict:
+            return self.bad_partition_records()
+        check(rc)
+        return 0
 
     # -- read-back --------------------------------------------------------------------------------
     def counter(self, which: int, p: int) -> int:

@@ -330,6 +330,7 @@ def test_out_of_range_partitions_are_left_out_of_every_metric():
                     e.finalize()
             assert ei.value.code == 4
             assert e.bad_partition_records() == int(badp.sum())
+            assert e.finalize(strict=False) == int(badp.sum())     # the same as a warning: the count, no exception
             assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10), extra_partitions=())
 
 

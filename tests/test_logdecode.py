@@ -224,3 +224,51 @@ def test_synthetic_topic_as_log_segments_full_path():
         assert e.push_log_segments(segs) == spec.n_total
         e.finalize()
         assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(11))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch_records", [40, 300])
+def test_device_entry_points_one_buffer_many_partitions(batch_records):
+    """kta_scan_log_batches_device: the batches of all partitions in ONE device buffer, decoded and scanned in one go; and
+    kta_scan_log_segment_device per partition.  40 records per batch (≈ 12 KB: staged in shared memory by a bulk copy) and 300
+    (≈ 90 KB: read in place); the buffer has no slack behind its last byte, so the last batch is read in place too."""
+    import torch
+    P = 5
+    spec = synth.make_spec(P * 12_000, P, distinct_keys=3000, tombstone_per_10k=2000, key_mode=1, ts_missing_per_10k=30)
+    o = Oracle(count_alive_keys=True, now=NOW)
+    chunks, offs, parts, total = [], [], [], 0
+    for p in range(P):
+        t = synth.fill_host(spec, rank=p, world=P)
+        o.handle_batch(t.partition, t.ts_ms, t.key_len, t.value_len, t.key_bytes)
+        s = synth.encode_segment(spec, p, batch_records=batch_records)
+        pos = 0
+        while pos + 61 <= s.size:
+            offs.append(total + pos)
+            parts.append(p)
+            pos += 12 + int.from_bytes(s[pos + 8:pos + 12].tobytes(), "big", signed=True)
+        chunks.append(s)
+        total += s.size                       # packed back to back: batches start at arbitrary alignments
+    buf = torch.from_numpy(np.concatenate(chunks)).cuda()
+    assert buf.numel() == total
+    d_off = torch.tensor(offs, dtype=torch.int64).cuda()
+    d_part = torch.tensor(parts, dtype=torch.int32).cuda()
+    with KtaEngine(P, count_alive_keys=True, hll_precision=10, now=NOW) as e:
+        assert e.scan_log_batches_device(buf, total, d_off, d_part, len(offs)) == spec.n_total
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10))
+        # partition by partition through the single-partition entry point: the result is the same
+        e.reset()
+        import ctypes as C
+        at, b0 = 0, 0
+        for p in range(P):
+            nb = parts.count(p)
+            n = C.c_int64()
+            rel = (d_off[b0:b0 + nb] - at).contiguous()
+            seg = buf[at:at + chunks[p].size].clone()
+            from kafka_topic_analyzer_b200._native import check, lib
+            check(lib().kta_scan_log_segment_device(e.handle, p, seg.data_ptr(), seg.numel(), rel.data_ptr(), nb, C.byref(n)))
+            assert n.value == spec.n_total // P
+            at += chunks[p].size
+            b0 += nb
+        e.finalize()
+        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(10))
