@@ -126,6 +126,8 @@ struct kta_handle {
     int32_t *d_dec_part = nullptr, *d_dec_klen = nullptr, *d_dec_vlen = nullptr; int64_t *d_dec_ts = nullptr; int64_t dec_rec_cap = 0;
     uint8_t *d_dec_keys = nullptr; int64_t dec_key_cap = 0;
     uint64_t *d_dec_ksrc = nullptr;          // per decoded record: where its key bytes lie in the segment buffer
+    uint8_t *d_unc = nullptr; int64_t unc_cap = 0;   // uncompressed images of LZ4 / Snappy batches
+    uint64_t *d_unc_slot = nullptr; int64_t unc_slot_cap = 0;
     uint32_t *d_log_err = nullptr;
     size_t nsums = 0, nhll = 0;
     // landing ring
@@ -273,7 +275,7 @@ extern "C" int kta_destroy(kta_handle *h) {
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
     cudaFree(h->d_alive_status); cudaFree(h->d_alive_cache); cudaFreeHost(h->h_alive_status); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
     cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt);
-    cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys); cudaFree(h->d_dec_ksrc);
+    cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys); cudaFree(h->d_dec_ksrc); cudaFree(h->d_unc); cudaFree(h->d_unc_slot);
     cudaFree(h->d_log_err);
     for (auto &e : h->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -727,9 +729,30 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     CU(cudaMemcpyAsync(&nrec, h->d_log_cnt + nbatches, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(err, h->d_log_err, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    if (err[0] & LOGB_COMPRESSED) return fail(KTA_ERR_INVALID, "compressed record batches are not supported (no decompressor on this path)");
-    if (err[0]) return fail(KTA_ERR_INVALID, "malformed record batch header in partition %d", partition);
+    if (err[0] & LOGB_COMPRESSED)
+        return fail(KTA_ERR_INVALID, "gzip / zstd record batches are not supported (LZ4 and Snappy are decompressed on the GPU)");
+    if (err[0] & LOGB_BAD) return fail(KTA_ERR_INVALID, "malformed record batch header in partition %d", partition);
     if (nrec == 0) return KTA_OK;
+    if (err[0] & (LOGB_LZ4 | LOGB_SNAPPY)) {
+        // compressed batches: size pass, scratch allocation, decompression; afterwards they are ordinary batches that
+        // happen to lie in the scratch buffer
+        if ((rc = grow(h->d_unc_slot, h->unc_slot_cap, nbatches + 2, s))) return rc;
+        CU(cudaMemsetAsync(h->d_log_err, 0, 4, s));
+        log_unc_size_kernel<<<grid, 128, 0, s>>>(dev_bytes, h->d_log_info, nbatches, h->d_unc_slot, h->d_log_err);
+        tile_base_scan_kernel<<<1, 1024, 0, s>>>(h->d_unc_slot, nbatches);
+        CU(cudaGetLastError());
+        h->launches += 2;
+        uint64_t unc_total = 0;
+        CU(cudaMemcpyAsync(&unc_total, h->d_unc_slot + nbatches, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(err, h->d_log_err, 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (err[0]) return fail(KTA_ERR_INVALID, "malformed compressed record batch in partition %d", partition);
+        if ((rc = grow(h->d_unc, h->unc_cap, (int64_t)unc_total + 64, s))) return rc;
+        log_decompress_kernel<<<(int)std::min<int64_t>((nbatches + 3) / 4, (int64_t)h->sm_count * 16), 128, 0, s>>>(
+            dev_bytes, h->d_log_info, nbatches, h->d_unc_slot, h->d_unc, h->d_log_err);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
     if ((int64_t)nrec >= ((int64_t)1 << 31) - 2) return fail(KTA_ERR_INVALID, "%llu records in one call: split the segments", (unsigned long long)nrec);
     const bool hash = h->need_hash || h->d_hash_out;
     if ((int64_t)nrec > h->dec_rec_cap) {

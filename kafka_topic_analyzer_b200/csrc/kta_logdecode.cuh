@@ -13,6 +13,9 @@
 // LogAppendTime batches (attributes bit 3) stamp every record with maxTimestamp; a record's timestamp is baseTimestamp +
 // timestampDelta as the consumer computes it, and only a RESULT of -1 means "not available"; key/value length -1 means
 // null.  CRCs are not verified (librdkafka's default check.crcs=false).
+// Compression (attributes bits 0-2, librdkafka decompresses inside poll, src/kafka.rs:93): LZ4 (frame format) and Snappy
+// (raw or xerial-framed) batches are decompressed on the GPU into a scratch buffer and then decoded like the others;
+// gzip and zstd are rejected.
 // Not handled: records of aborted transactions are delivered (a read_committed consumer would filter them through the
 // .txnindex / abort markers), legacy magic 0/1 message sets are flagged as malformed.
 #pragma once
@@ -22,7 +25,9 @@
 namespace kta {
 
 constexpr int LOG_HEADER_BYTES = 61;
-enum LogBatchFlags { LOGB_OK = 0, LOGB_SKIP_CONTROL = 1, LOGB_BAD = 2, LOGB_COMPRESSED = 4 };
+// LOGB_COMPRESSED: a codec without a decompressor here (gzip, zstd).  LOGB_LZ4 / LOGB_SNAPPY: the records section must be
+// decompressed first (log_unc_size_kernel + log_decompress_kernel turn such a batch into LOGB_OK).
+enum LogBatchFlags { LOGB_OK = 0, LOGB_SKIP_CONTROL = 1, LOGB_BAD = 2, LOGB_COMPRESSED = 4, LOGB_LZ4 = 8, LOGB_SNAPPY = 16 };
 
 __device__ __forceinline__ uint64_t be_u64(const uint8_t *p) {
     uint64_t v = 0;
@@ -65,22 +70,23 @@ __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const ui
             const int32_t count = (int32_t)be_u32(p + 57);
             // recordsCount sizes the output columns, so it must be plausible before anything is allocated for it: the
             // smallest record is 7 bytes (length, attributes, two deltas, key length, value length, header count)
+            const uint32_t codec = attrs & 0x7u;
+            // (for a compressed batch the 7-bytes-per-record bound is checked against the uncompressed size later)
             if (magic == 2 && batch_len >= LOG_HEADER_BYTES - 12 && bi.off + 12 + (uint64_t)batch_len <= (uint64_t)nbytes && count >= 0 &&
-                (uint64_t)count * 7u + (uint64_t)(LOG_HEADER_BYTES - 12) <= (uint64_t)batch_len) {
+                (codec != 0 || (uint64_t)count * 7u + (uint64_t)(LOG_HEADER_BYTES - 12) <= (uint64_t)batch_len)) {
                 bi.len = 12u + (uint32_t)batch_len;
                 bi.base_offset = (int64_t)be_u64(p);
                 bi.base_ts = (int64_t)be_u64(p + 27);
                 bi.max_ts = (int64_t)be_u64(p + 35);
                 bi.log_append_time = (attrs >> 3) & 1u;
-                if (attrs & 0x7u) bi.flags = LOGB_COMPRESSED;
-                else if (attrs & 0x20u) bi.flags = LOGB_SKIP_CONTROL;
-                else {
-                    bi.flags = LOGB_OK;
+                if (attrs & 0x20u) bi.flags = LOGB_SKIP_CONTROL;
+                else if (codec == 0 || codec == 2 || codec == 3) {
+                    bi.flags = codec == 0 ? LOGB_OK : codec == 2 ? LOGB_SNAPPY : LOGB_LZ4;
                     bi.records = count;
-                }
+                } else bi.flags = LOGB_COMPRESSED;   // gzip (1), zstd (4)
             }
         }
-        if (bi.flags & (LOGB_BAD | LOGB_COMPRESSED)) atomicOr(error_flags, bi.flags);
+        if (bi.flags & (LOGB_BAD | LOGB_COMPRESSED | LOGB_LZ4 | LOGB_SNAPPY)) atomicOr(error_flags, bi.flags);
         else if (bi.flags == LOGB_OK) atomicMax(error_flags + 1, bi.len);   // [1]: the longest batch (sizes the decode stage)
         info[b] = bi;
         rec_count[b + 1] = (uint64_t)bi.records;
@@ -104,6 +110,218 @@ __device__ __forceinline__ int uvarint_g(const uint8_t *p, const uint8_t *end, u
         shift += 7;
     }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decompression of the records section (everything behind the 61-byte header) of LZ4 and Snappy batches.
+//   LZ4: the frame format (magic 0x184D2204 | FLG | BD | [content size] | [dict id] | HC | blocks… | EndMark | [checksum]);
+//        a block is a u32 LE size (top bit = stored uncompressed) + data [+ block checksum]; block data = sequences of
+//        token | literal length… | literals | offset u16 | match length… ; matches may reach back into earlier blocks.
+//   Snappy: raw (uvarint uncompressed length, then elements: literal / copy with 1-, 2-, 4-byte offset) or the xerial
+//        framing Java clients write ("\x82SNAPPY\0", two version words, then chunks of u32 BE length + raw snappy).
+// A "walk" goes through the elements once; with out == nullptr it only adds up the output size.  One lane parses, all 32
+// lanes of the warp copy (a match that overlaps itself repeats with period `offset`, so every byte's source is known up
+// front: out[op + i] = out[op - offset + i % offset]).
+// ------------------------------------------------------------------------------------------------
+struct LzWalk {
+    uint64_t out_len;   // bytes produced
+    bool ok;
+};
+
+template <bool COPY>
+__device__ __forceinline__ void lz_emit_literals(uint8_t *out, uint64_t op, const uint8_t *in, uint32_t n, int lane) {
+    if (COPY) for (uint32_t i = lane; i < n; i += 32) out[op + i] = in[i];
+}
+template <bool COPY>
+__device__ __forceinline__ void lz_emit_match(uint8_t *out, uint64_t op, uint32_t offset, uint32_t n, int lane) {
+    if (COPY) {
+        __syncwarp();   // the bytes the match refers to have been written
+        for (uint32_t i = lane; i < n; i += 32) out[op + i] = out[op - offset + (i % offset)];
+        __syncwarp();
+    }
+}
+
+// LZ4 frame at in[0, n).  COPY: the whole warp calls this (lane-uniform control flow: every lane parses the same bytes).
+template <bool COPY>
+__device__ LzWalk lz4_frame_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, int lane) {
+    LzWalk w{0, false};
+    if (n < 7 || in[0] != 0x04 || in[1] != 0x22 || in[2] != 0x4D || in[3] != 0x18) return w;
+    const uint32_t flg = in[4];
+    if ((flg >> 6) != 1) return w;
+    uint32_t ip = 6 + ((flg & 0x08) ? 8u : 0u) + ((flg & 0x01) ? 4u : 0u) + 1u;   // FLG, BD, [content size], [dict id], HC
+    const bool block_checksum = (flg & 0x10) != 0;
+    for (;;) {
+        if (ip + 4 > n) return w;
+        const uint32_t bs = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16) | ((uint32_t)in[ip + 3] << 24);
+        ip += 4;
+        if (bs == 0) break;                                  // EndMark
+        const uint32_t blen = bs & 0x7fffffffu;
+        if (blen > n - ip) return w;
+        if (bs & 0x80000000u) {                              // stored block
+            if (COPY && w.out_len + blen > out_cap) return w;
+            lz_emit_literals<COPY>(out, w.out_len, in + ip, blen, lane);
+            w.out_len += blen;
+        } else {
+            uint32_t p = ip;
+            const uint32_t bend = ip + blen;
+            while (p < bend) {
+                const uint32_t token = in[p++];
+                uint32_t lit = token >> 4;
+                if (lit == 15) {
+                    uint32_t b;
+                    do { if (p >= bend) return w; b = in[p++]; lit += b; } while (b == 255);
+                }
+                if (lit > bend - p) return w;
+                if (COPY && w.out_len + lit > out_cap) return w;
+                lz_emit_literals<COPY>(out, w.out_len, in + p, lit, lane);
+                w.out_len += lit;
+                p += lit;
+                if (p >= bend) break;                        // the last sequence of a block has no match
+                if (p + 2 > bend) return w;
+                const uint32_t offset = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8);
+                p += 2;
+                uint32_t ml = (token & 15u) + 4u;
+                if ((token & 15u) == 15u) {
+                    uint32_t b;
+                    do { if (p >= bend) return w; b = in[p++]; ml += b; } while (b == 255);
+                }
+                if (offset == 0 || offset > w.out_len) return w;
+                if (COPY && w.out_len + ml > out_cap) return w;
+                lz_emit_match<COPY>(out, w.out_len, offset, ml, lane);
+                w.out_len += ml;
+            }
+        }
+        ip += blen + (block_checksum ? 4u : 0u);
+    }
+    w.ok = true;
+    return w;
+}
+
+// one raw Snappy block at in[0, n)
+template <bool COPY>
+__device__ bool snappy_raw_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, uint64_t &op, int lane) {
+    uint64_t want;
+    const int hn = uvarint_g(in, in + n, want);
+    if (hn <= 0) return false;
+    const uint64_t start = op;
+    uint32_t p = (uint32_t)hn;
+    while (p < n) {
+        const uint32_t tag = in[p++];
+        if ((tag & 3u) == 0) {                               // literal
+            uint32_t len = (tag >> 2) + 1u;
+            if (len > 60) {
+                const uint32_t nb = len - 60;                // 1..4 length bytes follow
+                if (p + nb > n) return false;
+                len = 0;
+                for (uint32_t i = 0; i < nb; i++) len |= (uint32_t)in[p + i] << (8 * i);
+                len += 1u;
+                p += nb;
+            }
+            if (len > n - p) return false;
+            if (COPY && op + len > out_cap) return false;
+            lz_emit_literals<COPY>(out, op, in + p, len, lane);
+            op += len;
+            p += len;
+        } else {
+            uint32_t len, offset;
+            if ((tag & 3u) == 1) {
+                if (p + 1 > n) return false;
+                len = ((tag >> 2) & 7u) + 4u;
+                offset = ((tag >> 5) << 8) | in[p];
+                p += 1;
+            } else if ((tag & 3u) == 2) {
+                if (p + 2 > n) return false;
+                len = (tag >> 2) + 1u;
+                offset = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8);
+                p += 2;
+            } else {
+                if (p + 4 > n) return false;
+                len = (tag >> 2) + 1u;
+                offset = (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8) | ((uint32_t)in[p + 2] << 16) | ((uint32_t)in[p + 3] << 24);
+                p += 4;
+            }
+            if (offset == 0 || offset > op - start) return false;
+            if (COPY && op + len > out_cap) return false;
+            lz_emit_match<COPY>(out, op, offset, len, lane);
+            op += len;
+        }
+    }
+    return op - start == want;
+}
+
+template <bool COPY>
+__device__ LzWalk snappy_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, int lane) {
+    LzWalk w{0, false};
+    const bool xerial = n >= 16 && in[0] == 0x82 && in[1] == 'S' && in[2] == 'N' && in[3] == 'A' && in[4] == 'P' && in[5] == 'P' &&
+                        in[6] == 'Y' && in[7] == 0;
+    if (!xerial) {
+        w.ok = snappy_raw_walk<COPY>(in, n, out, out_cap, w.out_len, lane);
+        return w;
+    }
+    uint32_t p = 16;                                         // magic (8) + version (4) + compatible version (4)
+    while (p < n) {
+        if (p + 4 > n) return w;
+        const uint32_t cl = ((uint32_t)in[p] << 24) | ((uint32_t)in[p + 1] << 16) | ((uint32_t)in[p + 2] << 8) | in[p + 3];
+        p += 4;
+        if (cl > n - p) return w;
+        if (!snappy_raw_walk<COPY>(in + p, cl, out, out_cap, w.out_len, lane)) return w;
+        p += cl;
+    }
+    w.ok = true;
+    return w;
+}
+
+// thread per batch: the uncompressed size of a compressed batch's records section → slot[b + 1] = bytes its uncompressed
+// image (header + records, rounded up to 16) needs in the scratch buffer (0 for batches that are not compressed)
+__global__ void log_unc_size_kernel(const uint8_t *bytes, const LogBatchInfo *info, int64_t nbatches, uint64_t *slot, uint32_t *error_flags) {
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbatches; b += (int64_t)gridDim.x * blockDim.x) {
+        const LogBatchInfo bi = info[b];
+        uint64_t need = 0;
+        if (bi.flags == LOGB_LZ4 || bi.flags == LOGB_SNAPPY) {
+            const uint8_t *in = bytes + bi.off + LOG_HEADER_BYTES;
+            const uint32_t n = bi.len - LOG_HEADER_BYTES;
+            const LzWalk w = bi.flags == LOGB_LZ4 ? lz4_frame_walk<false>(in, n, nullptr, 0, 0) : snappy_walk<false>(in, n, nullptr, 0, 0);
+            // recordsCount sizes the output columns: it must be plausible for the uncompressed size (7 bytes per record at least)
+            if (!w.ok || w.out_len > 0x7fffff00ull || (uint64_t)bi.records * 7u > w.out_len) atomicOr(error_flags, (uint32_t)LOGB_BAD);
+            else need = ((uint64_t)LOG_HEADER_BYTES + w.out_len + 15u) & ~15ull;
+        }
+        slot[b + 1] = need;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) slot[0] = 0;
+}
+
+// warp per compressed batch: header copy (compression bits cleared, batchLength = uncompressed) + decompressed records into
+// scratch + slot[b]; the batch's info then points there (offsets are relative to `bytes`: the scratch buffer is simply
+// another place in the same address space) and it is an ordinary LOGB_OK batch for the decoder.
+__global__ void __launch_bounds__(128) log_decompress_kernel(const uint8_t *bytes, LogBatchInfo *info, int64_t nbatches, const uint64_t *slot,
+                                                             uint8_t *scratch, uint32_t *error_flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = gw; b < nbatches; b += gs) {
+        const LogBatchInfo bi = info[b];
+        if (bi.flags != LOGB_LZ4 && bi.flags != LOGB_SNAPPY) continue;
+        const uint64_t need = slot[b + 1] - slot[b];
+        uint8_t *dst = scratch + slot[b];
+        if (need < (uint64_t)LOG_HEADER_BYTES) {             // the size pass rejected it
+            if (lane == 0) info[b].flags = LOGB_BAD;
+            continue;
+        }
+        const uint8_t *src = bytes + bi.off;
+        const uint64_t cap = need - LOG_HEADER_BYTES;
+        const LzWalk w = bi.flags == LOGB_LZ4 ? lz4_frame_walk<true>(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, lane)
+                                              : snappy_walk<true>(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, lane);
+        for (int i = lane; i < LOG_HEADER_BYTES; i += 32) dst[i] = src[i];
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t ulen = LOG_HEADER_BYTES + (uint32_t)w.out_len, bl = ulen - 12u;
+            dst[8] = (uint8_t)(bl >> 24); dst[9] = (uint8_t)(bl >> 16); dst[10] = (uint8_t)(bl >> 8); dst[11] = (uint8_t)bl;   // batchLength
+            dst[22] &= 0xf8;                                  // attributes: no compression
+            if (!w.ok) atomicOr(error_flags, (uint32_t)LOGB_BAD);
+            info[b].off = (uint64_t)(dst - bytes);            // relative to `bytes` (may wrap: one address space)
+            info[b].len = ulen;
+            info[b].flags = w.ok ? LOGB_OK : LOGB_BAD;
+        }
+    }
 }
 
 // One WARP per batch.  Records are length-prefixed, so finding where record i starts is a serial chain: lane 0 hops through
@@ -253,7 +471,20 @@ __global__ void __launch_bounds__(256) log_gather_keys_kernel(const uint8_t *byt
         for (int k = 0; k < 4; k++) {
             if (len[k] > 0) {
                 const uint8_t *sp = bytes + src[k];
-                for (int j = 0; j < len[k]; j++) o[j] = __ldg(sp + j);
+                int j = 0;
+                if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
+                    // word-aligned destination (always, for keys whose lengths are multiples of 4: ids, hashes, UUIDs): whole
+                    // words from aligned source words put together with a funnel shift
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u) * 8u;
+                    uint32_t lo = __ldg(wp);
+                    for (; j + 4 <= len[k]; j += 4) {
+                        const uint32_t hi = sh ? __ldg(wp + j / 4 + 1) : 0u;
+                        reinterpret_cast<uint32_t *>(o)[j / 4] = sh ? __funnelshift_r(lo, hi, sh) : lo;
+                        lo = sh ? hi : (j + 8 <= len[k] || (len[k] & 3) ? __ldg(wp + j / 4 + 1) : 0u);
+                    }
+                }
+                for (; j < len[k]; j++) o[j] = __ldg(sp + j);
                 o += len[k];
             }
         }

@@ -43,9 +43,34 @@ def encode_record(offset_delta, ts_delta, key, value_len, headers=()):
     return varint(len(body)) + bytes(body)
 
 
-def encode_batch(base_offset, base_ts, records, attributes=0, max_ts=None):
+def compress_records(recs: bytes, codec: str) -> bytes:
+    """The records section as a producer with compression.type=<codec> writes it.  The compressors are pyarrow's (LZ4 frame
+    format, raw Snappy): independent of the GPU decompressor under test.  'snappy-xerial' adds the framing of the Java
+    client's snappy-java stream (magic, two version words, chunks of u32 BE length + raw snappy)."""
+    import pyarrow as pa
+    if codec == "lz4":
+        return pa.compress(recs, codec="lz4", asbytes=True)
+    if codec == "snappy":
+        return pa.compress(recs, codec="snappy", asbytes=True)
+    if codec == "snappy-xerial":
+        out = bytearray(b"\x82SNAPPY\x00" + struct.pack(">ii", 1, 1))
+        step = max(1, len(recs) // 3 + 1)              # several chunks per batch
+        for i in range(0, len(recs), step):
+            c = pa.compress(recs[i:i + step], codec="snappy", asbytes=True)
+            out += struct.pack(">i", len(c)) + c
+        return bytes(out)
+    raise ValueError(codec)
+
+
+CODEC_BITS = {None: 0, "gzip": 1, "snappy": 2, "snappy-xerial": 2, "lz4": 3, "zstd": 4}
+
+
+def encode_batch(base_offset, base_ts, records, attributes=0, max_ts=None, compression=None):
     """records: list of (offset_delta, ts_delta, key|None, value_len|None[, headers])"""
     recs = b"".join(encode_record(*r) for r in records)
+    if compression:
+        recs = compress_records(recs, compression)
+        attributes |= CODEC_BITS[compression]
     last_delta = max((r[0] for r in records), default=0)
     if max_ts is None:
         max_ts = max((base_ts + r[1] for r in records), default=base_ts)
@@ -53,7 +78,7 @@ def encode_batch(base_offset, base_ts, records, attributes=0, max_ts=None):
     return struct.pack(">qi", base_offset, len(after_len)) + after_len
 
 
-def encode_partition(partition_records, rng, max_batch=40, log_append_time=False):
+def encode_partition(partition_records, rng, max_batch=40, log_append_time=False, compression=None):
     """partition_records: list of (ts_ms, key|None, value_len|None) in offset order → one log segment (bytes).
     ts_ms == -1 (not available) forces a batch with base timestamp -1."""
     out = bytearray()
@@ -79,6 +104,9 @@ def encode_partition(partition_records, rng, max_batch=40, log_append_time=False
             hdrs = ((b"h", b"v"), (b"trace", None)) if (i + j) % 7 == 0 else ()
             recs.append((j, 0 if base_ts == -1 else ts - base_ts, key, vl, hdrs))
         attrs = 0x08 if log_append_time else 0
-        out += encode_batch(i, base_ts, recs, attributes=attrs)
+        codec = compression
+        if isinstance(compression, (list, tuple)):          # a mix: every batch picks its own codec
+            codec = compression[int(rng.integers(0, len(compression)))]
+        out += encode_batch(i, base_ts, recs, attributes=attrs, compression=codec)
         i += len(chunk)
     return bytes(out)
