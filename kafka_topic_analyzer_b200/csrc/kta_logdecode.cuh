@@ -474,15 +474,23 @@ __global__ void __launch_bounds__(256) log_gather_keys_kernel(const uint8_t *byt
                 int j = 0;
                 if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
                     // word-aligned destination (always, for keys whose lengths are multiples of 4: ids, hashes, UUIDs): whole
-                    // words from aligned source words put together with a funnel shift
-                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)3);
-                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u) * 8u;
-                    uint32_t lo = __ldg(wp);
-                    for (; j + 4 <= len[k]; j += 4) {
-                        const uint32_t hi = sh ? __ldg(wp + j / 4 + 1) : 0u;
-                        reinterpret_cast<uint32_t *>(o)[j / 4] = sh ? __funnelshift_r(lo, hi, sh) : lo;
-                        lo = sh ? hi : (j + 8 <= len[k] || (len[k] & 3) ? __ldg(wp + j / 4 + 1) : 0u);
+                    // words, from aligned source words put together with a funnel shift
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(sp);
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+                    const int nw = len[k] >> 2;
+                    uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                    if (sh == 0) {
+                        for (int w = 0; w < nw; w++) ow[w] = __ldg(wp + w);
+                    } else {
+                        uint32_t lo = __ldg(wp);
+                        for (int w = 0; w < nw; w++) {
+                            const uint32_t hi = __ldg(wp + w + 1);   // holds the word's last bytes: inside the record
+                            ow[w] = __funnelshift_r(lo, hi, sh);
+                            lo = hi;
+                        }
                     }
+                    j = nw * 4;
                 }
                 for (; j < len[k]; j++) o[j] = __ldg(sp + j);
                 o += len[k];
