@@ -9,12 +9,34 @@ from kafka_topic_analyzer_b200._native import lib, check
 
 P, N, VM = 16, 8_000_000, int(sys.argv[1]) if len(sys.argv) > 1 else 256
 BR = int(sys.argv[2]) if len(sys.argv) > 2 else 56   # ~16 KB batches (the producer default batch.size) at 256 B values
+CODEC = sys.argv[3] if len(sys.argv) > 3 else None   # lz4 | snappy: every batch's records section compressed (pyarrow) on the host
+if CODEC:
+    N = 2_000_000
+
+
+def compress_segment(seg: np.ndarray, codec: str) -> np.ndarray:
+    """re-writes every batch of an uncompressed segment with its records section compressed"""
+    import pyarrow as pa
+    raw, out, pos = seg.tobytes(), bytearray(), 0
+    while pos + 61 <= len(raw):
+        bl = int.from_bytes(raw[pos + 8:pos + 12], "big", signed=True)
+        hdr = bytearray(raw[pos:pos + 61])
+        body = pa.compress(raw[pos + 61:pos + 12 + bl], codec=codec, asbytes=True)
+        hdr[8:12] = (49 + len(body)).to_bytes(4, "big")
+        hdr[22] |= {"snappy": 2, "lz4": 3}[codec]
+        out += hdr + body
+        pos += 12 + bl
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
 spec = synth.make_spec(N, P, value_mean=VM, distinct_keys=1_000_000)
 chunks, offs, parts = [], [], []
 t0 = time.time()
 total = 0
 for p in range(P):
     s = synth.encode_segment(spec, p, batch_records=BR)
+    unc = int(s.size)
+    if CODEC:
+        s = compress_segment(s, CODEC)
     pos = 0
     while pos + 61 <= s.size:      # batch offsets by hopping headers on the host
         offs.append(total + pos)
@@ -30,7 +52,7 @@ for s in chunks:
     at += (s.size + 15) // 16 * 16
 d_off = torch.tensor(offs, dtype=torch.int64).cuda()
 d_part = torch.tensor(parts, dtype=torch.int32).cuda()
-print("encoded %d records, %.2f GB raw log, %d batches of ~%d KB in %.1f s" % (N, raw / 1e9, len(offs), raw // len(offs) // 1024, time.time() - t0), flush=True)
+print("encoded %d records, %.2f GB raw log%s, %d batches of ~%d KB in %.1f s" % (N, raw / 1e9, " (%s-compressed)" % CODEC if CODEC else "", len(offs), raw // len(offs) // 1024, time.time() - t0), flush=True)
 for mode, kw in (("counters", {}), ("fused HLL", dict(hll_precision=14)), ("-c exact", dict(count_alive_keys=True))):
     e = kta.KtaEngine(P, **kw)
     best = 1e9
