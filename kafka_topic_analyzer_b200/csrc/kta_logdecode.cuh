@@ -482,15 +482,18 @@ __global__ void __launch_bounds__(256) log_gather_keys_kernel(const uint8_t *byt
                     uint32_t *ow = reinterpret_cast<uint32_t *>(o);
                     if (sh == 0) {
                         for (int w = 0; w < nw; w++) ow[w] = __ldg(wp + w);
+                        j = nw * 4;
                     } else {
+                        // the aligned word behind the last full one may reach past the key (and past the buffer): the last
+                        // word is left to the byte loop
                         uint32_t lo = __ldg(wp);
-                        for (int w = 0; w < nw; w++) {
-                            const uint32_t hi = __ldg(wp + w + 1);   // holds the word's last bytes: inside the record
+                        for (int w = 0; w + 1 < nw; w++) {
+                            const uint32_t hi = __ldg(wp + w + 1);
                             ow[w] = __funnelshift_r(lo, hi, sh);
                             lo = hi;
                         }
+                        j = nw > 0 ? (nw - 1) * 4 : 0;
                     }
-                    j = nw * 4;
                 }
                 for (; j < len[k]; j++) o[j] = __ldg(sp + j);
                 o += len[k];
