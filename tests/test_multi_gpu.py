@@ -70,7 +70,7 @@ whole = synth.fill_host(spec)
 ow = Oracle(count_alive_keys=True); ow.handle_batch(whole.partition, whole.ts_ms, whole.key_len, whole.value_len, whole.key_bytes)
 assert alive == ow.scalar("sum_all_alive"), (alive, ow.scalar("sum_all_alive"))
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank {rank} ok\n"); sys.stdout.flush()
 '''
 
 GPU_WORKER = r'''
@@ -99,7 +99,7 @@ for exact in (False, True):
     assert_parity(e, o, P, check_alive=exact, hll_regs=o.hll_alive_regs(12) if exact else o.hll_stream_regs(12))
     e.close()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write(f"rank {rank} ok\n"); sys.stdout.flush()
 '''
 
 
@@ -116,7 +116,7 @@ def _run(world, script, extra_env=None, timeout=300):
 def test_shard_and_merge_logic_gloo(world):
     r = _run(world, WORKER)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert r.stdout.count(" ok") == world
+    assert r.stdout.count("ok") == world
 
 
 @pytest.mark.gpu
@@ -126,7 +126,7 @@ def test_two_gpu_scan_and_nccl_merge():
         pytest.skip("needs 2 GPUs")
     r = _run(2, GPU_WORKER)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert r.stdout.count(" ok") == 2
+    assert r.stdout.count("ok") == 2
 
 
 def test_reference_arm_under_torchrun():
