@@ -445,7 +445,8 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     const uint32_t rpairs = h->alive_pairs >> h->alive_rbits;
     bool part = exact && !prm.alive_only && !capture && part_min > 0 && prm.n >= part_min && h->alive_rbits >= PART_BITS &&
                 rpairs <= PART_REGION_MAX_PAIRS && (size_t)rpairs * 16 <= h->smem_optin;
-    if (exact && !part && prm.n >= ALIVE_CACHE_MIN_RECORDS) {
+    const char *cache_env = getenv("KTA_ALIVE_CACHE_MIN");   // tests: the seen cache on small batches too
+    if (exact && prm.n >= (cache_env ? (int64_t)atoll(cache_env) : ALIVE_CACHE_MIN_RECORDS)) {
         // the seen cache pays for its clearing (32 MiB, ~10 µs) on batches of a million records and more.
         // Waves cut the batch's seq range [lo, hi] into <= 127 equal slices (any monotone function of seq will do).
         static const bool off = getenv("KTA_ALIVE_NO_CACHE") != nullptr;   // tuning / ablation knob
@@ -494,7 +495,9 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     if (part) {
         // chunk pool: every CTA fills its own slice; a CTA sees at most ceil(ntiles / warps) tiles per warp
         const int64_t nwarps = threads / 32, tiles_cta = ((prm.ntiles + (int64_t)grid * nwarps - 1) / ((int64_t)grid * nwarps)) * nwarps;
-        const int64_t cap = (tiles_cta * TILE + PART_C - 1) / PART_C + PART_B + 8, total = cap * grid;
+        // sized for a batch half of whose records survive the seen cache (a compacted topic: ~10 %); a CTA whose slice
+        // runs out stamps the rest directly
+        const int64_t cap = (tiles_cta * TILE / 2 + PART_C - 1) / PART_C + PART_B + 8, total = cap * grid;
         if (total >= ((int64_t)1 << 29)) part = false;
         else if (total > h->part_cap_chunks || !h->d_part_hist) {
             cudaFree(h->d_part_chunks); cudaFree(h->d_part_tags); cudaFree(h->d_part_order);
@@ -523,7 +526,7 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
             prm.part_cta_cap = (uint32_t)cap;
             CU(cudaMemsetAsync(h->d_part_aux, 0, (size_t)2 * PART_B * 4, h->stream));
         } else {
-            // fall back to the direct path (the seen cache is skipped for this one batch: correct, only slower)
+            // fall back to the direct path
             scan_shape(h, true, true, prm.n, key_bytes, threads, keybuf, sm);
             prm.keybuf = keybuf;
             grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);

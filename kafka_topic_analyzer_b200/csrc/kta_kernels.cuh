@@ -567,15 +567,15 @@ __device__ __forceinline__ unsigned long long alive_atom_cas(unsigned long long 
 // large batches) loads into shared memory one at a time, so a large table is cut until a region fits there.
 constexpr int PART_BITS = 10, PART_B = 1 << PART_BITS;     // buckets of the in-scan partition = top PART_BITS bits of x
 #ifndef KTA_PART_C
-#define KTA_PART_C 8
+#define KTA_PART_C 4
 #endif
 #ifndef KTA_PART_FENCES
 #define KTA_PART_FENCES 0
 #endif
 #ifndef KTA_PART_THREADS
-#define KTA_PART_THREADS 896   // the stages take 72 KiB: 28 warps fit next to them (64 partitions, 16-byte keys)
+#define KTA_PART_THREADS 1024  // the stages take 40 KiB: 32 warps fit next to them (64 partitions, 16-byte keys)
 #endif
-constexpr int PART_C = KTA_PART_C;                         // items per chunk (8 x 8 B = 64 B = two DRAM sectors)
+constexpr int PART_C = KTA_PART_C;                         // items per chunk (4 x 8 B = one 32-byte DRAM sector)
 constexpr uint32_t PART_REGION_MAX_PAIRS = 12288;          // 192 KiB of shared memory per region
 constexpr uint32_t PART_MIN_REGION_PAIRS = 64;
 __host__ __device__ inline int alive_layout_rbits(uint32_t npairs) {
@@ -792,10 +792,9 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
     const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P, prm.P, SHARD ? prm.shard_world : 1, SHARD ? prm.shard_rank : 0};
     // MODE_EXACT: the alive table's lines are asked to stay in L2 (evict_last), the record stream to leave first
-    constexpr bool HINTS = MODE == MODE_EXACT && KTA_L2_HINTS;
+    constexpr bool HINTS = NEWEST_FIRST && KTA_L2_HINTS;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
-    constexpr bool TABLE_POLICY = NEWEST_FIRST && KTA_L2_HINTS;   // MODE_PART touches the table only for the rare direct stamps
-    const AliveTable AT{prm.alive_table, prm.alive_pairs, prm.alive_status, TABLE_POLICY ? l2_policy_evict_last() : 0,
+    const AliveTable AT{prm.alive_table, prm.alive_pairs, prm.alive_status, HINTS ? l2_policy_evict_last() : 0,
                         prm.alive_rbits, prm.alive_pairs >> prm.alive_rbits};
     const AliveWaves AW{prm.alive_cache, prm.alive_wave_base, prm.alive_wave_shift};
     const bool count_it = !(MODE == MODE_EXACT && prm.alive_only);   // false: a stamps-only re-run after the table grew
@@ -868,7 +867,7 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
         __threadfence_block();   // acquire: the other lanes' items are visible
 #endif
         const uint32_t ci = atom_shared_add(pcursor, 1u);
-        if (ci < prm.part_cta_cap) {
+        if (ci < prm.part_cta_cap) {   // (the cursor keeps counting past the cap: part_hist only counts written chunks)
             const size_t idx = (size_t)blockIdx.x * prm.part_cta_cap + ci;
             uint4 *dst = reinterpret_cast<uint4 *>(prm.part_chunks + idx * PART_C);
             const uint32_t src = pstage + b * (uint32_t)(PART_C * 8);
@@ -877,7 +876,12 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
             prm.part_tags[idx] = b | (cnt << 16);
             red_shared_add(phist + 4u * b, 1u);
         } else {
-            atomicAdd(prm.alive_status, 1u);   // cannot happen (the pool is sized for every item); if it does the host re-runs the batch
+            // this CTA's slice of the pool is used up (it is sized for a batch half of whose records survive the seen
+            // cache): the staged items go straight to the table
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t low = lds32(pstage + (b * PART_C + j) * 8u), x = lds32(pstage + (b * PART_C + j) * 8u + 4u);
+                alive_stamp_slow(AT, alive_home(x, AT), x, low);
+            }
         }
 #if KTA_PART_FENCES
         __threadfence_block();   // release: the stage has been read before it is reopened
@@ -1180,9 +1184,9 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
                     if (valid[k]) prm.hash_out[rbase + 32 * k] = kl[k] >= 0 ? h[k] : 0u;
             }
         };
-        if (MODE != MODE_EXACT) count_records();
+        if (!NEWEST_FIRST) count_records();
         if (HASH) hash_keys();
-        if (MODE == MODE_EXACT) {
+        if (NEWEST_FIRST) {
             // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
             // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
             // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
@@ -1230,6 +1234,32 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
             }
             __syncwarp();
 #if KTA_EXP_ALIVE_STAGE >= 2
+            if (MODE == MODE_PART) {
+                // LARGE batches: the survivors do not go to the table (two to three dependent DRAM round trips per tile,
+                // the bulk of MODE_EXACT's time) but into shared-memory stages keyed by the top PART_BITS bits of the mixed
+                // hash; a full stage leaves as one chunk of the CTA's own, sequentially written slice of the chunk pool,
+                // and alive_resolve_kernel replays the chunks region by region against the table afterwards.
+                // Stage protocol (no waiting anywhere): word = arrivals (low half) | commits (high half).  An arrival
+                // numbered < PART_C owns that slot: write, commit; the commit that completes the stage flushes it and zeroes
+                // the word.  An arrival numbered >= PART_C met a full stage (being flushed) and stamps the table directly —
+                // nobody holds the table in shared memory while this kernel runs.
+                for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
+                    if (q0 + lane < qn) {
+                        const uint4 item = queue[q0 + lane];
+                        // the cache learns that a record of this hash and wave exists (and will be resolved)
+                        if (cached) alive_cache_put(AW.cache, item.z, item.x, alive_wave(item.y >> 1, AW), item.y >> 1);
+                        const uint32_t b = item.x >> (32 - PART_BITS);
+                        const uint32_t pos = atom_shared_add(pword + 4u * b, 1u) & 0xffffu;
+                        if (pos < (uint32_t)PART_C) {
+                            sts64(pstage + (b * PART_C + pos) * 8u, item.y, item.x);
+                            const uint32_t old = atom_shared_add(pword + 4u * b, 0x10000u);
+                            if ((old >> 16) == (uint32_t)(PART_C - 1)) part_flush(b, (uint32_t)PART_C);
+                        } else {
+                            alive_stamp_slow(AT, alive_home(item.x, AT), item.x, item.y);
+                        }
+                    }
+                }
+            } else
             for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
                 if (q0 + lane < qn) {
                     const uint4 item = queue[q0 + lane];
@@ -1248,56 +1278,6 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
 #endif
-        }
-        if (MODE == MODE_PART) {
-            // metric.rs:291-302 for a LARGE batch: nothing random is touched here.  Every record with a key becomes one
-            // 8-byte item (mixed hash, stamp low word) that is staged in shared memory under the top PART_BITS bits of its
-            // hash; a full stage leaves as one 64-byte chunk of the CTA's own, sequentially written slice of the chunk
-            // pool.  alive_resolve_kernel replays the items bucket by bucket against the table afterwards.
-            // Stage protocol (no waiting anywhere): word = arrivals (low half) | commits (high half).  An arrival numbered
-            // < PART_C owns that slot: write, fence, commit; the commit that completes the stage flushes it and zeroes the
-            // word.  An arrival numbered >= PART_C met a full stage (being flushed): it stamps the table directly, like
-            // MODE_EXACT does — the table is not held in shared memory by anybody while this kernel runs.
-            const uint32_t r32 = (uint32_t)rbase;
-            uint32_t x[ROWS], low[ROWS], pos[ROWS];
-            bool live[ROWS];
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                live[k] = (clean || use[k]) && kl[k] >= 0;
-                uint32_t field;
-                if (prm.seq) {
-                    const uint64_t f = live[k] ? ld_stream_u64(prm.seq + rbase + 32 * k) - prm.alive_origin + 1ull : 1ull;
-                    if (f - 1ull >= (uint64_t)ALIVE_FIELD_MAX) {
-                        atomicAdd(prm.alive_status + 1, 1u);
-                        live[k] = false;
-                    }
-                    field = (uint32_t)f;
-                } else {
-                    field = (uint32_t)prm.alive_fbase + r32 + 32u * k;
-                }
-                low[k] = (field << 1) | (vl[k] >= 0 ? 1u : 0u);
-                x[k] = hll_mix(h[k]);
-                pos[k] = 0xffffu;
-                if (live[k]) pos[k] = atom_shared_add(pword + 4u * (x[k] >> (32 - PART_BITS)), 1u) & 0xffffu;
-            }
-#pragma unroll
-            for (int k = 0; k < ROWS; k++)
-                if (live[k] && pos[k] < (uint32_t)PART_C) sts64(pstage + ((x[k] >> (32 - PART_BITS)) * PART_C + pos[k]) * 8u, low[k], x[k]);
-#if KTA_PART_FENCES
-            __threadfence_block();
-#endif
-#pragma unroll
-            for (int k = 0; k < ROWS; k++) {
-                if (live[k]) {
-                    const uint32_t b = x[k] >> (32 - PART_BITS);
-                    if (pos[k] < (uint32_t)PART_C) {
-                        const uint32_t old = atom_shared_add(pword + 4u * b, 0x10000u);
-                        if ((old >> 16) == (uint32_t)(PART_C - 1)) part_flush(b, (uint32_t)PART_C);
-                    } else {
-                        alive_stamp_slow(AT, alive_home(x[k], AT), x[k], low[k]);
-                    }
-                }
-            }
         }
 #ifndef KTA_EXP_NO_HLL
         if (MODE == MODE_HLL) {

@@ -751,11 +751,15 @@ def test_partition_sharded_engines_merge_to_the_whole_topic(P, world, run_len):
 # the partitioned alive-key path (scan_kernel<MODE_PART> + alive_resolve_kernel): what large -c batches take.  The tests
 # lower its size threshold (KTA_ALIVE_PART_MIN, read per scan) so that small oracle-checkable batches go through it.
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seen_cache", [True, False])
 @pytest.mark.parametrize("case", ["binary64", "ascii_runs", "ragged_tail", "many_partitions", "hot_keys", "region_pairs_odd"])
-def test_partitioned_alive_path_equals_bitset_replay(case, monkeypatch):
-    """metric.rs:288-305 through the partitioned path: items staged per hash bucket in the scan, replayed region by region
-    in shared memory — bit-equal to the BitSet replay, table occupancy = distinct hashes, and the path must have run."""
+def test_partitioned_alive_path_equals_bitset_replay(case, seen_cache, monkeypatch):
+    """metric.rs:288-305 through the partitioned path: the records that survive the seen cache are staged per hash bucket
+    in the scan and replayed region by region in shared memory — bit-equal to the BitSet replay, table occupancy = distinct
+    hashes, and the path must have run.  Without the seen cache every keyed record is staged and the chunk pool (sized for
+    half of them) runs out, so the direct stamps of the overflow are covered too."""
     monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1")
+    monkeypatch.setenv("KTA_ALIVE_CACHE_MIN", "1" if seen_cache else str(1 << 40))
     kib = 1024                                                      # 1 MiB = 1024 regions of 64 pairs
     kw = dict(tombstone_per_10k=2500, null_key_per_10k=300, ts_missing_per_10k=5)
     if case == "binary64":
@@ -792,6 +796,7 @@ def test_partitioned_and_direct_batches_share_one_table(monkeypatch):
     cols = [torch_dev(c) for c in (t.partition, t.ts_ms, t.key_len, t.value_len)]
     tb = torch_dev(t.key_tile_base)
     cuts = [0, 700 * T, 701 * T, 1900 * T, 2500 * T, n]
+    monkeypatch.setenv("KTA_ALIVE_CACHE_MIN", "1")
     with KtaEngine(P, count_alive_keys=True, hll_precision=11, now=NOW, alive_table_kib=2048) as e:
         for i, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
             monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1" if i % 2 == 0 else "0")
