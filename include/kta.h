@@ -232,9 +232,6 @@ int kta_scan_time_ms(kta_handle *h, double *total_ms, uint64_t *launches);
 /* alive-key table: slots allocated, slots occupied (= distinct key hashes seen), how often it was grown and how many
  * batches had to be re-stamped because it was too small when they were scanned (any pointer may be NULL) */
 int kta_alive_table_stats(kta_handle *h, uint64_t *slots, uint64_t *occupied, uint64_t *grows, uint64_t *reruns);
-/* how many scans since create/reset took the partitioned alive-key path (batches of >= 2^24 records with
- * count_alive_keys: items partitioned by hash in the scan, then replayed region by region in shared memory) */
-int kta_alive_part_scans(const kta_handle *h, uint64_t *out);
 /* raw cudaStream_t of the handle (so a torch caller can order against it) */
 void *kta_stream(kta_handle *h);
 /* adopt a caller-owned cudaStream_t (e.g. torch's current stream) for all further work of this handle */

@@ -123,7 +123,6 @@ SYMBOLS = {
     "kta_bad_partition_records": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "kta_alive_table_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64)]),
-    "kta_alive_part_scans": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "kta_hist": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(C.c_uint64)]),
     "kta_alive_keys_hll": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "kta_hll_registers": (C.c_int, [_P, _P, C.c_size_t]),

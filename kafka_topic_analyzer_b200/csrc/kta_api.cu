@@ -61,8 +61,7 @@ extern "C" int kta_device_count(void) {
 // handle
 // ------------------------------------------------------------------------------------------------
 static constexpr int NCHUNK = 3;
-static constexpr int32_t ALIVE_DEFAULT_KIB = 192 * 1024;       // initial alive-key table: 192 MiB = 1024 regions of 192 KiB (KTA_ALIVE_TABLE_KIB overrides: tuning)
-static constexpr int64_t ALIVE_PART_MIN_RECORDS = 1 << 24;     // batches this large take the partitioned path (KTA_ALIVE_PART_MIN overrides; 0 = never)
+static constexpr int32_t ALIVE_DEFAULT_KIB = 256 * 1024;       // initial alive-key table: 256 MiB = 2^25 slots (KTA_ALIVE_TABLE_KIB overrides: tuning)
 static constexpr int32_t ALIVE_MAX_KIB = 32 * 1024 * 1024;     // 32 GiB = one slot per possible 32-bit hash
 static constexpr int64_t ALIVE_CACHE_MIN_RECORDS = 1 << 20;    // smaller batches go straight to the table
 static constexpr int64_t DEFAULT_RING_RECORDS = 1 << 22;  // 4 Mi records per chunk
@@ -106,12 +105,6 @@ struct kta_handle {
     uint32_t *d_hll_floor = nullptr;
     unsigned long long *d_alive_table = nullptr;   // open-addressed last-writer table, 2 * alive_pairs slots
     uint32_t alive_pairs = 0;
-    int alive_rbits = 0;                     // log2(regions) of the table (alive_layout_rbits)
-    // scratch of the partitioned path (large batches): chunk pool, tags, grouped chunk ids, per-CTA counts and offsets
-    unsigned long long *d_part_chunks = nullptr;
-    uint32_t *d_part_tags = nullptr, *d_part_order = nullptr, *d_part_hist = nullptr, *d_part_aux = nullptr;
-    int64_t part_cap_chunks = 0;
-    uint64_t part_scans = 0;
     uint64_t alive_origin = 0;               // seq that a stamp's field value 1 stands for
     bool alive_rebased = false;              // a rebase dropped absolute sequence numbers (exports are refused then)
     uint32_t *d_alive_cache = nullptr;       // seen cache of the batch being scanned (32 MiB, cleared per launch)
@@ -178,15 +171,12 @@ static int set_device(const kta_handle *h) {
     return KTA_OK;
 }
 
-static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf, bool exact, bool part = false) {
-    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf, exact) +
-           (part ? part_smem_bytes() : 0);
+static size_t scan_smem_bytes(bool hash, bool smem, int P, int threads, int keybuf, bool exact) {
+    return (smem ? smem_counter_bytes(P) : CTA_SCRATCH) + (size_t)(threads / 32) * warp_smem_bytes(hash, keybuf, exact);
 }
 
 // Launch shape for one scan: key-stage bytes from the batch's mean key length, then as many warps as fit.
-static void scan_shape(const kta_handle *h, bool hash, bool exact, int64_t n, int64_t key_bytes, int &threads, int &keybuf, size_t &smem,
-                       bool part = false) {
-    const int max_threads = part ? std::min(MAX_THREADS, KTA_PART_THREADS) : MAX_THREADS;
+static void scan_shape(const kta_handle *h, bool hash, bool exact, int64_t n, int64_t key_bytes, int &threads, int &keybuf, size_t &smem) {
     keybuf = KEYBUF_MIN;
     if (hash && n > 0) {
         const int64_t per_tile = (key_bytes * TILE + n - 1) / n;           // mean key bytes per 128-record tile
@@ -200,22 +190,21 @@ static void scan_shape(const kta_handle *h, bool hash, bool exact, int64_t n, in
     // memory the loads in flight are throttled (measured at P = 256).  KTA_SCAN_L1_RESERVE (bytes) is a tuning knob.
     static const size_t l1_reserve = [] { const char *e = getenv("KTA_SCAN_L1_RESERVE"); return e ? (size_t)atoll(e) : (size_t)0; }();
     const size_t budget = h->smem_optin > l1_reserve ? h->smem_optin - l1_reserve : h->smem_optin;
-    for (threads = max_threads;; threads -= 128) {
-        smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf, exact, part);
+    for (threads = MAX_THREADS;; threads -= 128) {
+        smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf, exact);
         if (smem <= budget || threads <= 256) break;
     }
     if (smem > h->smem_optin) {   // still too big with 8 warps: fall back to the smallest stage (long keys go through global)
         keybuf = KEYBUF_MIN;
-        for (threads = max_threads;; threads -= 128) {
-            smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf, exact, part);
+        for (threads = MAX_THREADS;; threads -= 128) {
+            smem = scan_smem_bytes(hash, h->smem_counters, P, threads, keybuf, exact);
             if (smem <= h->smem_optin || threads <= 128) break;
         }
     }
 }
 
 // one persistent CTA per SM; every variant may use the whole opt-in shared memory (the shape is chosen per launch).
-// variant index: 0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture, 5..7 = 0..2 for a partition-sharded handle,
-// 8 / 9 the partitioning exact scan (MODE_PART) for a plain / a partition-sharded handle
+// variant index: 0 counters, 1 HLL, 2 exact, 3 HLL+capture, 4 exact+capture, 5..7 = 0..2 for a partition-sharded handle
 template <int MODE, bool SMEM, bool CAPTURE, bool SHARD>
 static int prepare_variant(kta_handle *h) {
     CU(cudaFuncSetAttribute(scan_kernel<MODE, SMEM, CAPTURE, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
@@ -233,9 +222,6 @@ static int prepare_all(kta_handle *h) {
     if ((rc = prepare_variant<MODE_COUNTERS, SMEM, false, true>(h))) return rc;
     if ((rc = prepare_variant<MODE_HLL, SMEM, false, true>(h))) return rc;
     if ((rc = prepare_variant<MODE_EXACT, SMEM, false, true>(h))) return rc;
-    if ((rc = prepare_variant<MODE_PART, SMEM, false, false>(h))) return rc;
-    if ((rc = prepare_variant<MODE_PART, SMEM, false, true>(h))) return rc;
-    CU(cudaFuncSetAttribute(alive_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
     return KTA_OK;
 }
 
@@ -249,9 +235,7 @@ static void launch_variant(int v, int grid, int threads, size_t sm, cudaStream_t
         case 4: scan_kernel<MODE_EXACT, SMEM, true><<<grid, threads, sm, st>>>(prm); break;
         case 5: scan_kernel<MODE_COUNTERS, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
         case 6: scan_kernel<MODE_HLL, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
-        case 7: scan_kernel<MODE_EXACT, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
-        case 8: scan_kernel<MODE_PART, SMEM, false><<<grid, threads, sm, st>>>(prm); break;
-        default: scan_kernel<MODE_PART, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
+        default: scan_kernel<MODE_EXACT, SMEM, false, true><<<grid, threads, sm, st>>>(prm); break;
     }
 }
 
@@ -268,7 +252,6 @@ static int state_reset_device(kta_handle *h) {
         h->alive_origin = 0;
         h->alive_rebased = false;
         h->alive_window_errors = 0;
-        h->part_scans = 0;
         h->pending.clear();
     }
     return KTA_OK;
@@ -290,7 +273,6 @@ extern "C" int kta_destroy(kta_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &c : h->chunks) free_chunk(c);
     cudaFree(h->d_sums); cudaFree(h->d_minmax); cudaFree(h->d_hll); cudaFree(h->d_alive_table);
-    cudaFree(h->d_part_chunks); cudaFree(h->d_part_tags); cudaFree(h->d_part_order); cudaFree(h->d_part_hist); cudaFree(h->d_part_aux);
     cudaFree(h->d_alive_status); cudaFree(h->d_alive_cache); cudaFreeHost(h->h_alive_status); cudaFree(h->d_scalar); cudaFree(h->d_tb_scratch);
     cudaFree(h->d_log_bytes); cudaFree(h->d_log_off); cudaFree(h->d_log_info); cudaFree(h->d_log_cnt);
     cudaFree(h->d_dec_part); cudaFree(h->d_dec_klen); cudaFree(h->d_dec_vlen); cudaFree(h->d_dec_ts); cudaFree(h->d_dec_keys); cudaFree(h->d_dec_ksrc); cudaFree(h->d_unc); cudaFree(h->d_unc_slot);
@@ -351,7 +333,6 @@ static int create_impl(const kta_config *cfg, kta_handle *h) {
         static const int64_t env_kib = [] { const char *e = getenv("KTA_ALIVE_TABLE_KIB"); return e ? atoll(e) : 0ll; }();   // tuning knob
         const int64_t kib = cfg->alive_table_kib ? cfg->alive_table_kib : env_kib > 0 ? env_kib : ALIVE_DEFAULT_KIB;
         h->alive_pairs = (uint32_t)std::max<int64_t>(kib * 64, 16);   // 16 bytes per pair
-        h->alive_rbits = alive_layout_rbits(h->alive_pairs);
         CU(cudaMalloc(&h->d_alive_table, (size_t)h->alive_pairs * 16));
         CU(cudaMalloc(&h->d_alive_status, 8));
         CU(cudaMalloc(&h->d_alive_cache, ((size_t)4 << ALIVE_CACHE_SET_BITS)));
@@ -433,20 +414,11 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     prm.hll_floor = h->d_hll_floor;
     prm.alive_table = h->d_alive_table;
     prm.alive_pairs = h->alive_pairs;
-    prm.alive_rbits = h->alive_rbits;
     prm.alive_origin = h->alive_origin;
     prm.alive_count = h->d_scalar;
     prm.alive_status = h->d_alive_status;
     prm.alive_cache = nullptr;
-    // Large batches take the partitioned path (scan_kernel<MODE_PART> + alive_resolve_kernel): no random access per record.
-    // It needs a table cut into regions that fit shared memory; a stamps-only re-run and the capture hook use MODE_EXACT.
-    const char *part_env = getenv("KTA_ALIVE_PART_MIN");   // read per scan: the tests switch paths between batches
-    const int64_t part_min = part_env ? (int64_t)atoll(part_env) : ALIVE_PART_MIN_RECORDS;
-    const uint32_t rpairs = h->alive_pairs >> h->alive_rbits;
-    bool part = exact && !prm.alive_only && !capture && part_min > 0 && prm.n >= part_min && h->alive_rbits >= PART_BITS &&
-                rpairs <= PART_REGION_MAX_PAIRS && (size_t)rpairs * 16 <= h->smem_optin;
-    const char *cache_env = getenv("KTA_ALIVE_CACHE_MIN");   // tests: the seen cache on small batches too
-    if (exact && prm.n >= (cache_env ? (int64_t)atoll(cache_env) : ALIVE_CACHE_MIN_RECORDS)) {
+    if (exact && prm.n >= ALIVE_CACHE_MIN_RECORDS) {
         // the seen cache pays for its clearing (32 MiB, ~10 µs) on batches of a million records and more.
         // Waves cut the batch's seq range [lo, hi] into <= 127 equal slices (any monotone function of seq will do).
         static const bool off = getenv("KTA_ALIVE_NO_CACHE") != nullptr;   // tuning / ablation knob
@@ -482,57 +454,13 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
         prm.stage_limit = (((uintptr_t)prm.key_bytes & 15u) == 0) ? ((uint64_t)key_readable & ~15ull) : 0;
     }
     if (capture && h->shard_world > 1) return fail(KTA_ERR_INVALID, "hash capture is not available on a partition-sharded handle");
+    const int variant = h->shard_world > 1 ? 5 + mode : mode + (capture ? 2 : 0);
     int threads = 0, keybuf = 0;
     size_t sm = 0;
-    if (part) {
-        scan_shape(h, true, true, prm.n, key_bytes, threads, keybuf, sm, true);
-        if (sm > h->smem_optin || threads < 256) part = false;   // the stages do not fit next to this topic's counters / keys
-    }
-    if (!part) scan_shape(h, mode != MODE_COUNTERS, mode == MODE_EXACT, prm.n, key_bytes, threads, keybuf, sm);
+    scan_shape(h, mode != MODE_COUNTERS, mode == MODE_EXACT, prm.n, key_bytes, threads, keybuf, sm);
     if (sm > h->smem_optin) return fail(KTA_ERR_INVALID, "scan kernel does not fit: %zu B shared memory", sm);
     prm.keybuf = keybuf;
-    int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
-    if (part) {
-        // chunk pool: every CTA fills its own slice; a CTA sees at most ceil(ntiles / warps) tiles per warp
-        const int64_t nwarps = threads / 32, tiles_cta = ((prm.ntiles + (int64_t)grid * nwarps - 1) / ((int64_t)grid * nwarps)) * nwarps;
-        // sized for a batch half of whose records survive the seen cache (a compacted topic: ~10 %); a CTA whose slice
-        // runs out stamps the rest directly
-        const int64_t cap = (tiles_cta * TILE / 2 + PART_C - 1) / PART_C + PART_B + 8, total = cap * grid;
-        if (total >= ((int64_t)1 << 29)) part = false;
-        else if (total > h->part_cap_chunks || !h->d_part_hist) {
-            cudaFree(h->d_part_chunks); cudaFree(h->d_part_tags); cudaFree(h->d_part_order);
-            h->d_part_chunks = nullptr; h->d_part_tags = h->d_part_order = nullptr;
-            h->part_cap_chunks = 0;
-            const int64_t want = total + total / 16;
-            if (cudaMalloc(&h->d_part_chunks, (size_t)want * PART_C * 8) != cudaSuccess || cudaMalloc(&h->d_part_tags, (size_t)want * 4) != cudaSuccess ||
-                cudaMalloc(&h->d_part_order, (size_t)want * 4) != cudaSuccess) {
-                cudaGetLastError();   // no room for the pool next to the caller's data: the direct path needs none
-                cudaFree(h->d_part_chunks); cudaFree(h->d_part_tags); cudaFree(h->d_part_order);
-                h->d_part_chunks = nullptr; h->d_part_tags = h->d_part_order = nullptr;
-                part = false;
-            } else {
-                h->part_cap_chunks = want;
-                if (!h->d_part_hist) {
-                    CU(cudaMalloc(&h->d_part_hist, (size_t)h->sm_count * PART_B * 4));
-                    CU(cudaMalloc(&h->d_part_aux, (size_t)(3 * PART_B + 1) * 4));
-                }
-            }
-        }
-        if (part) {
-            prm.part_chunks = h->d_part_chunks;
-            prm.part_tags = h->d_part_tags;
-            prm.part_hist = h->d_part_hist;
-            prm.part_total = h->d_part_aux;
-            prm.part_cta_cap = (uint32_t)cap;
-            CU(cudaMemsetAsync(h->d_part_aux, 0, (size_t)2 * PART_B * 4, h->stream));
-        } else {
-            // fall back to the direct path
-            scan_shape(h, true, true, prm.n, key_bytes, threads, keybuf, sm);
-            prm.keybuf = keybuf;
-            grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
-        }
-    }
-    const int variant = part ? (h->shard_world > 1 ? 9 : 8) : h->shard_world > 1 ? 5 + mode : mode + (capture ? 2 : 0);
+    const int grid = (int)std::min<int64_t>((prm.ntiles + threads / 32 - 1) / (threads / 32), h->sm_count);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->timing) {
         if (h->ev_used == h->ev_pool.size()) {
@@ -550,16 +478,6 @@ static int launch_scan_raw(kta_handle *h, ScanParams prm, int64_t key_readable, 
     else launch_variant<false>(variant, grid, threads, sm, h->stream, prm);
     CU(cudaGetLastError());
     h->launches++;
-    if (part) {
-        // group the chunks by bucket, then replay every bucket against its region(s) of the table in shared memory
-        part_scatter_kernel<<<grid, 1024, 0, h->stream>>>(h->d_part_tags, prm.part_cta_cap, h->d_part_hist, h->d_part_aux, h->d_part_order);
-        const ResolveParams q{h->d_alive_table, h->d_alive_status, h->d_part_chunks, h->d_part_order, h->d_part_aux + 2 * PART_B, rpairs, h->alive_rbits};
-        const int rgrid = (int)std::min<int64_t>((int64_t)1 << h->alive_rbits, h->sm_count);
-        alive_resolve_kernel<<<rgrid, 1024, (size_t)rpairs * 16, h->stream>>>(q);
-        CU(cudaGetLastError());
-        h->launches += 2;
-        h->part_scans++;
-    }
     if (h->timing) CU(cudaEventRecord(e1, h->stream));
     return KTA_OK;
 }
@@ -573,15 +491,13 @@ static int alive_grow(kta_handle *h, uint32_t new_pairs) {
     CU(cudaMalloc(&nt, (size_t)new_pairs * 16));
     CU(cudaMemsetAsync(nt, 0xff, (size_t)new_pairs * 16, s));
     const size_t old_slots = (size_t)h->alive_pairs * 2;
-    const int new_rbits = alive_layout_rbits(new_pairs);
-    alive_rehash_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, old_slots, nt, new_pairs, new_rbits, h->d_alive_status);
+    alive_rehash_kernel<<<h->sm_count * 8, THREADS, 0, s>>>(h->d_alive_table, old_slots, nt, new_pairs, h->d_alive_status);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     cudaFree(h->d_alive_table);
     h->d_alive_table = nt;
     h->alive_pairs = new_pairs;
-    h->alive_rbits = new_rbits;
     h->alive_grows++;
     return KTA_OK;
 }
@@ -1595,7 +1511,7 @@ extern "C" int kta_alive_import_device(kta_handle *h, const uint32_t *dev_hash, 
     if ((rc = alive_check(h))) return rc;   // nothing pending: a re-run below only concerns the imported stamps
     const int grid = (int)std::min<int64_t>((count + THREADS - 1) / THREADS, (int64_t)h->sm_count * 8);
     for (int round = 0;; round++) {
-        const AliveTable t{h->d_alive_table, h->alive_pairs, h->d_alive_status, 0, h->alive_rbits, h->alive_pairs >> h->alive_rbits};
+        const AliveTable t{h->d_alive_table, h->alive_pairs, h->d_alive_status, 0};
         alive_import_kernel<<<grid, THREADS, 0, h->stream>>>(t, h->alive_origin, dev_hash,
                                                              reinterpret_cast<const unsigned long long *>(dev_stamp), count);
         h->launches++;
@@ -1634,12 +1550,6 @@ extern "C" int kta_alive_table_stats(kta_handle *h, uint64_t *slots, uint64_t *o
     if (occupied) *occupied = h->alive_occupied;
     if (grows) *grows = h->alive_grows;
     if (reruns) *reruns = h->alive_reruns;
-    return KTA_OK;
-}
-
-extern "C" int kta_alive_part_scans(const kta_handle *h, uint64_t *out) {
-    if (!h || !out) return fail(KTA_ERR_INVALID, "null argument");
-    *out = h->part_scans;
     return KTA_OK;
 }
 

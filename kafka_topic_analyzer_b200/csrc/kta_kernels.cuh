@@ -37,8 +37,6 @@ __host__ __device__ inline size_t warp_smem_bytes(bool hash, int keybuf, bool ex
     (void)exact;   // MODE_EXACT's queue of table-bound records lives in the key stage the tile has just finished with
     return hash ? 128 + 2 * (size_t)keybuf : 128;
 }
-// MODE_PART: per CTA, after the warps' areas: fill/commit word per bucket, chunk count per bucket, the buckets' stages
-__host__ __device__ inline size_t part_smem_bytes();
 constexpr uint32_t FNV_BASIS = 0x811c9dc5u;  // src/fnv32.rs:80
 constexpr uint32_t FNV_MULT = 0x811c9dc5u;   // src/fnv32.rs:97 (NOT the FNV prime — kept for parity)
 constexpr int FOLD_TILES = 8;             // every warp checks the CTA's 16-bit-split sums after every 8th tile of its own
@@ -49,7 +47,7 @@ constexpr int FOLD_TILES = 8;             // every warp checks the CTA's 16-bit-
 // bucket(len) = bfind(len) + 1: 0 for len 0, 1 + floor(log2 len) otherwise, and 32 for len = -1 (null),
 // so "null" needs neither a branch nor a select.
 constexpr int ROW_V = NB + 1, ROW_KSUM = 2 * NB + 2, ROW_VSUM = 2 * NB + 4, SMEM_ROWS = 2 * NB + 6;
-enum ScanMode { MODE_COUNTERS = 0, MODE_HLL = 1, MODE_EXACT = 2, MODE_PART = 3 };
+enum ScanMode { MODE_COUNTERS = 0, MODE_HLL = 1, MODE_EXACT = 2 };
 
 // words of the u64 "sums" state: khist[P][32] | vhist[P][32] | ksum[P] | vsum[P] | knull[P] | bad
 __host__ __device__ inline size_t sums_words(int P) { return (size_t)P * (2 * NB + 3) + 1; }
@@ -84,7 +82,6 @@ struct ScanParams {
                                      // table), [1..HLL_SLICES] per-slice minima it is derived from
     unsigned long long *alive_table; // [2 * alive_pairs] stamps: hash(32) | seq - alive_origin + 1 (31) | alive(1); ~0 = empty
     uint32_t alive_pairs;            // table size in 16-byte pairs of slots (any value >= 1, not only powers of two)
-    int32_t alive_rbits;             // the table is 2^rbits independent REGIONS of alive_pairs >> rbits pairs (alive_layout_rbits)
     int32_t alive_only;              // 1: MODE_EXACT re-run after the table grew — stamps only, no counters / extrema
     uint64_t alive_origin;           // seq that field value 1 stands for (moved forward by a rebase)
     uint64_t alive_fbase;            // seq_base - alive_origin + 1: the field of record 0 when seq is implicit
@@ -95,13 +92,6 @@ struct ScanParams {
     uint32_t *alive_status;          // [0] stamps that found no slot (table too full: host grows it and re-runs the
                                      //     batch), [1] records whose seq lies outside the 31-bit window of the table
     uint32_t *hash_out;              // per-record hash capture (CAPTURE kernels only; test hook), 0 for null keys
-    // MODE_PART (large -c batches): the scan partitions (mixed hash, stamp) items by the top PART_BITS hash bits into
-    // 64-byte chunks instead of touching the table; alive_resolve_kernel applies them region by region afterwards
-    unsigned long long *part_chunks; // [part_cta_cap * gridDim.x][PART_C] items: x << 32 | low word of the stamp
-    uint32_t *part_tags;             // per chunk: bucket | items << 16
-    uint32_t *part_hist;             // [gridDim.x][PART_B] chunks this CTA wrote per bucket
-    uint32_t *part_total;            // [PART_B] chunks per bucket over all CTAs (accumulated at the end of the kernel)
-    uint32_t part_cta_cap;           // chunks a CTA may write (its slice of the pool starts at blockIdx.x * part_cta_cap)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -165,20 +155,6 @@ __device__ __forceinline__ long long pack64(uint32_t lo, uint32_t hi) {
 }
 __device__ __forceinline__ void red_shared_add_nz(uint32_t addr, uint32_t v) {
     asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0; @p red.shared.add.u32 [%0], %1; }" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t atom_shared_add(uint32_t addr, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-    return old;
-}
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t lo, uint32_t hi) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void stg128_stream(void *p, uint4 v) {   // written once, read by a later kernel: do not keep it
-    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -561,54 +537,20 @@ __device__ __forceinline__ unsigned long long alive_atom_cas(unsigned long long 
     return atomicCAS(p, cmp, v);
 }
 
-// Table layout: 2^rbits independent REGIONS of rpairs = npairs >> rbits pairs each.  A hash lives in the region its top
-// rbits bits (of the mixed hash x) name, at home = mulhi(x << rbits, rpairs) inside it, and linear probing wraps inside the
-// region.  rbits = 0 is one region = the whole table.  Regions are what alive_resolve_kernel (the partitioned path for
-// large batches) loads into shared memory one at a time, so a large table is cut until a region fits there.
-constexpr int PART_BITS = 10, PART_B = 1 << PART_BITS;     // buckets of the in-scan partition = top PART_BITS bits of x
-#ifndef KTA_PART_C
-#define KTA_PART_C 4
+__host__ __device__ __forceinline__ uint32_t alive_home(uint32_t x /* mixed hash */, uint32_t npairs) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(x, npairs);
+#else
+    return (uint32_t)(((uint64_t)x * npairs) >> 32);
 #endif
-#ifndef KTA_PART_FENCES
-#define KTA_PART_FENCES 0
-#endif
-#ifndef KTA_PART_THREADS
-#define KTA_PART_THREADS 1024  // the stages take 40 KiB: 32 warps fit next to them (64 partitions, 16-byte keys)
-#endif
-constexpr int PART_C = KTA_PART_C;                         // items per chunk (4 x 8 B = one 32-byte DRAM sector)
-constexpr uint32_t PART_REGION_MAX_PAIRS = 12288;          // 192 KiB of shared memory per region
-constexpr uint32_t PART_MIN_REGION_PAIRS = 64;
-__host__ __device__ inline int alive_layout_rbits(uint32_t npairs) {
-    if (npairs < (PART_MIN_REGION_PAIRS << PART_BITS) || (npairs & (PART_B - 1u))) return 0;   // small / odd-sized tables: one region
-    int r = PART_BITS;
-    while ((npairs >> r) > PART_REGION_MAX_PAIRS && ((npairs >> r) & 1u) == 0 && r < 24) r++;
-    return r;
 }
-
-__host__ __device__ inline size_t part_smem_bytes() { return (size_t)PART_B * 8 + (size_t)PART_B * PART_C * 8; }
 
 struct AliveTable {
     unsigned long long *slots;
     uint32_t npairs;
     uint32_t *status;
     uint64_t pol;       // L2 evict_last policy for the table's lines
-    int rbits;          // log2(regions)
-    uint32_t rpairs;    // pairs per region = npairs >> rbits
 };
-__host__ __device__ __forceinline__ uint32_t alive_region(uint32_t x /* mixed hash */, int rbits) {
-    return rbits ? x >> (32 - rbits) : 0u;
-}
-// home pair inside its region
-__host__ __device__ __forceinline__ uint32_t alive_home_in(uint32_t x, int rbits, uint32_t rpairs) {
-#ifdef __CUDA_ARCH__
-    return __umulhi(x << rbits, rpairs);
-#else
-    return (uint32_t)(((uint64_t)(uint32_t)(x << rbits) * rpairs) >> 32);
-#endif
-}
-__host__ __device__ __forceinline__ uint32_t alive_home(uint32_t x, const AliveTable &t) {
-    return alive_region(x, t.rbits) * t.rpairs + alive_home_in(x, t.rbits, t.rpairs);
-}
 
 // raise an entry that holds this stamp's hash: no return value, the warp does not wait
 __device__ __forceinline__ void alive_red_max(unsigned long long *p, unsigned long long v, uint64_t pol) {
@@ -623,7 +565,6 @@ __device__ __forceinline__ void alive_red_max(unsigned long long *p, unsigned lo
 // stamp known for this hash afterwards (the record's own if it won).
 __device__ __noinline__ uint32_t alive_stamp_slow(const AliveTable t, uint32_t pair, uint32_t hash, uint32_t low) {
     const unsigned long long stamp = ((unsigned long long)hash << 32) | low;
-    const uint32_t rbase = alive_region(hash, t.rbits) * t.rpairs;   // probing wraps inside the hash's region
     for (int probe = 0; probe < ALIVE_MAX_PROBES; probe++) {
         unsigned long long *slot = t.slots + 2 * (size_t)pair;
         const ulonglong2 e = alive_ld_pair(slot, t.pol);
@@ -640,7 +581,7 @@ __device__ __noinline__ uint32_t alive_stamp_slow(const AliveTable t, uint32_t p
                 return low;
             }
         }
-        pair = pair + 1 == rbase + t.rpairs ? rbase : pair + 1;
+        pair = pair + 1 == t.npairs ? 0 : pair + 1;
     }
     atomicAdd(t.status, 1u);   // table too full: the host grows it and re-runs this batch's stamps
     return low;
@@ -711,15 +652,14 @@ __device__ __forceinline__ void alive_cache_put(uint32_t *cache, uint32_t c, uin
 }
 
 // plain insert of an entry whose hash is known to be absent (rehash into a fresh table)
-__device__ __forceinline__ bool alive_insert_unique(unsigned long long *slots, uint32_t npairs, int rbits, unsigned long long entry) {
-    const uint32_t x = (uint32_t)(entry >> 32), rpairs = npairs >> rbits, rbase = alive_region(x, rbits) * rpairs;
-    uint32_t pair = rbase + alive_home_in(x, rbits, rpairs);
-    for (uint32_t probe = 0; probe < rpairs; probe++) {
+__device__ __forceinline__ bool alive_insert_unique(unsigned long long *slots, uint32_t npairs, unsigned long long entry) {
+    uint32_t pair = alive_home((uint32_t)(entry >> 32), npairs);
+    for (uint32_t probe = 0; probe < npairs; probe++) {
         unsigned long long *slot = slots + 2 * (size_t)pair;
 #pragma unroll
         for (int s = 0; s < 2; s++)
             if (__ldcg(slot + s) == ALIVE_EMPTY && atomicCAS(slot + s, ALIVE_EMPTY, entry) == ALIVE_EMPTY) return true;
-        pair = pair + 1 == rbase + rpairs ? rbase : pair + 1;
+        pair = pair + 1 == npairs ? 0 : pair + 1;
     }
     return false;
 }
@@ -772,9 +712,8 @@ __device__ __forceinline__ uint32_t alive_wave(uint32_t field, const AliveWaves 
 // the others.  Only the per-partition counters are shared (shared-memory reductions).
 // ------------------------------------------------------------------------------------------------
 template <int MODE, bool SMEM, bool CAPTURE, bool SHARD = false>
-__global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THREADS, 1) scan_kernel(const ScanParams prm) {
+__global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams prm) {
     constexpr bool HASH = MODE != MODE_COUNTERS;
-    constexpr bool NEWEST_FIRST = MODE == MODE_EXACT || MODE == MODE_PART;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const unsigned full = 0xffffffffu;
@@ -792,25 +731,15 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
     const uint32_t keybuf = smem_u32(wsm) + 128;    // two KEYBUF-byte stages
     const Counters<SMEM> C{smem_u32(scnt), scnt, prm.sums, P, prm.P, SHARD ? prm.shard_world : 1, SHARD ? prm.shard_rank : 0};
     // MODE_EXACT: the alive table's lines are asked to stay in L2 (evict_last), the record stream to leave first
-    constexpr bool HINTS = NEWEST_FIRST && KTA_L2_HINTS;
+    constexpr bool HINTS = MODE == MODE_EXACT && KTA_L2_HINTS;
     const uint64_t pol_stream = HINTS ? l2_policy_evict_first() : 0;
-    const AliveTable AT{prm.alive_table, prm.alive_pairs, prm.alive_status, HINTS ? l2_policy_evict_last() : 0,
-                        prm.alive_rbits, prm.alive_pairs >> prm.alive_rbits};
+    const AliveTable AT{prm.alive_table, prm.alive_pairs, prm.alive_status, HINTS ? l2_policy_evict_last() : 0};
     const AliveWaves AW{prm.alive_cache, prm.alive_wave_base, prm.alive_wave_shift};
     const bool count_it = !(MODE == MODE_EXACT && prm.alive_only);   // false: a stamps-only re-run after the table grew
-    // MODE_PART: [PART_B] fill/commit words | [PART_B] chunk counts | [PART_B][PART_C] staged items; the chunk cursor of the
-    // CTA is word 2 of the CTA scratch line
-    const uint32_t part_base = smem_u32(smem_raw + cta_bytes + (size_t)nwarps * warp_bytes);
-    const uint32_t pword = part_base, phist = part_base + 4u * PART_B, pstage = part_base + 8u * PART_B;
-    const uint32_t pcursor = smem_u32(smem_raw + cta_bytes - CTA_SCRATCH + 8);
 
     if (SMEM) {
         const int nw = P * SMEM_ROWS;
         for (int i = tid; i < nw; i += blockDim.x) scnt[i] = 0;
-    }
-    if (MODE == MODE_PART) {
-        for (int i = tid; i < 2 * PART_B; i += blockDim.x) sts32(part_base + 4u * (uint32_t)i, 0u);
-        if (tid == 0) sts32(pcursor, 0u);
     }
     if (HASH && lane == 0) {
         mbar_init(mbar, 1);
@@ -852,42 +781,7 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
     // tile indices fit 32 bits (the host refuses batches of 2^31 tiles = 2.7e11 records): the loop control stays out of
     // 64-bit arithmetic and out of local memory
     const int ntiles = (int)prm.ntiles;
-    auto phys = [&](int t) { return NEWEST_FIRST ? ntiles - 1 - t : t; };
-
-    // MODE_PART: one thread moves a bucket's staged items into the CTA's next chunk of the pool and reopens the stage.
-    // Only the thread whose commit completed the stage (or, at the end, the bucket's owner) gets here, so nobody else
-    // touches the stage meanwhile: late arrivals see a fill count >= PART_C and go straight to the table.
-    // Ordering without fences (MEMBAR.SC.CTA after the chunk's global stores costs the flusher ~1 µs with the stage
-    // closed; measured 2.0 ms per 1e8 records with fences): shared-memory instructions of one thread are performed in
-    // program order by the shared-memory pipe.  A writer's item store precedes its commit; the flusher's loads are issued
-    // after its own commit returned "all committed"; its reopening store is issued after the chunk's global stores, which
-    // wait for the loaded registers.  KTA_PART_FENCES=1 puts the formal fences back (debug).
-    auto part_flush = [&](uint32_t b, uint32_t cnt) {
-#if KTA_PART_FENCES
-        __threadfence_block();   // acquire: the other lanes' items are visible
-#endif
-        const uint32_t ci = atom_shared_add(pcursor, 1u);
-        if (ci < prm.part_cta_cap) {   // (the cursor keeps counting past the cap: part_hist only counts written chunks)
-            const size_t idx = (size_t)blockIdx.x * prm.part_cta_cap + ci;
-            uint4 *dst = reinterpret_cast<uint4 *>(prm.part_chunks + idx * PART_C);
-            const uint32_t src = pstage + b * (uint32_t)(PART_C * 8);
-#pragma unroll
-            for (int q = 0; q < PART_C / 2; q++) stg128_stream(dst + q, lds128(src + 16u * q));
-            prm.part_tags[idx] = b | (cnt << 16);
-            red_shared_add(phist + 4u * b, 1u);
-        } else {
-            // this CTA's slice of the pool is used up (it is sized for a batch half of whose records survive the seen
-            // cache): the staged items go straight to the table
-            for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t low = lds32(pstage + (b * PART_C + j) * 8u), x = lds32(pstage + (b * PART_C + j) * 8u + 4u);
-                alive_stamp_slow(AT, alive_home(x, AT), x, low);
-            }
-        }
-#if KTA_PART_FENCES
-        __threadfence_block();   // release: the stage has been read before it is reopened
-#endif
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(pword + 4u * b), "r"(0u) : "memory");
-    };
+    auto phys = [&](int t) { return MODE == MODE_EXACT ? ntiles - 1 - t : t; };
     const int gstride = (int)gridDim.x * nwarps;
     int tile = (int)blockIdx.x * nwarps + warp;
     if (HASH && lane == 0 && tile < ntiles) nxt_info = issue(phys(tile), 0);
@@ -1184,9 +1078,9 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
                     if (valid[k]) prm.hash_out[rbase + 32 * k] = kl[k] >= 0 ? h[k] : 0u;
             }
         };
-        if (!NEWEST_FIRST) count_records();
+        if (MODE != MODE_EXACT) count_records();
         if (HASH) hash_keys();
-        if (NEWEST_FIRST) {
+        if (MODE == MODE_EXACT) {
             // metric.rs:291-302: Some(key) → insert (value) / remove (tombstone); None → nothing.
             // Last-writer-wins per hash in seq order IS the BitSet insert/remove sequence replayed in order
             // (metric.rs:295 mark_key_alive, :298 mark_key_dead).
@@ -1234,36 +1128,10 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
             }
             __syncwarp();
 #if KTA_EXP_ALIVE_STAGE >= 2
-            if (MODE == MODE_PART) {
-                // LARGE batches: the survivors do not go to the table (two to three dependent DRAM round trips per tile,
-                // the bulk of MODE_EXACT's time) but into shared-memory stages keyed by the top PART_BITS bits of the mixed
-                // hash; a full stage leaves as one chunk of the CTA's own, sequentially written slice of the chunk pool,
-                // and alive_resolve_kernel replays the chunks region by region against the table afterwards.
-                // Stage protocol (no waiting anywhere): word = arrivals (low half) | commits (high half).  An arrival
-                // numbered < PART_C owns that slot: write, commit; the commit that completes the stage flushes it and zeroes
-                // the word.  An arrival numbered >= PART_C met a full stage (being flushed) and stamps the table directly —
-                // nobody holds the table in shared memory while this kernel runs.
-                for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
-                    if (q0 + lane < qn) {
-                        const uint4 item = queue[q0 + lane];
-                        // the cache learns that a record of this hash and wave exists (and will be resolved)
-                        if (cached) alive_cache_put(AW.cache, item.z, item.x, alive_wave(item.y >> 1, AW), item.y >> 1);
-                        const uint32_t b = item.x >> (32 - PART_BITS);
-                        const uint32_t pos = atom_shared_add(pword + 4u * b, 1u) & 0xffffu;
-                        if (pos < (uint32_t)PART_C) {
-                            sts64(pstage + (b * PART_C + pos) * 8u, item.y, item.x);
-                            const uint32_t old = atom_shared_add(pword + 4u * b, 0x10000u);
-                            if ((old >> 16) == (uint32_t)(PART_C - 1)) part_flush(b, (uint32_t)PART_C);
-                        } else {
-                            alive_stamp_slow(AT, alive_home(item.x, AT), item.x, item.y);
-                        }
-                    }
-                }
-            } else
             for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
                 if (q0 + lane < qn) {
                     const uint4 item = queue[q0 + lane];
-                    const uint32_t pr = alive_home(item.x, AT);
+                    const uint32_t pr = alive_home(item.x, AT.npairs);
                     const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
                     const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
                     // tell the cache what the table knows now: the newest stamp of this hash as a wave of THIS batch (0 =
@@ -1323,19 +1191,6 @@ __global__ void __launch_bounds__(MODE == MODE_PART ? KTA_PART_THREADS : MAX_THR
 
     // ---- flush CTA-private state ----
     __syncthreads();
-    if (MODE == MODE_PART) {
-        // every stage is at rest now (arrivals == commits < PART_C): the owner thread of a bucket sends its remainder off
-        for (uint32_t b = tid; b < (uint32_t)PART_B; b += blockDim.x) {
-            const uint32_t cnt = lds32(pword + 4u * b) & 0xffffu;
-            if (cnt) part_flush(b, min(cnt, (uint32_t)PART_C));
-        }
-        __syncthreads();
-        for (uint32_t b = tid; b < (uint32_t)PART_B; b += blockDim.x) {
-            const uint32_t c = lds32(phist + 4u * b);
-            prm.part_hist[(size_t)blockIdx.x * PART_B + b] = c;
-            if (c) atomicAdd(prm.part_total + b, c);   // bucket sizes in chunks (zeroed by the host before the launch)
-        }
-    }
     if (SMEM) {
         // bucket rows → global [which][p][bucket]; row 32 → knull; row 65 (tombstones) is derived, not stored
         const int nh = (ROW_V + NB) * P;
@@ -1494,7 +1349,7 @@ __global__ void __launch_bounds__(THREADS) alive_import_kernel(const AliveTable 
             continue;
         }
         const uint32_t x = hll_mix(hash[i]);
-        alive_stamp_slow(tt, alive_home(x, tt), x, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
+        alive_stamp_slow(tt, alive_home(x, t.npairs), x, ((uint32_t)field << 1) | (uint32_t)(st & 1ull));
     }
 }
 
@@ -1517,11 +1372,11 @@ __global__ void __launch_bounds__(THREADS) alive_count_kernel(const unsigned lon
 
 // growth: every entry of the old table moves to its place in the new one (hashes are unique, so plain claims)
 __global__ void __launch_bounds__(THREADS) alive_rehash_kernel(const unsigned long long *old_slots, size_t old_nslots,
-                                                               unsigned long long *new_slots, uint32_t new_npairs, int new_rbits, uint32_t *status) {
+                                                               unsigned long long *new_slots, uint32_t new_npairs, uint32_t *status) {
     const size_t stride = (size_t)gridDim.x * THREADS;
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < old_nslots; i += stride) {
         const unsigned long long v = old_slots[i];
-        if (v != ALIVE_EMPTY && !alive_insert_unique(new_slots, new_npairs, new_rbits, v)) atomicAdd(status, 1u);
+        if (v != ALIVE_EMPTY && !alive_insert_unique(new_slots, new_npairs, v)) atomicAdd(status, 1u);
     }
 }
 
@@ -1531,133 +1386,6 @@ __global__ void __launch_bounds__(THREADS) alive_rebase_kernel(unsigned long lon
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < nslots; i += stride) {
         const unsigned long long v = slots[i];
         if (v != ALIVE_EMPTY) slots[i] = v & 0xffffffff00000001ull;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The partitioned path for large -c batches (metric.rs:288-305 once more, without one random access per record):
-//   scan_kernel<MODE_PART>  writes every keyed record as an 8-byte item into 64-byte chunks tagged with a bucket (the top
-//                           PART_BITS bits of the mixed hash); every CTA fills its own slice of the chunk pool front to back
-//   part_scatter_kernel     chunk ids grouped by bucket (counting sort; 4 bytes per chunk)
-//   alive_resolve_kernel    one CTA per table region: region → shared memory, the bucket's items applied with shared-memory
-//                           atomics (claim by 64-bit CAS, raise by 32-bit max on the stamp word: same last-writer rule as
-//                           alive_stamp), region → table.  All traffic is sequential: 8 B written + 8 B read per record and
-//                           the table once in, once out.
-// ------------------------------------------------------------------------------------------------
-// order[] entry: chunk id (29 bits) | items - 1 (3 bits).  Every CTA re-derives the buckets' starts from the totals (an
-// exclusive scan of 1024 words), reserves the place of each of its (CTA, bucket) runs with one atomic on the bucket's cursor,
-// and drops its chunk ids there.  aux = [PART_B] totals | [PART_B] cursors (zeroed before the scan) | [PART_B + 1] starts (out).
-__global__ void __launch_bounds__(1024) part_scatter_kernel(const uint32_t *tags, uint32_t cta_cap, const uint32_t *hist, uint32_t *aux,
-                                                            uint32_t *order) {
-    __shared__ uint32_t cur[PART_B];
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t total;
-    static_assert(PART_B == 1024, "one bucket per thread");
-    const int c = blockIdx.x, b = threadIdx.x, lane = b & 31, warp = b >> 5;
-    if (b == 0) total = 0;
-    const uint32_t tot = aux[b], mine = hist[(size_t)c * PART_B + b];
-    uint32_t inc = tot;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wb = 0;
-    for (int w = 0; w < warp; w++) wb += wsum[w];
-    const uint32_t start = wb + inc - tot;
-    if (c == 0) {
-        aux[2 * PART_B + b] = start;
-        if (b == PART_B - 1) aux[3 * PART_B] = start + tot;
-    }
-    cur[b] = start + (mine ? atomicAdd(aux + PART_B + b, mine) : 0u);
-    if (mine) atomicAdd(&total, mine);
-    __syncthreads();
-    const uint32_t n = total, base = (uint32_t)c * cta_cap;
-    for (uint32_t i0 = b; i0 < n; i0 += 4 * 1024) {
-        uint32_t t[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) t[u] = i0 + u * 1024 < n ? __ldcs(tags + base + i0 + u * 1024) : 0u;
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (i0 + u * 1024 < n) order[atomicAdd(&cur[t[u] & 0xffffu], 1u)] = (base + i0 + u * 1024) | (((t[u] >> 16) - 1u) << 29);
-    }
-}
-
-struct ResolveParams {
-    unsigned long long *table;
-    uint32_t *status;
-    const unsigned long long *chunks;
-    const uint32_t *order, *bucket_start;
-    uint32_t rpairs;
-    int rbits;
-};
-
-__device__ __forceinline__ void resolve_stamp(uint32_t region /*smem addr*/, uint32_t rpairs, int rbits, uint32_t x, uint32_t low, uint32_t *status) {
-    uint32_t w = alive_home_in(x, rbits, rpairs);
-    const unsigned long long stamp = ((unsigned long long)x << 32) | low;
-    for (int probe = 0; probe < ALIVE_MAX_PROBES; probe++) {
-        const uint32_t a = region + 16u * w;
-        const uint4 e = lds128(a);   // (x.lo, x.hi, y.lo, y.hi): two entries, low word = stamp, high word = hash
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            uint32_t vlo = s ? e.z : e.x, vhi = s ? e.w : e.y;
-            if ((vlo & vhi) == 0xffffffffu) {   // empty: claim it
-                unsigned long long old;
-                asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a + 8u * s), "l"(ALIVE_EMPTY), "l"(stamp) : "memory");
-                if (old == ALIVE_EMPTY) return;
-                vlo = (uint32_t)old;
-                vhi = (uint32_t)(old >> 32);
-            }
-            if (vhi == x) {   // a real entry of this hash (an entry's low word is never 0xffffffff: see ALIVE_FIELD_MAX)
-                if (vlo < low) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a + 8u * s), "r"(low) : "memory");
-                return;
-            }
-        }
-        w = w + 1 == rpairs ? 0 : w + 1;
-    }
-    atomicAdd(status, 1u);   // region too full: the host grows the table and re-runs the batch
-}
-
-__global__ void __launch_bounds__(1024, 1) alive_resolve_kernel(const ResolveParams q) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t region = smem_u32(smem_raw);
-    const int tid = threadIdx.x;
-    const uint32_t nregions = 1u << q.rbits, nvec = q.rpairs;   // 16-byte vectors per region
-    const int sub_bits = q.rbits - PART_BITS;                   // regions per bucket = 2^sub_bits
-    for (uint32_t r = blockIdx.x; r < nregions; r += gridDim.x) {
-        const uint32_t b = r >> sub_bits;
-        const uint32_t cs = q.bucket_start[b], ce = q.bucket_start[b + 1];
-        if (cs == ce) continue;
-        uint4 *g = reinterpret_cast<uint4 *>(q.table + (size_t)r * q.rpairs * 2);
-        uint4 *sm = reinterpret_cast<uint4 *>(smem_raw);
-        for (uint32_t i = tid; i < nvec; i += blockDim.x) sm[i] = __ldcg(g + i);
-        __syncthreads();
-        // a warp takes 32 chunks at a time: one coalesced read of their ids, then PART_C rounds in which 32 / PART_C chunks
-        // are read by PART_C lanes each — all of a lane's item loads are in flight before the first is used
-        constexpr int LPC = PART_C, CPR = 32 / PART_C;   // lanes per chunk, chunks per round
-        const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-        for (uint32_t c0 = cs + 32u * warp; c0 < ce; c0 += 32u * nw) {
-            const uint32_t mine = c0 + lane < ce ? __ldcs(q.order + c0 + lane) : 0u;
-            unsigned long long item[PART_C];
-            bool ok[PART_C];
-#pragma unroll
-            for (int j = 0; j < PART_C; j++) {
-                const int ch = j * CPR + lane / LPC, sub = lane % LPC;
-                const uint32_t e = __shfl_sync(0xffffffffu, mine, ch);
-                ok[j] = c0 + ch < ce && (uint32_t)sub <= (e >> 29);
-                item[j] = ok[j] ? __ldcs(q.chunks + (size_t)(e & 0x1fffffffu) * PART_C + sub) : 0ull;
-            }
-#pragma unroll
-            for (int j = 0; j < PART_C; j++) {
-                const uint32_t x = (uint32_t)(item[j] >> 32);
-                if (ok[j] && (sub_bits == 0 || (x >> (32 - q.rbits)) == r)) resolve_stamp(region, q.rpairs, q.rbits, x, (uint32_t)item[j], q.status);
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = tid; i < nvec; i += blockDim.x) __stcg(g + i, sm[i]);
-        __syncthreads();
     }
 }
 

@@ -240,12 +240,6 @@ class KtaEngine:
         check(lib().kta_alive_table_stats(self._h, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
 
-    def alive_part_scans(self) -> int:
-        """Scans that took the partitioned alive-key path (large -c batches)."""
-        out = C.c_uint64()
-        check(lib().kta_alive_part_scans(self._h, C.byref(out)))
-        return out.value
-
     def alive_keys_hll(self) -> float:
         out = C.c_double()
         check(lib().kta_alive_keys_hll(self._h, C.byref(out)))

@@ -745,115 +745,3 @@ def test_partition_sharded_engines_merge_to_the_whole_topic(P, world, run_len):
     finally:
         for e in engines:
             e.close()
-
-
-# ------------------------------------------------------------------------------------------------
-# the partitioned alive-key path (scan_kernel<MODE_PART> + alive_resolve_kernel): what large -c batches take.  The tests
-# lower its size threshold (KTA_ALIVE_PART_MIN, read per scan) so that small oracle-checkable batches go through it.
-# ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("seen_cache", [True, False])
-@pytest.mark.parametrize("case", ["binary64", "ascii_runs", "ragged_tail", "many_partitions", "hot_keys", "region_pairs_odd"])
-def test_partitioned_alive_path_equals_bitset_replay(case, seen_cache, monkeypatch):
-    """metric.rs:288-305 through the partitioned path: the records that survive the seen cache are staged per hash bucket
-    in the scan and replayed region by region in shared memory — bit-equal to the BitSet replay, table occupancy = distinct
-    hashes, and the path must have run.  Without the seen cache every keyed record is staged and the chunk pool (sized for
-    half of them) runs out, so the direct stamps of the overflow are covered too."""
-    monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1")
-    monkeypatch.setenv("KTA_ALIVE_CACHE_MIN", "1" if seen_cache else str(1 << 40))
-    kib = 1024                                                      # 1 MiB = 1024 regions of 64 pairs
-    kw = dict(tombstone_per_10k=2500, null_key_per_10k=300, ts_missing_per_10k=5)
-    if case == "binary64":
-        P, n, kw = 64, 64 * 4700, dict(kw, distinct_keys=15_000)
-    elif case == "ascii_runs":
-        P, n, kw = 16, 16 * 64 * 300, dict(kw, key_mode=1, run_len=64, distinct_keys=9_000)
-    elif case == "ragged_tail":
-        P, n, kw = 5, 5 * 7 * 8001, dict(kw, key_mode=2, run_len=7, distinct_keys=20_000)      # n is not a multiple of 128
-    elif case == "many_partitions":
-        P, n, kw = 700, 700 * 300, dict(kw, key_mode=2, distinct_keys=30_000)                  # counters in global memory
-    elif case == "hot_keys":
-        P, n, kw = 8, 8 * 40_000, dict(kw, distinct_keys=8 * 4096, zipf_keys=True, geometric_values=True, value_mean=2048)
-    else:
-        P, n, kw, kib = 64, 64 * 4700, dict(kw, distinct_keys=40_000), 1024 * 3               # 192 pairs per region
-    t = synth.fill_host(synth.make_spec(n, P, **kw))
-    o = oracle_for(t, count_alive_keys=True, now=NOW)
-    with KtaEngine(P, count_alive_keys=True, hll_precision=12, now=NOW, alive_table_kib=kib) as e:
-        scan_device(e, t)
-        assert e.alive_part_scans() == 1
-        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(12))
-        slots, occupied, grows, reruns = e.alive_table_stats()
-        assert occupied == len(set(np_oracle.fnv32_many(t.key_len, t.key_bytes)[t.key_len >= 0].tolist()))
-
-
-def test_partitioned_and_direct_batches_share_one_table(monkeypatch):
-    """A topic cut into batches that alternate between the two -c paths (and one pushed record by record): the table
-    layout is common, so the result is the BitSet replay of the whole topic in order."""
-    import torch
-    P, n, T = 16, 16 * 25_000, N.KTA_KEY_TILE
-    t = synth.fill_host(synth.make_spec(n, P, key_mode=1, distinct_keys=12_000, tombstone_per_10k=3000, null_key_per_10k=200))
-    o = oracle_for(t, count_alive_keys=True, now=NOW)
-    kb = torch.zeros(t.key_bytes.size + 16, dtype=torch.uint8, device="cuda")
-    kb[: t.key_bytes.size] = torch_dev(t.key_bytes)
-    cols = [torch_dev(c) for c in (t.partition, t.ts_ms, t.key_len, t.value_len)]
-    tb = torch_dev(t.key_tile_base)
-    cuts = [0, 700 * T, 701 * T, 1900 * T, 2500 * T, n]
-    monkeypatch.setenv("KTA_ALIVE_CACHE_MIN", "1")
-    with KtaEngine(P, count_alive_keys=True, hll_precision=11, now=NOW, alive_table_kib=2048) as e:
-        for i, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
-            monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1" if i % 2 == 0 else "0")
-            e.scan_batch_device(*[c[lo:hi] for c in cols], key_bytes=kb, key_bytes_len=int(t.key_bytes.size), key_tile_base=tb[lo // T:])
-        e.finalize()
-        assert e.alive_part_scans() == 3
-        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(11))
-        # the same topic once more through the partitioned path alone: new sequence numbers, same alive set
-        before = e.alive_keys()
-        monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1")
-        e.scan_batch_device(*cols, key_bytes=kb, key_bytes_len=int(t.key_bytes.size), key_tile_base=tb)
-        e.finalize()
-        assert e.alive_keys() == before and e.message_metrics.overall_count() == 2 * n and e.alive_part_scans() == 4
-
-
-def test_partitioned_path_grows_a_table_whose_regions_overflow(monkeypatch):
-    """150k distinct keys into a 1 MiB table (131072 slots): regions fill up in alive_resolve_kernel, the dropped stamps are
-    counted, the table is grown (layout re-derived) and the batch re-stamped — result = BitSet replay, counters once."""
-    monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1")
-    P, n = 32, 32 * 12_500
-    t = synth.fill_host(synth.make_spec(n, P, distinct_keys=150_016, tombstone_per_10k=2000, null_key_per_10k=100))
-    o = oracle_for(t, count_alive_keys=True, now=NOW)
-    with KtaEngine(P, count_alive_keys=True, hll_precision=12, now=NOW, alive_table_kib=1024) as e:
-        scan_device(e, t)
-        slots, occupied, grows, reruns = e.alive_table_stats()
-        assert e.alive_part_scans() == 1 and grows >= 1 and reruns >= 1 and slots > 131072
-        assert_parity(e, o, P, check_alive=True, hll_regs=o.hll_alive_regs(12))
-        scan_device(e, t)                                           # and the grown table takes the partitioned path again
-        assert e.alive_part_scans() == 2 and e.alive_keys() == o.scalar("sum_all_alive")
-
-
-def test_partitioned_path_with_explicit_seq_on_sharded_handles(monkeypatch):
-    """Partition-sharded -c scans carry absolute sequence numbers in a column; two shards through the partitioned path,
-    their tables merged by export / import, equal the BitSet replay of the whole topic."""
-    import torch
-    monkeypatch.setenv("KTA_ALIVE_PART_MIN", "1")
-    P, world, n = 8, 2, 8 * 30_000
-    whole = synth.fill_host(synth.make_spec(n, P, distinct_keys=20_000, tombstone_per_10k=3000, null_key_per_10k=100))
-    o = oracle_for(whole, count_alive_keys=True, now=NOW)
-    from kafka_topic_analyzer_b200.synth import HostTopic, tile_base_from_key_len
-    engines = [KtaEngine(P, count_alive_keys=True, now=NOW, shard=(r, world), alive_table_kib=1024) for r in range(world)]
-    try:
-        for r, e in enumerate(engines):
-            sel = (whole.partition % world) == r
-            keyed = whole.key_len >= 0
-            kb = whole.key_bytes.reshape(-1, 16)[sel[keyed]].reshape(-1) if whole.key_bytes.size else whole.key_bytes
-            t = HostTopic(whole.partition[sel], whole.offset[sel], whole.ts_ms[sel], whole.key_len[sel], whole.value_len[sel],
-                          whole.seq[sel], np.ascontiguousarray(kb), tile_base_from_key_len(whole.key_len[sel]))
-            scan_device(e, t, with_seq=True)
-            assert e.alive_part_scans() == 1
-        cnt = engines[1].alive_export_count()
-        hs = torch.empty(cnt, dtype=torch.int32, device="cuda")
-        st = torch.empty(cnt, dtype=torch.int64, device="cuda")
-        assert engines[1].alive_export(hs, st, cnt) == cnt
-        engines[0].alive_import(hs, st, cnt)
-        engines[0].finalize()
-        assert engines[0].alive_keys() == o.scalar("sum_all_alive")
-    finally:
-        for e in engines:
-            e.close()
