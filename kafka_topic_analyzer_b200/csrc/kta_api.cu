@@ -730,10 +730,10 @@ static int scan_log_batches(kta_handle *h, int32_t partition, const int32_t *dev
     CU(cudaMemcpyAsync(err, h->d_log_err, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (err[0] & LOGB_COMPRESSED)
-        return fail(KTA_ERR_INVALID, "gzip / zstd record batches are not supported (LZ4 and Snappy are decompressed on the GPU)");
+        return fail(KTA_ERR_INVALID, "zstd record batches are not supported (gzip, LZ4 and Snappy are decompressed on the GPU)");
     if (err[0] & LOGB_BAD) return fail(KTA_ERR_INVALID, "malformed record batch header in partition %d", partition);
     if (nrec == 0) return KTA_OK;
-    if (err[0] & (LOGB_LZ4 | LOGB_SNAPPY)) {
+    if (err[0] & LOGB_CODECS) {
         // compressed batches: size pass, scratch allocation, decompression; afterwards they are ordinary batches that
         // happen to lie in the scratch buffer
         if ((rc = grow(h->d_unc_slot, h->unc_slot_cap, nbatches + 2, s))) return rc;

@@ -1131,9 +1131,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) scan_kernel(const ScanParams p
             for (uint32_t q0 = 0; q0 < qn; q0 += 32) {
                 if (q0 + lane < qn) {
                     const uint4 item = queue[q0 + lane];
+#if KTA_EXP_ALIVE_STAGE == 3   // ablation: the survivors update the seen cache but never go to the table
+                    const uint32_t newest = item.y;
+#else
                     const uint32_t pr = alive_home(item.x, AT.npairs);
                     const ulonglong2 e = alive_ld_pair(AT.slots + 2 * (size_t)pr, AT.pol);
                     const uint32_t newest = alive_stamp(AT, pr, e, item.x, item.y);
+#endif
                     // tell the cache what the table knows now: the newest stamp of this hash as a wave of THIS batch (0 =
                     // older than the batch: says nothing), or the record's own wave
                     if (cached)

@@ -13,21 +13,24 @@
 // LogAppendTime batches (attributes bit 3) stamp every record with maxTimestamp; a record's timestamp is baseTimestamp +
 // timestampDelta as the consumer computes it, and only a RESULT of -1 means "not available"; key/value length -1 means
 // null.  CRCs are not verified (librdkafka's default check.crcs=false).
-// Compression (attributes bits 0-2, librdkafka decompresses inside poll, src/kafka.rs:93): LZ4 (frame format) and Snappy
-// (raw or xerial-framed) batches are decompressed on the GPU into a scratch buffer and then decoded like the others;
-// gzip and zstd are rejected.
+// Compression (attributes bits 0-2, librdkafka decompresses inside poll, src/kafka.rs:93): gzip (kta_inflate.cuh), LZ4 (frame
+// format) and Snappy (raw or xerial-framed) batches are decompressed on the GPU into a scratch buffer and then decoded like
+// the others; zstd is rejected.
 // Not handled: records of aborted transactions are delivered (a read_committed consumer would filter them through the
 // .txnindex / abort markers), legacy magic 0/1 message sets are flagged as malformed.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kta_inflate.cuh"
+
 namespace kta {
 
 constexpr int LOG_HEADER_BYTES = 61;
-// LOGB_COMPRESSED: a codec without a decompressor here (gzip, zstd).  LOGB_LZ4 / LOGB_SNAPPY: the records section must be
+// LOGB_COMPRESSED: a codec without a decompressor here (zstd).  LOGB_LZ4 / LOGB_SNAPPY / LOGB_GZIP: the records section must be
 // decompressed first (log_unc_size_kernel + log_decompress_kernel turn such a batch into LOGB_OK).
-enum LogBatchFlags { LOGB_OK = 0, LOGB_SKIP_CONTROL = 1, LOGB_BAD = 2, LOGB_COMPRESSED = 4, LOGB_LZ4 = 8, LOGB_SNAPPY = 16 };
+enum LogBatchFlags { LOGB_OK = 0, LOGB_SKIP_CONTROL = 1, LOGB_BAD = 2, LOGB_COMPRESSED = 4, LOGB_LZ4 = 8, LOGB_SNAPPY = 16, LOGB_GZIP = 32 };
+constexpr uint32_t LOGB_CODECS = LOGB_LZ4 | LOGB_SNAPPY | LOGB_GZIP;   // batches log_decompress_kernel turns into LOGB_OK
 
 __device__ __forceinline__ uint64_t be_u64(const uint8_t *p) {
     uint64_t v = 0;
@@ -80,13 +83,13 @@ __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const ui
                 bi.max_ts = (int64_t)be_u64(p + 35);
                 bi.log_append_time = (attrs >> 3) & 1u;
                 if (attrs & 0x20u) bi.flags = LOGB_SKIP_CONTROL;
-                else if (codec == 0 || codec == 2 || codec == 3) {
-                    bi.flags = codec == 0 ? LOGB_OK : codec == 2 ? LOGB_SNAPPY : LOGB_LZ4;
+                else if (codec <= 3) {
+                    bi.flags = codec == 0 ? LOGB_OK : codec == 1 ? LOGB_GZIP : codec == 2 ? LOGB_SNAPPY : LOGB_LZ4;
                     bi.records = count;
-                } else bi.flags = LOGB_COMPRESSED;   // gzip (1), zstd (4)
+                } else bi.flags = LOGB_COMPRESSED;   // zstd (4) and unassigned codes
             }
         }
-        if (bi.flags & (LOGB_BAD | LOGB_COMPRESSED | LOGB_LZ4 | LOGB_SNAPPY)) atomicOr(error_flags, bi.flags);
+        if (bi.flags & (LOGB_BAD | LOGB_COMPRESSED | LOGB_CODECS)) atomicOr(error_flags, bi.flags);
         else if (bi.flags == LOGB_OK) atomicMax(error_flags + 1, bi.len);   // [1]: the longest batch (sizes the decode stage)
         info[b] = bi;
         rec_count[b + 1] = (uint64_t)bi.records;
@@ -271,16 +274,57 @@ __device__ LzWalk snappy_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint6
     return w;
 }
 
+// gzip: one member (what producers write: the records section is one gzip stream).  The size pass trusts ISIZE; the copy
+// pass is bounded by it and must produce exactly that many bytes.  The CRC32 of the trailer is not verified (like the batch
+// CRC: check.crcs=false).
+struct InfWarpOut {
+    uint8_t *out;
+    uint64_t op, cap;
+    int lane;
+    __device__ bool lit(uint8_t b) {
+        if (op >= cap) return false;
+        if (lane == 0) out[op] = b;
+        op++;
+        return true;
+    }
+    __device__ bool match(uint32_t dist, uint32_t len) {
+        if (dist > op || op + len > cap) return false;
+        lz_emit_match<true>(out, op, dist, len, lane);   // syncs the warp first: lane 0's literals are visible
+        op += len;
+        return true;
+    }
+    __device__ bool stored(const uint8_t *src, uint32_t len) {
+        if (op + len > cap) return false;
+        lz_emit_literals<true>(out, op, src, len, lane);
+        op += len;
+        return true;
+    }
+};
+__device__ inline LzWalk gzip_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, InfWork &work, int lane) {
+    LzWalk w{0, false};
+    const uint32_t hl = gzip_header_len(in, n);
+    if (!hl) return w;
+    InfBits s{in + hl, n - hl - 8u, 0u, 0ull, 0, false};
+    InfWarpOut o{out, 0, out_cap, lane};
+    const bool ok = inf_stream(s, o, work, lane);
+    w.out_len = o.op;
+    w.ok = ok && o.op == (uint64_t)gzip_isize(in, n);
+    return w;
+}
+
 // thread per batch: the uncompressed size of a compressed batch's records section → slot[b + 1] = bytes its uncompressed
 // image (header + records, rounded up to 16) needs in the scratch buffer (0 for batches that are not compressed)
 __global__ void log_unc_size_kernel(const uint8_t *bytes, const LogBatchInfo *info, int64_t nbatches, uint64_t *slot, uint32_t *error_flags) {
     for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbatches; b += (int64_t)gridDim.x * blockDim.x) {
         const LogBatchInfo bi = info[b];
         uint64_t need = 0;
-        if (bi.flags == LOGB_LZ4 || bi.flags == LOGB_SNAPPY) {
+        if (bi.flags & LOGB_CODECS) {
             const uint8_t *in = bytes + bi.off + LOG_HEADER_BYTES;
             const uint32_t n = bi.len - LOG_HEADER_BYTES;
-            const LzWalk w = bi.flags == LOGB_LZ4 ? lz4_frame_walk<false>(in, n, nullptr, 0, 0) : snappy_walk<false>(in, n, nullptr, 0, 0);
+            LzWalk w{0, false};
+            if (bi.flags == LOGB_GZIP) {
+                if (gzip_header_len(in, n)) w = LzWalk{gzip_isize(in, n), true};
+            } else w = bi.flags == LOGB_LZ4 ? lz4_frame_walk<false>(in, n, nullptr, 0, 0) : snappy_walk<false>(in, n, nullptr, 0, 0);
             // recordsCount sizes the output columns: it must be plausible for the uncompressed size (7 bytes per record at least)
             if (!w.ok || w.out_len > 0x7fffff00ull || (uint64_t)bi.records * 7u > w.out_len) atomicOr(error_flags, (uint32_t)LOGB_BAD);
             else need = ((uint64_t)LOG_HEADER_BYTES + w.out_len + 15u) & ~15ull;
@@ -295,11 +339,12 @@ __global__ void log_unc_size_kernel(const uint8_t *bytes, const LogBatchInfo *in
 // another place in the same address space) and it is an ordinary LOGB_OK batch for the decoder.
 __global__ void __launch_bounds__(128) log_decompress_kernel(const uint8_t *bytes, LogBatchInfo *info, int64_t nbatches, const uint64_t *slot,
                                                              uint8_t *scratch, uint32_t *error_flags) {
+    __shared__ InfWork inf_work[4];   // Huffman tables of the warp's gzip batch
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, gs = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t b = gw; b < nbatches; b += gs) {
         const LogBatchInfo bi = info[b];
-        if (bi.flags != LOGB_LZ4 && bi.flags != LOGB_SNAPPY) continue;
+        if (!(bi.flags & LOGB_CODECS)) continue;
         const uint64_t need = slot[b + 1] - slot[b];
         uint8_t *dst = scratch + slot[b];
         if (need < (uint64_t)LOG_HEADER_BYTES) {             // the size pass rejected it
@@ -308,8 +353,9 @@ __global__ void __launch_bounds__(128) log_decompress_kernel(const uint8_t *byte
         }
         const uint8_t *src = bytes + bi.off;
         const uint64_t cap = need - LOG_HEADER_BYTES;
-        const LzWalk w = bi.flags == LOGB_LZ4 ? lz4_frame_walk<true>(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, lane)
-                                              : snappy_walk<true>(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, lane);
+        const LzWalk w = bi.flags == LOGB_LZ4    ? lz4_frame_walk<true>(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, lane)
+                         : bi.flags == LOGB_GZIP ? gzip_walk(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, inf_work[threadIdx.x >> 5], lane)
+                                                 : snappy_walk<true>(src + LOG_HEADER_BYTES, bi.len - LOG_HEADER_BYTES, dst + LOG_HEADER_BYTES, cap, lane);
         for (int i = lane; i < LOG_HEADER_BYTES; i += 32) dst[i] = src[i];
         __syncwarp();
         if (lane == 0) {

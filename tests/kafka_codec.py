@@ -44,10 +44,14 @@ def encode_record(offset_delta, ts_delta, key, value_len, headers=()):
 
 
 def compress_records(recs: bytes, codec: str) -> bytes:
-    """The records section as a producer with compression.type=<codec> writes it.  The compressors are pyarrow's (LZ4 frame
-    format, raw Snappy): independent of the GPU decompressor under test.  'snappy-xerial' adds the framing of the Java
+    """The records section as a producer with compression.type=<codec> writes it.  The compressors are zlib's (gzip) and
+    pyarrow's (LZ4 frame format, raw Snappy): independent of the GPU decompressor under test.  'snappy-xerial' adds the framing of the Java
     client's snappy-java stream (magic, two version words, chunks of u32 BE length + raw snappy)."""
     import pyarrow as pa
+    if codec == "gzip":                                  # zlib's gzip wrapper (what librdkafka and the Java client write)
+        import zlib
+        c = zlib.compressobj(6, zlib.DEFLATED, 31)
+        return c.compress(recs) + c.flush()
     if codec == "lz4":
         return pa.compress(recs, codec="lz4", asbytes=True)
     if codec == "snappy":

@@ -98,7 +98,9 @@ def test_compressed_and_malformed_batches_are_rejected():
     good = kc.encode_batch(0, 1000, [(0, 0, b"k", 1)])
     with KtaEngine(1, now=NOW) as e:
         with pytest.raises(KtaError):
-            e.push_log_segment(0, kc.encode_batch(0, 1000, [(0, 0, b"k", 1)], attributes=0x01))   # gzip
+            e.push_log_segment(0, kc.encode_batch(0, 1000, [(0, 0, b"k", 1)], attributes=0x04))   # zstd: no decompressor
+        with pytest.raises(KtaError):
+            e.push_log_segment(0, kc.encode_batch(0, 1000, [(0, 0, b"k", 1)], attributes=0x01))   # "gzip" that is not a gzip member
         bad = bytearray(good)
         bad[16] = 1                                                                              # magic 1
         with pytest.raises(KtaError):
@@ -282,6 +284,9 @@ def test_codec_compression_roundtrips_on_the_host():
     lz = kc.compress_records(recs, "lz4")
     assert lz[:4] == bytes([0x04, 0x22, 0x4D, 0x18]) and len(lz) < len(recs)
     assert pa.decompress(lz, decompressed_size=len(recs), codec="lz4", asbytes=True) == recs
+    gz = kc.compress_records(recs, "gzip")
+    import gzip
+    assert gz[:3] == b"\x1f\x8b\x08" and gzip.decompress(gz) == recs and len(gz) < len(recs)
     sn = kc.compress_records(recs, "snappy")
     assert pa.decompress(sn, decompressed_size=len(recs), codec="snappy", asbytes=True) == recs
     xe = kc.compress_records(recs, "snappy-xerial")
@@ -291,9 +296,9 @@ def test_codec_compression_roundtrips_on_the_host():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("codec", ["lz4", "snappy", "snappy-xerial", "mixed"])
+@pytest.mark.parametrize("codec", ["gzip", "lz4", "snappy", "snappy-xerial", "mixed"])
 def test_compressed_segments_decode_and_scan(codec):
-    """LZ4 (frame) and Snappy (raw / xerial) batches — what producers with compression.type set write and librdkafka
+    """gzip, LZ4 (frame) and Snappy (raw / xerial) batches — what producers with compression.type set write and librdkafka
     decompresses inside poll (src/kafka.rs:93) — are decompressed on the GPU and then give the reference's answer.
     'mixed': every batch picks its own codec, uncompressed ones included, in one segment."""
     rng = np.random.default_rng(11)
@@ -302,7 +307,7 @@ def test_compressed_segments_decode_and_scan(codec):
                            empty_value_per_10k=100, value_mean=120)
     per = _partition_lists(synth.fill_host(spec))
     o = _oracle_over(per, count_alive_keys=True)
-    comp = ["lz4", "snappy", "snappy-xerial", None] if codec == "mixed" else codec
+    comp = ["gzip", "lz4", "snappy", "snappy-xerial", None] if codec == "mixed" else codec
     with KtaEngine(P, count_alive_keys=True, hll_precision=10, now=NOW) as e:
         total = 0
         raw = comp_bytes = 0
@@ -326,17 +331,24 @@ def test_compressed_segments_decode_and_scan(codec):
 def test_corrupt_compressed_batches_are_rejected():
     recs = [(i, i, b"key-%d" % (i % 5), 30) for i in range(50)]
     with KtaEngine(1, now=NOW) as e:
-        for codec in ("lz4", "snappy"):
+        for codec in ("gzip", "lz4", "snappy"):
             good = kc.encode_batch(0, 1000, recs, compression=codec)
             assert e.push_log_segment(0, good) == 50
             bad = bytearray(good)
-            bad[61] ^= 0x15                          # LZ4: the frame magic; Snappy: the uncompressed-length preamble
+            bad[61] ^= 0x15                          # gzip / LZ4: the magic; Snappy: the uncompressed-length preamble
             with pytest.raises(KtaError):
                 e.push_log_segment(0, bytes(bad))
             cut = bytearray(good[:-7])               # shorter section under an adjusted batchLength
             cut[8:12] = (len(cut) - 12).to_bytes(4, "big")
             with pytest.raises(KtaError):
                 e.push_log_segment(0, bytes(cut))
-        for codec in ("gzip", "zstd"):               # no decompressor for these
+        with pytest.raises(KtaError):                # zstd: no decompressor
+            e.push_log_segment(0, kc.encode_batch(0, 1000, recs[:2], attributes=kc.CODEC_BITS["zstd"]))
+        # gzip: damage inside the deflate stream or a wrong ISIZE must be caught, not written past the scratch slot
+        good = kc.encode_batch(0, 1000, recs, compression="gzip")
+        for at, x in ((75, 0xFF), (len(good) - 1, 0x01), (len(good) - 4, 0x40)):
+            bad = bytearray(good)
+            bad[at] ^= x
             with pytest.raises(KtaError):
-                e.push_log_segment(0, kc.encode_batch(0, 1000, recs[:2], attributes=kc.CODEC_BITS[codec]))
+                e.push_log_segment(0, bytes(bad))
+        assert e.push_log_segment(0, good) == 50

@@ -3,12 +3,8 @@ import glob
 from kafka_topic_analyzer_b200 import _native as N
 variants = {
  'base': [],
- 'nohints': ['KTA_L2_HINTS=0'],
- 'stage0': ['KTA_EXP_ALIVE_STAGE=0'],
  'stage1': ['KTA_EXP_ALIVE_STAGE=1'],
- 'noprefetch': ['KTA_EXP_ALIVE_PREFETCH=0'],
- 't768': ['KTA_SCAN_THREADS=768'],
-
+ 'stage3': ['KTA_EXP_ALIVE_STAGE=3'],
 }
 for f in glob.glob(N.LIB_PATH.replace('.so','_exp_*.so')): os.remove(f)
 import concurrent.futures as cf

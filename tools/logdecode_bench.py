@@ -9,7 +9,7 @@ from kafka_topic_analyzer_b200._native import lib, check
 
 P, N, VM = 16, 8_000_000, int(sys.argv[1]) if len(sys.argv) > 1 else 256
 BR = int(sys.argv[2]) if len(sys.argv) > 2 else 56   # ~16 KB batches (the producer default batch.size) at 256 B values
-CODEC = sys.argv[3] if len(sys.argv) > 3 else None   # lz4 | snappy: every batch's records section compressed (pyarrow) on the host
+CODEC = sys.argv[3] if len(sys.argv) > 3 else None   # gzip | lz4 | snappy: every batch's records section compressed (zlib / pyarrow) on the host
 if CODEC:
     N = 2_000_000
 
@@ -21,9 +21,14 @@ def compress_segment(seg: np.ndarray, codec: str) -> np.ndarray:
     while pos + 61 <= len(raw):
         bl = int.from_bytes(raw[pos + 8:pos + 12], "big", signed=True)
         hdr = bytearray(raw[pos:pos + 61])
-        body = pa.compress(raw[pos + 61:pos + 12 + bl], codec=codec, asbytes=True)
+        if codec == "gzip":
+            import zlib
+            c = zlib.compressobj(6, zlib.DEFLATED, 31)
+            body = c.compress(raw[pos + 61:pos + 12 + bl]) + c.flush()
+        else:
+            body = pa.compress(raw[pos + 61:pos + 12 + bl], codec=codec, asbytes=True)
         hdr[8:12] = (49 + len(body)).to_bytes(4, "big")
-        hdr[22] |= {"snappy": 2, "lz4": 3}[codec]
+        hdr[22] |= {"gzip": 1, "snappy": 2, "lz4": 3}[codec]
         out += hdr + body
         pos += 12 + bl
     return np.frombuffer(bytes(out), dtype=np.uint8)
