@@ -13,8 +13,10 @@
 
 #ifdef __CUDA_ARCH__
 #define KTA_INF_SYNC() __syncwarp()
+#define KTA_INF_LANES 32        // table fills are spread over the warp
 #else
 #define KTA_INF_SYNC() ((void)0)
+#define KTA_INF_LANES 1
 #endif
 
 namespace kta {
@@ -42,14 +44,19 @@ __host__ __device__ inline uint32_t inf_bits(InfBits &s, int need) {   // need <
     return v;
 }
 
-// canonical Huffman code: count[l] = codes of length l, symbol[] = the symbols ordered by (length, value)
+// canonical Huffman code: count[l] = codes of length l, symbol[] = the symbols ordered by (length, value);
+// fast[] = direct lookup by the next INF_FAST_BITS bits of the stream for the codes that short: symbol | length << 12,
+// 0 = a longer code (or none): decode bit by bit
+constexpr int INF_FAST_BITS = 9;
 struct InfHuff {
     uint16_t *count;    // [16]
     uint16_t *symbol;
+    uint16_t *fast;     // [1 << INF_FAST_BITS], or nullptr (the code-length code: 19 symbols, used a few dozen times)
 };
 
 struct InfWork {        // per warp, in shared memory on the device
     uint16_t lencnt[16], lensym[288], distcnt[16], distsym[32], lengths[320], offs[16];
+    uint16_t lenfast[1 << INF_FAST_BITS], distfast[1 << INF_FAST_BITS];
 };
 
 // Huffman codes are packed MSB first (RFC 1951 3.1.1): extend the code bit by bit until it falls into the range of codes
@@ -59,6 +66,15 @@ __host__ __device__ inline int inf_decode(InfBits &s, const InfHuff &h) {
     while (s.cnt <= 48 && s.pos < s.n) {
         s.buf |= (uint64_t)s.p[s.pos++] << s.cnt;
         s.cnt += 8;
+    }
+    if (h.fast) {
+        const uint32_t e = h.fast[(uint32_t)s.buf & ((1u << INF_FAST_BITS) - 1u)];
+        const int len = (int)(e >> 12);
+        if (e != 0 && len <= s.cnt) {
+            s.buf >>= len;
+            s.cnt -= len;
+            return (int)(e & 0xfffu);
+        }
     }
     uint32_t bits = (uint32_t)s.buf;
     int code = 0, first = 0, index = 0;
@@ -82,13 +98,18 @@ __host__ __device__ inline int inf_decode(InfBits &s, const InfHuff &h) {
 }
 
 // Build the decoding tables from n code lengths (0 = symbol unused).  Returns 0 for a complete code, > 0 for an
-// incomplete one (codes left over), < 0 for an over-subscribed one.  Tables are written by lane 0 only.
+// incomplete one (codes left over), < 0 for an over-subscribed one.  count / symbol are written by lane 0, the lookup
+// table by all lanes.
 __host__ __device__ inline int inf_construct(InfHuff &h, const uint16_t *length, int n, uint16_t *offs, int lane) {
     if (lane == 0) {
         for (int l = 0; l <= 15; l++) h.count[l] = 0;
         for (int i = 0; i < n; i++) h.count[length[i]]++;
     }
     KTA_INF_SYNC();
+    if (h.fast) {   // no entry of an earlier block's code may survive
+        for (int i = lane; i < (1 << INF_FAST_BITS); i += KTA_INF_LANES) h.fast[i] = 0;
+        KTA_INF_SYNC();
+    }
     if (h.count[0] == n) return 0;   // no codes at all: complete, but decoding anything will fail
     int left = 1;
     for (int l = 1; l <= 15; l++) {
@@ -103,6 +124,26 @@ __host__ __device__ inline int inf_construct(InfHuff &h, const uint16_t *length,
             if (length[i] != 0) h.symbol[offs[length[i]]++] = (uint16_t)i;
     }
     KTA_INF_SYNC();
+    if (h.fast) {
+        // the lookup table: the code of the j-th symbol of length l is first_l + j (canonical order), sent MSB first, so
+        // it occupies the LOW l bits of the look-ahead in reversed order; every setting of the bits above it maps to it
+        int first = 0, index = 0;
+        for (int l = 1; l <= INF_FAST_BITS; l++) {
+            const int count = h.count[l];
+            for (int j = lane; j < count; j += KTA_INF_LANES) {
+                uint32_t code = (uint32_t)(first + j), rev = 0;
+                for (int b = 0; b < l; b++) {
+                    rev = (rev << 1) | (code & 1u);
+                    code >>= 1;
+                }
+                const uint16_t e = (uint16_t)(h.symbol[index + j] | (l << 12));
+                for (uint32_t k = rev; k < (1u << INF_FAST_BITS); k += 1u << l) h.fast[k] = e;
+            }
+            index += count;
+            first = (first + count) << 1;
+        }
+        KTA_INF_SYNC();
+    }
     return left;
 }
 
@@ -145,7 +186,8 @@ __host__ __device__ inline bool inf_codes(InfBits &s, Out &out, const InfHuff &l
 // The deflate stream at s (positioned on its first block header) up to and including the final block.
 template <class Out>
 __host__ __device__ inline bool inf_stream(InfBits &s, Out &out, InfWork &w, int lane) {
-    InfHuff lencode{w.lencnt, w.lensym}, distcode{w.distcnt, w.distsym};
+    InfHuff lencode{w.lencnt, w.lensym, w.lenfast}, distcode{w.distcnt, w.distsym, w.distfast};
+    InfHuff clcode{w.lencnt, w.lensym, nullptr};   // the code-length code borrows the literal code's arrays
     for (;;) {
         const uint32_t last = inf_bits(s, 1), type = inf_bits(s, 2);
         if (s.bad) return false;
@@ -192,14 +234,14 @@ __host__ __device__ inline bool inf_stream(InfBits &s, Out &out, InfWork &w, int
                         for (int i = 0; i < 19; i++) w.lengths[i] = cl[i];
                 }
                 KTA_INF_SYNC();
-                if (inf_construct(lencode, w.lengths, 19, w.offs, lane) != 0) return false;   // the code-length code must be complete
+                if (inf_construct(clcode, w.lengths, 19, w.offs, lane) != 0) return false;   // the code-length code must be complete
                 KTA_INF_SYNC();
                 // the nlen + ndist lengths; they go to a second array (the code-length code's own lengths are still in use
                 // through lencode's tables only, so w.lengths may be overwritten now)
                 int index = 0;
                 uint32_t prev = 0;
                 while (index < nlen + ndist) {
-                    const int sym = inf_decode(s, lencode);
+                    const int sym = inf_decode(s, clcode);
                     if (sym < 0) return false;
                     uint32_t val = 0;
                     int rep = 1;

@@ -49,5 +49,5 @@ cli=kafka_topic_analyzer_b200/csrc/cli/kafka-topic-analyzer
 for feed in push batch device; do for f in "" "-c"; do
   $cli -t bench -b none --synthetic n=40000000,partitions=64,distinct_keys=4000000 --feed $feed $f 2>&1 >/dev/null | grep feed= | sed "s/^/[$f] /" | tee -a $out/${tag}_cli_feeds.log
 done; done
-{ python tools/logdecode_bench.py 256 56; python tools/logdecode_bench.py 1024 14; python tools/logdecode_bench.py 256 56 lz4; python tools/logdecode_bench.py 256 56 snappy; } 2>&1 | grep -E "encoded|decode" | tee $out/${tag}_logdecode_bench.log
+{ python tools/logdecode_bench.py 256 56; python tools/logdecode_bench.py 1024 14; python tools/logdecode_bench.py 256 56 lz4; python tools/logdecode_bench.py 256 56 snappy; python tools/logdecode_bench.py 256 56 gzip; } 2>&1 | grep -E "encoded|decode" | tee $out/${tag}_logdecode_bench.log
 tools/sanitize.sh $tag
