@@ -323,7 +323,9 @@ __global__ void log_unc_size_kernel(const uint8_t *bytes, const LogBatchInfo *in
             const uint32_t n = bi.len - LOG_HEADER_BYTES;
             LzWalk w{0, false};
             if (bi.flags == LOGB_GZIP) {
-                if (gzip_header_len(in, n)) w = LzWalk{gzip_isize(in, n), true};
+                // ISIZE is taken on trust here (the copy pass must then produce exactly that much), but not beyond what
+                // DEFLATE can expand to (1032 : 1): a forged trailer must not size the scratch buffer
+                if (gzip_header_len(in, n) && (uint64_t)gzip_isize(in, n) <= (uint64_t)n * 1032u + 64u) w = LzWalk{gzip_isize(in, n), true};
             } else w = bi.flags == LOGB_LZ4 ? lz4_frame_walk<false>(in, n, nullptr, 0, 0) : snappy_walk<false>(in, n, nullptr, 0, 0);
             // recordsCount sizes the output columns: it must be plausible for the uncompressed size (7 bytes per record at least)
             if (!w.ok || w.out_len > 0x7fffff00ull || (uint64_t)bi.records * 7u > w.out_len) atomicOr(error_flags, (uint32_t)LOGB_BAD);
