@@ -142,13 +142,16 @@ def config_dict(a, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """nvidia-smi clocks + throttle reasons around the timed region.  The poller needs ~0.1 s to come up and samples every
+    20 ms, while 20 steps of a 0.65 ms scan are over in 13 ms: so it is started BEFORE the warm-up steps (same kernels, back
+    to back with the timed ones), the caller waits for its first line, and stop() reports the samples taken from then to the
+    end of the timed region (`samples`) and how many of them fell inside the timed region itself (`samples_in_region`)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.load_from = gpu_index, [], None, None
 
     def start(self):
         try:
@@ -161,24 +164,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=2.0):
+        """blocks until the poller has delivered a line (or `timeout` s); everything from now on counts as under load"""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.005)
+        self.load_from = time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        lo = self.load_from if self.load_from is not None else float("-inf")
+        hi = t1 + 0.025 if t1 is not None else float("inf")      # a sample describes the 20 ms before it
+        rows = [r for (t, r) in list(self.rows) if lo <= t <= hi and len(r) >= 9] or [r for (_, r) in list(self.rows) if len(r) >= 9]
+        inside = sum(1 for (t, r) in list(self.rows) if t0 is not None and t1 is not None and t0 <= t <= t1 + 0.025 and len(r) >= 9)
+        sm = sorted(int(r[1]) for r in rows if r[1].isdigit())
+        mx = [int(r[2]) for r in rows if r[2].isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_region": inside}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -358,20 +370,22 @@ def measure(a, ctx, full):
             allreduce_merge(eng)
         eng.finalize()
 
-    topic_pass(max(1, a.warmup))
-    barrier()
-    eng.set_timing(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()          # the poller is up before the warm-up steps: they and the timed steps are its "under load"
+    topic_pass(max(1, a.warmup))
+    barrier()
+    eng.set_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.perf_counter()
     e0.record(stream)
     topic_pass(a.steps)
     e1.record(stream)
     launches = eng.stats()[0]
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
     ms = e0.elapsed_time(e1)
     kern_ms, kern_n = eng.scan_time_ms()
     eng.set_timing(False)
@@ -476,6 +490,8 @@ def measure(a, ctx, full):
         sampler2 = ClockSampler(local)
         if rank == 0:
             sampler2.start()
+            sampler2.wait_first()
+        barrier()
         e0.record(stream)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -484,7 +500,7 @@ def measure(a, ctx, full):
         barrier()
         wall = time.perf_counter() - t0
         if rank == 0:
-            line["clocks_e2e"] = sampler2.stop()
+            line["clocks_e2e"] = sampler2.stop(t0, t0 + wall)
         t = torch.tensor([max(e0.elapsed_time(e1) / 1e3, wall)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
