@@ -99,7 +99,7 @@ __global__ void log_header_kernel(const uint8_t *bytes, int64_t nbytes, const ui
 
 // unsigned LEB128 at p (bounded by end); returns bytes consumed, 0 on malformed input.  Generic byte loads: the batch may
 // sit in shared memory or in global memory.
-__device__ __forceinline__ int uvarint_g(const uint8_t *p, const uint8_t *end, uint64_t &out) {
+__host__ __device__ __forceinline__ int uvarint_g(const uint8_t *p, const uint8_t *end, uint64_t &out) {
     uint64_t v = 0;
     int shift = 0, n = 0;
     while (p + n < end && n < 10) {
@@ -131,22 +131,24 @@ struct LzWalk {
     bool ok;
 };
 
+// (the walks are __host__ __device__ like kta_inflate.cuh: tests/test_lzwalk_host.py runs them on the host, where the
+// "warp" is one lane; the product calls them on the device only)
 template <bool COPY>
-__device__ __forceinline__ void lz_emit_literals(uint8_t *out, uint64_t op, const uint8_t *in, uint32_t n, int lane) {
-    if (COPY) for (uint32_t i = lane; i < n; i += 32) out[op + i] = in[i];
+__host__ __device__ __forceinline__ void lz_emit_literals(uint8_t *out, uint64_t op, const uint8_t *in, uint32_t n, int lane) {
+    if (COPY) for (uint32_t i = lane; i < n; i += KTA_INF_LANES) out[op + i] = in[i];
 }
 template <bool COPY>
-__device__ __forceinline__ void lz_emit_match(uint8_t *out, uint64_t op, uint32_t offset, uint32_t n, int lane) {
+__host__ __device__ __forceinline__ void lz_emit_match(uint8_t *out, uint64_t op, uint32_t offset, uint32_t n, int lane) {
     if (COPY) {
-        __syncwarp();   // the bytes the match refers to have been written
-        for (uint32_t i = lane; i < n; i += 32) out[op + i] = out[op - offset + (i % offset)];
-        __syncwarp();
+        KTA_INF_SYNC();   // the bytes the match refers to have been written
+        for (uint32_t i = lane; i < n; i += KTA_INF_LANES) out[op + i] = out[op - offset + (i % offset)];
+        KTA_INF_SYNC();
     }
 }
 
 // LZ4 frame at in[0, n).  COPY: the whole warp calls this (lane-uniform control flow: every lane parses the same bytes).
 template <bool COPY>
-__device__ LzWalk lz4_frame_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, int lane) {
+__host__ __device__ LzWalk lz4_frame_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, int lane) {
     LzWalk w{0, false};
     if (n < 7 || in[0] != 0x04 || in[1] != 0x22 || in[2] != 0x4D || in[3] != 0x18) return w;
     const uint32_t flg = in[4];
@@ -202,7 +204,7 @@ __device__ LzWalk lz4_frame_walk(const uint8_t *in, uint32_t n, uint8_t *out, ui
 
 // one raw Snappy block at in[0, n)
 template <bool COPY>
-__device__ bool snappy_raw_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, uint64_t &op, int lane) {
+__host__ __device__ bool snappy_raw_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, uint64_t &op, int lane) {
     uint64_t want;
     const int hn = uvarint_g(in, in + n, want);
     if (hn <= 0) return false;
@@ -253,7 +255,7 @@ __device__ bool snappy_raw_walk(const uint8_t *in, uint32_t n, uint8_t *out, uin
 }
 
 template <bool COPY>
-__device__ LzWalk snappy_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, int lane) {
+__host__ __device__ LzWalk snappy_walk(const uint8_t *in, uint32_t n, uint8_t *out, uint64_t out_cap, int lane) {
     LzWalk w{0, false};
     const bool xerial = n >= 16 && in[0] == 0x82 && in[1] == 'S' && in[2] == 'N' && in[3] == 'A' && in[4] == 'P' && in[5] == 'P' &&
                         in[6] == 'Y' && in[7] == 0;
